@@ -1,0 +1,115 @@
+// C-ABI plumbing: version, error reporting, device checks, tensor-map encoding.
+#include <mutex>
+
+#include "../../include/idb.h"
+#include "idb_host.h"
+
+namespace idb {
+
+static thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+struct DeviceInfo {
+  int major = -1, minor = -1, sms = 0;
+};
+static DeviceInfo g_dev[64];
+static std::mutex g_dev_mu;
+
+static const DeviceInfo* device_info() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DeviceInfo& d = g_dev[dev];
+  if (d.major < 0) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return nullptr;
+    d.major = prop.major;
+    d.minor = prop.minor;
+    d.sms = prop.multiProcessorCount;
+  }
+  return &d;
+}
+
+int require_sm100() {
+  const DeviceInfo* d = device_info();
+  if (d == nullptr) return fail(IDB_E_CUDA, "no CUDA device available (libidb_b200 has no CPU fallback)");
+  if (d->major != 10)
+    return fail(IDB_E_ARCH, "device is sm_" + std::to_string(d->major) + std::to_string(d->minor) +
+                                "; libidb_b200 is built for sm_100a only (no fallback path)");
+  return IDB_OK;
+}
+
+int num_sms() {
+  const DeviceInfo* d = device_info();
+  return d ? d->sms : 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(IDB_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(IDB_E_BADARG, "TMA operand must be 16-byte aligned");
+  cuuint64_t gdims[5];
+  cuuint64_t gstr[4];
+  cuuint32_t gbox[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdims[i] = dims[i];
+    gbox[i] = box[i];
+    estr[i] = 1;
+    if (box[i] == 0 || box[i] > 256) return fail(IDB_E_BADARG, "TMA box dimension out of range");
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    if (gstr[i] % 16) return fail(IDB_E_BADARG, "TMA stride must be a multiple of 16 bytes");
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base), gdims,
+                  gstr, gbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::string d = "cuTensorMapEncodeTiled failed (CUresult " + std::to_string(static_cast<int>(r)) + ") rank " +
+                    std::to_string(rank) + " dims";
+    for (int i = 0; i < rank; ++i) d += " " + std::to_string(dims[i]);
+    d += " box";
+    for (int i = 0; i < rank; ++i) d += " " + std::to_string(box[i]);
+    return fail(IDB_E_CUDA, d);
+  }
+  return IDB_OK;
+}
+
+}  // namespace idb
+
+extern "C" int idb_version(void) { return IDB_VERSION; }
+
+extern "C" int idb_last_error(char* buf, size_t n) {
+  if (buf == nullptr || n == 0) return IDB_E_BADARG;
+  const std::string& s = idb::g_last_error;
+  size_t m = s.size() < n - 1 ? s.size() : n - 1;
+  memcpy(buf, s.data(), m);
+  buf[m] = 0;
+  return IDB_OK;
+}
+
+extern "C" int idb_device_check(void) { return idb::require_sm100(); }
+extern "C" int idb_num_sms(void) { return idb::num_sms(); }

@@ -1,0 +1,532 @@
+// idb_gemm_conv: persistent, warp-specialised tcgen05 implicit-GEMM for sm_100a.
+//
+//   D[M, N] = epilogue( sum_k im2col(A)[M, k] * W[N, k] )          bf16 x bf16 -> fp32 (TMEM)
+//
+// One CTA per SM, 320 threads:
+//   warps 0-7 : epilogue   (TMEM -> registers -> bias / time-emb / LoRA-up / GEGLU / residual -> global)
+//   warp  8   : TMA producer (im2col by signed TMA coordinates over the NHWC image; halo = OOB zero fill)
+//   warp  9   : tcgen05.mma issuer (one elected lane), owns the TMEM allocation
+// Pipelines: STAGES-deep smem ring (full/empty mbarriers) and a double-buffered TMEM
+// accumulator (tmem_full/tmem_empty) so the epilogue of tile i overlaps the mainloop of tile i+1.
+// A tile is 128 output pixels laid out as a (BW x BH x BB) rectangle of the (x, y, image) space,
+// so a 3x3 tap is one 4-D TMA box shifted by (dx-1, dy-1); a stride-2 conv uses a 5-D view
+// [B, H/2, 2, W/2, 2*C] of the same tensor.  A Linear is the 1x1 "image" [1, 1, M, K].
+// A fused rank-r LoRA rides along as 16 extra UMMA N-columns (x A^T kept in TMEM) and is
+// applied as 4-16 FMAs per output in the epilogue -- base weights are never touched.
+#include <string>
+
+#include "../../include/idb.h"
+#include "idb_common.cuh"
+#include "idb_host.h"
+
+namespace idb {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;
+constexpr int TMEM_COLS = 512;
+constexpr int TMEM_BUF_STRIDE = 256;
+
+struct GemmParams {
+  CUtensorMap tmA0, tmA1, tmW, tmL;
+  int mode0, cpb0, c0, nkb0, nkb1;
+  int Ho, Wo, B;
+  int BW, BH, BB;
+  int tiles_x, tiles_y;
+  int n_tiles_m, n_tiles_n, k_splits, kb_per_split;
+  int N, N_out;
+  long long M;
+  const float* bias;
+  const float* rowvec;
+  const float* residual;
+  const float* lora_up;
+  int lora_rank_pad, lora_seg_n;
+  int flags;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  float* workspace;
+};
+
+template <int BLOCK_N, int STAGES, bool LORA>
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
+  constexpr int B_TILE_BYTES = UMMA_N * BLOCK_K * 2;
+  constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+  constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, UMMA_N, 0, 0);
+  static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
+  static_assert(UMMA_N <= TMEM_BUF_STRIDE, "accumulator does not fit its TMEM buffer");
+  static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment for SWIZZLE_128B");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == NUM_EPI_WARPS && lane == 0) {
+    tma_prefetch_desc(&p.tmA0);
+    tma_prefetch_desc(&p.tmW);
+    if (p.nkb1 > 0) tma_prefetch_desc(&p.tmA1);
+    if (LORA) tma_prefetch_desc(&p.tmL);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], NUM_EPI_WARPS);
+    }
+    mbar_fence_init();
+  }
+  if (warp == NUM_EPI_WARPS + 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.n_tiles_m * p.n_tiles_n * p.k_splits;
+  const int nkb_total = p.nkb0 + p.nkb1;
+
+  if (warp == NUM_EPI_WARPS) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int t = tile;
+        const int n_blk = t % p.n_tiles_n;
+        t /= p.n_tiles_n;
+        const int ks = t % p.k_splits;
+        const int m_blk = t / p.k_splits;
+        const int tx = m_blk % p.tiles_x;
+        const int ty = (m_blk / p.tiles_x) % p.tiles_y;
+        const int tb = m_blk / (p.tiles_x * p.tiles_y);
+        const int x0 = tx * p.BW, y0 = ty * p.BH, b0 = tb * p.BB;
+        const int n0 = n_blk * BLOCK_N;
+        const int kb_begin = ks * p.kb_per_split;
+        const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_TILE_BYTES;
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if (kb < p.nkb0) {
+            const int tap = kb / p.cpb0;
+            const int cb = (kb - tap * p.cpb0) * BLOCK_K;
+            if (p.mode0 == IDB_A_1X1) {
+              tma_load_4d(sa, &p.tmA0, &full_bar[stage], cb, x0, y0, b0);
+            } else {
+              const int dy = tap / 3, dx = tap - dy * 3;
+              if (p.mode0 == IDB_A_3X3) {
+                tma_load_4d(sa, &p.tmA0, &full_bar[stage], cb, x0 + dx - 1, y0 + dy - 1, b0);
+              } else {  // stride 2: input (2*yo + dy - 1, 2*xo + dx - 1) in the [B, H/2, 2, W/2, 2C] view
+                const int px = (dx == 1) ? 0 : 1, py = (dy == 1) ? 0 : 1;
+                const int ox = (dx == 0) ? -1 : 0, oy = (dy == 0) ? -1 : 0;
+                tma_load_5d(sa, &p.tmA0, &full_bar[stage], px * p.c0 + cb, x0 + ox, py, y0 + oy, b0);
+              }
+            }
+          } else {
+            tma_load_4d(sa, &p.tmA1, &full_bar[stage], (kb - p.nkb0) * BLOCK_K, x0, y0, b0);
+          }
+          tma_load_2d(sb, &p.tmW, &full_bar[stage], kb * BLOCK_K, n0);
+          if (LORA) {
+            const int seg = n0 / p.lora_seg_n;
+            tma_load_2d(sb + BLOCK_N * BLOCK_K * 2, &p.tmL, &full_bar[stage], kb * BLOCK_K, seg * 16);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == NUM_EPI_WARPS + 1) {
+    // ================================================================ MMA issuer
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int ks = (tile / p.n_tiles_n) % p.k_splits;
+      const int kb_begin = ks * p.kb_per_split;
+      const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
+      const int buf = it & 1;
+      mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * TMEM_BUF_STRIDE;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {  // a single fixed thread issues every MMA and commit of this CTA
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = umma_smem_desc_sw128(sa);
+          const uint64_t bdesc = umma_smem_desc_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // +32 bytes (>>4 = 2) per UMMA_K=16 step inside the 128B swizzle atom
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (kb == kb_end - 1) umma_commit(&tmem_full[buf]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ================================================================ epilogue warps
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int half = warp >> 2;    // which interleaved set of 32-column chunks
+    const int r = quarter * 32 + lane;
+    const int rx = r % p.BW;
+    const int ry = (r / p.BW) % p.BH;
+    const int rb = r / (p.BW * p.BH);
+    const bool geglu = (p.flags & IDB_EPI_GEGLU) != 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      int t = tile;
+      const int n_blk = t % p.n_tiles_n;
+      t /= p.n_tiles_n;
+      const int ks = t % p.k_splits;
+      const int m_blk = t / p.k_splits;
+      const int tx = m_blk % p.tiles_x;
+      const int ty = (m_blk / p.tiles_x) % p.tiles_y;
+      const int tb = m_blk / (p.tiles_x * p.tiles_y);
+      const int x = tx * p.BW + rx, y = ty * p.BH + ry, b = tb * p.BB + rb;
+      const bool row_ok = (x < p.Wo) && (y < p.Ho) && (b < p.B);
+      const long long orow = (static_cast<long long>(b) * p.Ho + y) * p.Wo + x;
+      const int n0 = n_blk * BLOCK_N;
+      const int buf = it & 1;
+
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * TMEM_BUF_STRIDE;
+
+      float lt[16];
+      if (LORA) {
+        uint32_t lv[16];
+        IDB_TMEM_LD_X16(t_row + BLOCK_N, lv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) lt[j] = __uint_as_float(lv[j]);
+      }
+
+      for (int chunk = half; chunk < BLOCK_N / 32; chunk += 2) {
+        const int col = n0 + chunk * 32;
+        uint32_t v[32];
+        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-row predicated body
+        IDB_TMEM_LD_X32(t_row + chunk * 32, v);
+        tmem_ld_wait();
+        if (row_ok && col < p.N) {
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+
+        if (p.k_splits > 1) {  // raw partial sums; the finalize kernel applies the epilogue
+          float4* dst = reinterpret_cast<float4*>(p.workspace + (static_cast<long long>(ks) * p.M + orow) * p.N + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        } else {
+        if (p.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bv = __ldg(bp + j);
+            acc[4 * j] += bv.x, acc[4 * j + 1] += bv.y, acc[4 * j + 2] += bv.z, acc[4 * j + 3] += bv.w;
+          }
+        }
+        if (p.rowvec != nullptr) {
+          const float4* rp = reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(b) * p.N + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 rv = __ldg(rp + j);
+            acc[4 * j] += rv.x, acc[4 * j + 1] += rv.y, acc[4 * j + 2] += rv.z, acc[4 * j + 3] += rv.w;
+          }
+        }
+        if (LORA) {
+          const float* up = p.lora_up + static_cast<long long>(col) * p.lora_rank_pad;
+          for (int r4 = 0; r4 < p.lora_rank_pad; r4 += 4) {
+            // lt[] index must be compile-time to stay in registers: unrolled select over r4
+            float t0, t1, t2, t3;
+            if (r4 == 0) t0 = lt[0], t1 = lt[1], t2 = lt[2], t3 = lt[3];
+            else if (r4 == 4) t0 = lt[4], t1 = lt[5], t2 = lt[6], t3 = lt[7];
+            else if (r4 == 8) t0 = lt[8], t1 = lt[9], t2 = lt[10], t3 = lt[11];
+            else t0 = lt[12], t1 = lt[13], t2 = lt[14], t3 = lt[15];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float4 u = __ldg(reinterpret_cast<const float4*>(up + j * p.lora_rank_pad + r4));
+              acc[j] += t0 * u.x + t1 * u.y + t2 * u.z + t3 * u.w;
+            }
+          }
+        }
+        if (geglu) {
+          // chunk = [a(16) | g(16)] -> 16 outputs at column col/2
+          const int ocol = col >> 1;
+          float o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j] = acc[j] * gelu_erf_f(acc[16 + j]);
+          if (p.residual != nullptr) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + orow * p.N_out + ocol);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 rv = __ldg(rp + j);
+              o[4 * j] += rv.x, o[4 * j + 1] += rv.y, o[4 * j + 2] += rv.z, o[4 * j + 3] += rv.w;
+            }
+          }
+          if (p.out_f32 != nullptr) {
+            float4* dst = reinterpret_cast<float4*>(p.out_f32 + orow * p.N_out + ocol);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          if (p.out_bf16 != nullptr) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + orow * p.N_out + ocol);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              dst[j] = make_uint4(pack_bf16x2(o[8 * j], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
+                                  pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
+          }
+        } else {
+          if (p.residual != nullptr) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + orow * p.N_out + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 rv = __ldg(rp + j);
+              acc[4 * j] += rv.x, acc[4 * j + 1] += rv.y, acc[4 * j + 2] += rv.z, acc[4 * j + 3] += rv.w;
+            }
+          }
+          if (p.out_f32 != nullptr) {
+            float4* dst = reinterpret_cast<float4*>(p.out_f32 + orow * p.N_out + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          }
+          if (p.out_bf16 != nullptr) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + orow * p.N_out + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              dst[j] = make_uint4(pack_bf16x2(acc[8 * j], acc[8 * j + 1]), pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]),
+                                  pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]), pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]));
+          }
+        }
+        }  // !split-K
+        }  // row_ok
+      }
+      // this warp is done reading the accumulator buffer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == NUM_EPI_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------- split-K finalize
+__global__ void splitk_finalize_kernel(const float* __restrict__ ws, int k_splits, long long M, int N, int hw,
+                                       const float* __restrict__ bias, const float* __restrict__ rowvec,
+                                       const float* __restrict__ residual, float* __restrict__ out_f32,
+                                       __nv_bfloat16* __restrict__ out_bf16) {
+  const long long total4 = M * N / 4;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long e = i * 4;
+    const long long row = e / N;
+    const int col = static_cast<int>(e - row * N);
+    float4 a = *reinterpret_cast<const float4*>(ws + e);
+    for (int s = 1; s < k_splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + static_cast<long long>(s) * M * N + e);
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    if (bias) {
+      const float4 v = *reinterpret_cast<const float4*>(bias + col);
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    if (rowvec) {
+      const float4 v = *reinterpret_cast<const float4*>(rowvec + (row / hw) * N + col);
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    if (residual) {
+      const float4 v = *reinterpret_cast<const float4*>(residual + e);
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + e) = a;
+    if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + e) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+  }
+}
+
+// ---------------------------------------------------------------------------------------- host side
+static int pow2_divisor(int v, int cap) {
+  int d = 1;
+  while (d * 2 <= cap && v % (d * 2) == 0) d *= 2;
+  return d;
+}
+
+template <int BLOCK_N, int STAGES, bool LORA>
+static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
+  constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
+  constexpr int smem_bytes = STAGES * (A_TILE_BYTES + UMMA_N * BLOCK_K * 2) + 1024 + 256;
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES, LORA>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    configured = true;
+  }
+  gemm_tc_kernel<BLOCK_N, STAGES, LORA><<<grid, NUM_THREADS, smem_bytes, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("gemm_tc launch: ") + cudaGetErrorString(e));
+  return IDB_OK;
+}
+
+}  // namespace idb
+
+using namespace idb;
+
+extern "C" size_t idb_gemm_conv_workspace_bytes(int64_t m, int64_t n, int32_t k_splits) {
+  return k_splits > 1 ? static_cast<size_t>(m) * n * k_splits * sizeof(float) : 0;
+}
+
+extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (a == nullptr) return fail(IDB_E_BADARG, "idb_gemm_conv: null args");
+  if (int rc = require_sm100()) return rc;
+  if (!a->a0 || !a->w) return fail(IDB_E_BADARG, "idb_gemm_conv: null operand");
+  if (a->c0 <= 0 || a->c0 % 64) return fail(IDB_E_BADARG, "idb_gemm_conv: C0 must be a positive multiple of 64");
+  if (a->a1 && (a->c1 <= 0 || a->c1 % 64)) return fail(IDB_E_BADARG, "idb_gemm_conv: C1 must be a multiple of 64");
+  if (a->n <= 0 || a->n % 32) return fail(IDB_E_BADARG, "idb_gemm_conv: N must be a positive multiple of 32");
+  if (a->batch <= 0 || a->height <= 0 || a->width <= 0) return fail(IDB_E_BADARG, "idb_gemm_conv: bad geometry");
+  if (a->a0_mode < IDB_A_1X1 || a->a0_mode > IDB_A_3X3_S2) return fail(IDB_E_BADARG, "idb_gemm_conv: bad a0_mode");
+  if (a->a0_mode == IDB_A_3X3_S2 && ((a->height | a->width) & 1))
+    return fail(IDB_E_BADARG, "idb_gemm_conv: stride-2 conv needs even H and W");
+  if (!a->out_f32 && !a->out_bf16) return fail(IDB_E_BADARG, "idb_gemm_conv: no output");
+  const bool lora = a->lora_down != nullptr;
+  const bool geglu = (a->flags & IDB_EPI_GEGLU) != 0;
+  if (lora && (!a->lora_up || a->lora_rank_pad <= 0 || a->lora_rank_pad > 16 || a->lora_rank_pad % 4 ||
+               a->lora_seg_n <= 0 || a->lora_seg_n % 160 || a->n % a->lora_seg_n))
+    return fail(IDB_E_BADARG, "idb_gemm_conv: bad LoRA arguments (rank_pad in {4,8,12,16}, seg_n % 160 == 0)");
+  if (lora && (geglu || a->a1)) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: LoRA with GEGLU / second segment");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  const int taps0 = (a->a0_mode == IDB_A_1X1) ? 1 : 9;
+  const int H = a->height, W = a->width, B = a->batch;
+  p.mode0 = a->a0_mode;
+  p.c0 = a->c0;
+  p.cpb0 = a->c0 / 64;
+  p.nkb0 = taps0 * p.cpb0;
+  p.nkb1 = a->a1 ? a->c1 / 64 : 0;
+  p.Ho = (a->a0_mode == IDB_A_3X3_S2) ? H / 2 : H;
+  p.Wo = (a->a0_mode == IDB_A_3X3_S2) ? W / 2 : W;
+  p.B = B;
+  p.M = static_cast<long long>(B) * p.Ho * p.Wo;
+  p.N = a->n;
+  p.N_out = geglu ? a->n / 2 : a->n;
+  const long long k_total = static_cast<long long>(p.nkb0 + p.nkb1) * 64;
+
+  // tile rectangle: 128 output pixels = BW x BH x BB
+  p.BW = pow2_divisor(p.Wo, 128);
+  if (p.Ho == 1 && B == 1) p.BW = 128;  // a Linear: rows are just rows; OOB handles the tail
+  p.BH = pow2_divisor(p.Ho, 128 / p.BW);
+  p.BB = 128 / (p.BW * p.BH);
+  p.tiles_x = (p.Wo + p.BW - 1) / p.BW;
+  p.tiles_y = (p.Ho + p.BH - 1) / p.BH;
+  const int tiles_b = (B + p.BB - 1) / p.BB;
+  p.n_tiles_m = p.tiles_x * p.tiles_y * tiles_b;
+
+  // N tile
+  int block_n;
+  if (lora) block_n = 160;
+  else if (a->n % 256 == 0) block_n = 256;
+  else if (a->n % 160 == 0) block_n = 160;
+  else if (a->n % 128 == 0) block_n = 128;
+  else block_n = (a->n > 160) ? 256 : (a->n > 128 ? 160 : 128);
+  if (geglu && block_n % 32) return fail(IDB_E_BADARG, "idb_gemm_conv: GEGLU tile");
+  p.n_tiles_n = (a->n + block_n - 1) / block_n;
+
+  const int nkb = p.nkb0 + p.nkb1;
+  int ksp = a->k_splits > 1 ? a->k_splits : 1;
+  if (ksp > 1 && (lora || geglu)) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: split-K with LoRA / GEGLU");
+  if (ksp > nkb) ksp = nkb;
+  p.kb_per_split = (nkb + ksp - 1) / ksp;
+  p.k_splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;
+  if (p.k_splits > 1 && !a->workspace) return fail(IDB_E_BADARG, "idb_gemm_conv: split-K needs a workspace");
+
+  p.bias = a->bias;
+  p.rowvec = a->rowvec;
+  p.residual = a->residual;
+  p.lora_up = a->lora_up;
+  p.lora_rank_pad = a->lora_rank_pad;
+  p.lora_seg_n = lora ? a->lora_seg_n : 1;
+  p.flags = a->flags;
+  p.out_f32 = a->out_f32;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
+  p.workspace = a->workspace;
+
+  // ---- tensor maps
+  if (a->a0_mode == IDB_A_3X3_S2) {
+    const uint64_t C = a->c0;
+    uint64_t dims[5] = {2 * C, uint64_t(W / 2), 2, uint64_t(H / 2), uint64_t(B)};
+    uint64_t strides[4] = {2 * C * 2, uint64_t(W) * C * 2, 2 * uint64_t(W) * C * 2, uint64_t(H) * W * C * 2};
+    uint32_t box[5] = {64, uint32_t(p.BW), 1, uint32_t(p.BH), uint32_t(p.BB)};
+    if (int rc = make_tmap_bf16(&p.tmA0, a->a0, 5, dims, strides, box)) return rc;
+  } else {
+    const uint64_t C = a->c0;
+    uint64_t dims[4] = {C, uint64_t(W), uint64_t(H), uint64_t(B)};
+    uint64_t strides[3] = {C * 2, uint64_t(W) * C * 2, uint64_t(H) * W * C * 2};
+    uint32_t box[4] = {64, uint32_t(p.BW), uint32_t(p.BH), uint32_t(p.BB)};
+    if (int rc = make_tmap_bf16(&p.tmA0, a->a0, 4, dims, strides, box)) return rc;
+  }
+  if (a->a1) {
+    const uint64_t C = a->c1;
+    uint64_t dims[4] = {C, uint64_t(p.Wo), uint64_t(p.Ho), uint64_t(B)};
+    uint64_t strides[3] = {C * 2, uint64_t(p.Wo) * C * 2, uint64_t(p.Ho) * p.Wo * C * 2};
+    uint32_t box[4] = {64, uint32_t(p.BW), uint32_t(p.BH), uint32_t(p.BB)};
+    if (int rc = make_tmap_bf16(&p.tmA1, a->a1, 4, dims, strides, box)) return rc;
+  }
+  {
+    uint64_t dims[2] = {uint64_t(k_total), uint64_t(a->n)};
+    uint64_t strides[1] = {uint64_t(k_total) * 2};
+    uint32_t box[2] = {64, uint32_t(block_n)};
+    if (int rc = make_tmap_bf16(&p.tmW, a->w, 2, dims, strides, box)) return rc;
+  }
+  if (lora) {
+    const int nseg = a->n / a->lora_seg_n;
+    uint64_t dims[2] = {uint64_t(k_total), uint64_t(nseg * 16)};
+    uint64_t strides[1] = {uint64_t(k_total) * 2};
+    uint32_t box[2] = {64, 16};
+    if (int rc = make_tmap_bf16(&p.tmL, a->lora_down, 2, dims, strides, box)) return rc;
+  }
+
+  const int total_tiles = p.n_tiles_m * p.n_tiles_n * p.k_splits;
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  int rc;
+  if (lora) rc = launch_gemm<160, 5, true>(p, grid, stream);
+  else if (block_n == 256) rc = launch_gemm<256, 4, false>(p, grid, stream);
+  else if (block_n == 160) rc = launch_gemm<160, 6, false>(p, grid, stream);
+  else rc = launch_gemm<128, 6, false>(p, grid, stream);
+  if (rc) return rc;
+
+  if (p.k_splits > 1) {
+    const long long total4 = p.M * p.N / 4;
+    int blocks = static_cast<int>((total4 + 255) / 256);
+    if (blocks > num_sms() * 8) blocks = num_sms() * 8;
+    splitk_finalize_kernel<<<blocks, 256, 0, stream>>>(p.workspace, p.k_splits, p.M, p.N, p.Ho * p.Wo, p.bias, p.rowvec,
+                                                       p.residual, p.out_f32, p.out_bf16);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("splitk_finalize launch: ") + cudaGetErrorString(e));
+  }
+  return IDB_OK;
+}

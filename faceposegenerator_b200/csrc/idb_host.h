@@ -1,0 +1,23 @@
+// Host-side helpers shared by the C-ABI translation units: thread-local error
+// message, device checks, and TMA tensor-map encoding through the driver entry
+// point (no link-time dependency on libcuda).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstring>
+#include <string>
+
+namespace idb {
+
+int fail(int code, const std::string& msg);  // records msg for idb_last_error(), returns code
+int require_sm100();                         // IDB_OK or IDB_E_ARCH
+int num_sms();
+
+// rank-D bf16 tensor map, SWIZZLE_128B, zero OOB fill.  dims/box innermost first;
+// strides_bytes has rank-1 entries (stride of dims[1..]).
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+}  // namespace idb

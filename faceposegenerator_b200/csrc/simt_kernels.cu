@@ -1,0 +1,605 @@
+// Bandwidth-bound SIMT kernels of the hot path: GroupNorm(+SiLU), LayerNorm, row softmax,
+// time embedding, edge convolutions (tiny Cin / tiny Cout), nearest-2x upsample, casts and the
+// fused CFG + DDPMScheduler.step.  All vectorised (16 B per thread per access where the layout
+// allows), coalesced along the NHWC channel axis, fp32 math.
+#include <string>
+
+#include "../../include/idb.h"
+#include "idb_common.cuh"
+#include "idb_host.h"
+
+namespace idb {
+
+#define IDB_CHECK_LAUNCH(name)                                                                \
+  do {                                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess) return fail(IDB_E_CUDA, std::string(name " launch: ") + cudaGetErrorString(e__)); \
+  } while (0)
+
+constexpr int GN_MAX_CHUNKS = 256;
+constexpr int GN_MAX_GROUPS = 64;
+
+// ---------------------------------------------------------------------------------------- GroupNorm
+struct GnParams {
+  const float* x0;
+  const float* x1;
+  int c0, c1, C, CQ, PY;
+  int hw, groups, cpg, nchunks, pix_per_chunk;
+  float eps;
+  const float* gamma;
+  const float* beta;
+  int silu;
+  __nv_bfloat16* out_norm;
+  __nv_bfloat16* out_raw;
+  float* partials;  // [B, nchunks, groups, 2]
+};
+
+__device__ __forceinline__ float4 gn_load(const GnParams& p, int b, int pix, int cq) {
+  const int c = cq * 4;
+  if (c < p.c0) return *reinterpret_cast<const float4*>(p.x0 + (static_cast<long long>(b) * p.hw + pix) * p.c0 + c);
+  return *reinterpret_cast<const float4*>(p.x1 + (static_cast<long long>(b) * p.hw + pix) * p.c1 + (c - p.c0));
+}
+
+__global__ void gn_stats_kernel(const GnParams p) {
+  __shared__ float gs[GN_MAX_GROUPS], gss[GN_MAX_GROUPS];
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  const int cq = threadIdx.x % p.CQ, py = threadIdx.x / p.CQ;
+  if (threadIdx.x < GN_MAX_GROUPS) gs[threadIdx.x] = 0.f, gss[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int pbeg = chunk * p.pix_per_chunk;
+  const int pend = min(p.hw, pbeg + p.pix_per_chunk);
+  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  if (py < p.PY) {
+    for (int pix = pbeg + py; pix < pend; pix += p.PY) {
+      const float4 v = gn_load(p, b, pix, cq);
+      s[0] += v.x, s[1] += v.y, s[2] += v.z, s[3] += v.w;
+      ss[0] += v.x * v.x, ss[1] += v.y * v.y, ss[2] += v.z * v.z, ss[3] += v.w * v.w;
+    }
+    const int c = cq * 4;
+    const int g0 = c / p.cpg, g3 = (c + 3) / p.cpg;
+    if (g0 == g3) {
+      atomicAdd(&gs[g0], (s[0] + s[1]) + (s[2] + s[3]));
+      atomicAdd(&gss[g0], (ss[0] + ss[1]) + (ss[2] + ss[3]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int g = (c + i) / p.cpg;
+        atomicAdd(&gs[g], s[i]);
+        atomicAdd(&gss[g], ss[i]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < p.groups) {
+    float* dst = p.partials + ((static_cast<long long>(b) * p.nchunks + chunk) * p.groups + threadIdx.x) * 2;
+    dst[0] = gs[threadIdx.x];
+    dst[1] = gss[threadIdx.x];
+  }
+}
+
+__global__ void gn_apply_kernel(const GnParams p) {
+  __shared__ float g_mean[GN_MAX_GROUPS], g_rstd[GN_MAX_GROUPS];
+  const int chunk = blockIdx.x, b = blockIdx.y;
+  if (threadIdx.x < p.groups) {
+    double s = 0.0, ss = 0.0;
+    const float* src = p.partials + (static_cast<long long>(b) * p.nchunks * p.groups + threadIdx.x) * 2;
+    for (int i = 0; i < p.nchunks; ++i) {
+      s += src[static_cast<long long>(i) * p.groups * 2];
+      ss += src[static_cast<long long>(i) * p.groups * 2 + 1];
+    }
+    const double n = static_cast<double>(p.hw) * p.cpg;
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    g_mean[threadIdx.x] = static_cast<float>(mean);
+    g_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+  }
+  __syncthreads();
+  const int cq = threadIdx.x % p.CQ, py = threadIdx.x / p.CQ;
+  if (py >= p.PY) return;
+  const int c = cq * 4;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int g = (c + i) / p.cpg;
+    const float ga = p.gamma[c + i] * g_rstd[g];
+    sc[i] = ga;
+    sh[i] = p.beta[c + i] - g_mean[g] * ga;
+  }
+  const int pbeg = chunk * p.pix_per_chunk;
+  const int pend = min(p.hw, pbeg + p.pix_per_chunk);
+  for (int pix = pbeg + py; pix < pend; pix += p.PY) {
+    const float4 v = gn_load(p, b, pix, cq);
+    float y[4] = {v.x * sc[0] + sh[0], v.y * sc[1] + sh[1], v.z * sc[2] + sh[2], v.w * sc[3] + sh[3]};
+    if (p.silu) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] = silu_f(y[i]);
+    }
+    const long long o = (static_cast<long long>(b) * p.hw + pix) * p.C + c;
+    *reinterpret_cast<uint2*>(p.out_norm + o) = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
+    if (p.out_raw) *reinterpret_cast<uint2*>(p.out_raw + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// ---------------------------------------------------------------------------------------- LayerNorm (warp per row)
+template <int MAXQ>
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, long long rows, int C,
+                                 float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nq = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * C);
+  float4 v[MAXQ];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    const int q = lane + i * 32;
+    if (q < nq) {
+      v[i] = xr[q];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    const int q = lane + i * 32;
+    if (q < nq) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      ss += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / C + eps);
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
+  uint2* orow = reinterpret_cast<uint2*>(out + row * C);
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    const int q = lane + i * 32;
+    if (q < nq) {
+      const float4 g = __ldg(g4 + q), bb = __ldg(b4 + q);
+      const float y0 = (v[i].x - mean) * rstd * g.x + bb.x, y1 = (v[i].y - mean) * rstd * g.y + bb.y;
+      const float y2 = (v[i].z - mean) * rstd * g.z + bb.z, y3 = (v[i].w - mean) * rstd * g.w + bb.w;
+      orow[q] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- row softmax (VAE attention)
+__global__ void softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int cols, float scale) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const float* sr = s + row * cols;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (int i = tid * 4; i < cols; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(sr + i);
+    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int i = 1; i < nw; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  const float c = scale * 1.4426950408889634f;
+  float sum = 0.f;
+  for (int i = tid * 4; i < cols; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(sr + i);
+    sum += (exp2f((v.x - m) * c) + exp2f((v.y - m) * c)) + (exp2f((v.z - m) * c) + exp2f((v.w - m) * c));
+  }
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < nw; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int i = tid * 4; i < cols; i += blockDim.x * 4) {
+    const float4 v = *reinterpret_cast<const float4*>(sr + i);
+    *reinterpret_cast<uint2*>(p + row * cols + i) =
+        make_uint2(pack_bf16x2(exp2f((v.x - m) * c) * inv, exp2f((v.y - m) * c) * inv),
+                   pack_bf16x2(exp2f((v.z - m) * c) * inv, exp2f((v.w - m) * c) * inv));
+  }
+}
+
+// ---------------------------------------------------------------------------------------- time embedding
+__global__ void sinusoid_kernel(const float* __restrict__ t, float* __restrict__ out, int batch, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= batch * half) return;
+  const int b = i / half, k = i % half;
+  const float f = expf(-logf(10000.0f) * static_cast<float>(k) / static_cast<float>(half));
+  const float a = t[b] * f;
+  out[b * dim + k] = cosf(a);  // flip_sin_to_cos: [cos | sin]
+  out[b * dim + half + k] = sinf(a);
+}
+
+// y[b, n] = act(sum_k x[b,k] W[n,k] + bias[n]); one warp per output feature, fp32 weights read once.
+__global__ void skinny_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                     const float* __restrict__ bias, float* __restrict__ y, int batch, int K, int N,
+                                     int silu_out) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const float4* wr = reinterpret_cast<const float4*>(w + static_cast<long long>(n) * K);
+  for (int b0 = 0; b0 < batch; b0 += 8) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int nb = min(8, batch - b0);
+    for (int q = lane; q < K / 4; q += 32) {
+      const float4 wv = __ldg(wr + q);
+#pragma unroll
+      for (int bb = 0; bb < 8; ++bb) {
+        if (bb < nb) {
+          const float4 xv = *reinterpret_cast<const float4*>(x + static_cast<long long>(b0 + bb) * K + q * 4);
+          acc[bb] += (wv.x * xv.x + wv.y * xv.y) + (wv.z * xv.z + wv.w * xv.w);
+        }
+      }
+    }
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb) {
+      float a = acc[bb];
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (lane == 0 && bb < nb) {
+        a += bias ? bias[n] : 0.f;
+        y[static_cast<long long>(b0 + bb) * N + n] = silu_out ? silu_f(a) : a;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- edge convolutions
+// conv3x3 pad 1, tiny Cin: thread = (pixel, 4 output channels), patch held in registers.
+template <int CIN>
+__global__ void conv_small_cin_kernel(const float* __restrict__ x, int x_nchw, const float* __restrict__ w,
+                                      const float* __restrict__ bias, float* __restrict__ out_f32,
+                                      __nv_bfloat16* __restrict__ out_bf16, int B, int H, int W, int Cout) {
+  const int cq_n = Cout / 4;
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long total = static_cast<long long>(B) * H * W * cq_n;
+  if (idx >= total) return;
+  const int cq = static_cast<int>(idx % cq_n);
+  const long long pix = idx / cq_n;
+  const int xw = static_cast<int>(pix % W);
+  const int yh = static_cast<int>((pix / W) % H);
+  const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  float patch[9 * CIN];
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      const int yy = yh + dy - 1, xx = xw + dx - 1;
+      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        float v = 0.f;
+        if (ok)
+          v = x_nchw ? x[((static_cast<long long>(b) * CIN + c) * H + yy) * W + xx]
+                     : x[((static_cast<long long>(b) * H + yy) * W + xx) * CIN + c];
+        patch[(dy * 3 + dx) * CIN + c] = v;
+      }
+    }
+  float o[4];
+#pragma unroll
+  for (int oc = 0; oc < 4; ++oc) {
+    const int co = cq * 4 + oc;
+    const float* wr = w + static_cast<long long>(co) * 9 * CIN;
+    float a = bias ? bias[co] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 9 * CIN; ++i) a += patch[i] * __ldg(wr + i);
+    o[oc] = a;
+  }
+  const long long off = pix * Cout + cq * 4;
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
+  if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + off) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+}
+
+// conv3x3 pad 1, tiny Cout: one warp per output pixel, lanes stride the channel axis (8 B loads).
+template <int COUT>
+__global__ void conv_small_cout_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                       const float* __restrict__ bias, float* __restrict__ out, int postprocess, int B,
+                                       int H, int W, int Cin) {
+  extern __shared__ float sw[];  // [COUT][9][Cin]
+  for (int i = threadIdx.x; i < COUT * 9 * Cin; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long pix = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long npix = static_cast<long long>(B) * H * W;
+  if (pix >= npix) return;
+  const int xw = static_cast<int>(pix % W);
+  const int yh = static_cast<int>((pix / W) % H);
+  const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+  for (int tap = 0; tap < 9; ++tap) {
+    const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+    const __nv_bfloat16* xr = x + ((static_cast<long long>(b) * H + yy) * W + xx) * Cin;
+    for (int c = lane * 4; c < Cin; c += 128) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(xr + c);
+      const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+      const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+      const float v0 = __low2float(p0), v1 = __high2float(p0), v2 = __low2float(p1), v3 = __high2float(p1);
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const float4 wv = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * Cin + c);
+        acc[o] += (v0 * wv.x + v1 * wv.y) + (v2 * wv.z + v3 * wv.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < COUT; ++o)
+    for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+  if (lane == 0) {
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+      float v = acc[o] + (bias ? bias[o] : 0.f);
+      if (postprocess) {
+        v = fminf(fmaxf(v * 0.5f + 0.5f, 0.f), 1.f);
+        out[pix * COUT + o] = v;  // NHWC image
+      } else {
+        out[((static_cast<long long>(b) * COUT + o) * H + yh) * W + xw] = v;  // NCHW
+      }
+    }
+  }
+}
+
+__global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W,
+                                  int C) {
+  const int cq_n = C / 4;
+  const long long total = static_cast<long long>(B) * 2 * H * 2 * W * cq_n;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cq = static_cast<int>(idx % cq_n);
+    long long pix = idx / cq_n;
+    const int xo = static_cast<int>(pix % (2 * W));
+    pix /= 2 * W;
+    const int yo = static_cast<int>(pix % (2 * H));
+    const int b = static_cast<int>(pix / (2 * H));
+    const float4 v = *reinterpret_cast<const float4*>(x + ((static_cast<long long>(b) * H + (yo >> 1)) * W + (xo >> 1)) * C + cq * 4);
+    *reinterpret_cast<uint2*>(out + idx * 4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+__global__ void vae_latent_prep_kernel(const float* __restrict__ z, const float* __restrict__ w,
+                                       const float* __restrict__ bias, float inv_scaling, float* __restrict__ out, int B,
+                                       int hw) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(B) * hw) return;
+  const int b = static_cast<int>(i / hw), pix = static_cast<int>(i % hw);
+  float v[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) v[c] = z[(static_cast<long long>(b) * 4 + c) * hw + pix] * inv_scaling;
+  float o[4];
+#pragma unroll
+  for (int oc = 0; oc < 4; ++oc) {
+    float a = bias[oc];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) a += w[oc * 4 + c] * v[c];
+    o[oc] = a;
+  }
+  *reinterpret_cast<float4*>(out + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// ---------------------------------------------------------------------------------------- CFG + DDPM step
+__global__ void cfg_ddpm_step_kernel(const float* __restrict__ eps2, const float* __restrict__ x,
+                                     const float* __restrict__ noise, const float* __restrict__ coef, float gs,
+                                     int use_cfg, int vpred, float* __restrict__ x_prev, float* __restrict__ x0_out,
+                                     long long n) {
+  const float sa = coef[0], sb = coef[1], c0 = coef[2], ct = coef[3], sigma = coef[4];
+  const float inv_sa = 1.0f / sa;
+  const long long n4 = n >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 eu = reinterpret_cast<const float4*>(eps2)[i];
+    float e[4] = {eu.x, eu.y, eu.z, eu.w};
+    if (use_cfg) {
+      const float4 ec = reinterpret_cast<const float4*>(eps2 + n)[i];
+      e[0] += gs * (ec.x - eu.x), e[1] += gs * (ec.y - eu.y), e[2] += gs * (ec.z - eu.z), e[3] += gs * (ec.w - eu.w);
+    }
+    const float4 xv4 = reinterpret_cast<const float4*>(x)[i];
+    const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+    float nz[4] = {0, 0, 0, 0};
+    if (noise != nullptr) {
+      const float4 t = reinterpret_cast<const float4*>(noise)[i];
+      nz[0] = t.x, nz[1] = t.y, nz[2] = t.z, nz[3] = t.w;
+    }
+    float x0[4], xp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      x0[k] = vpred ? (sa * xv[k] - sb * e[k]) : (xv[k] - sb * e[k]) * inv_sa;
+      xp[k] = c0 * x0[k] + ct * xv[k] + sigma * nz[k];
+    }
+    reinterpret_cast<float4*>(x_prev)[i] = make_float4(xp[0], xp[1], xp[2], xp[3]);
+    if (x0_out) reinterpret_cast<float4*>(x0_out)[i] = make_float4(x0[0], x0[1], x0[2], x0[3]);
+  }
+}
+
+static int grid_for(long long work_items, int block, int max_blocks) {
+  long long g = (work_items + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace idb
+
+using namespace idb;
+
+extern "C" size_t idb_groupnorm_workspace_bytes(int32_t batch, int32_t groups) {
+  return static_cast<size_t>(batch) * GN_MAX_CHUNKS * groups * 2 * sizeof(float);
+}
+
+extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (a == nullptr) return fail(IDB_E_BADARG, "idb_groupnorm: null args");
+  if (int rc = require_sm100()) return rc;
+  const int C = a->c0 + (a->x1 ? a->c1 : 0);
+  if (!a->x0 || !a->gamma || !a->beta || !a->out_norm || !a->partials) return fail(IDB_E_BADARG, "idb_groupnorm: null pointer");
+  if (a->c0 % 4 || (a->x1 && a->c1 % 4) || C % a->groups || a->groups > GN_MAX_GROUPS || a->groups <= 0)
+    return fail(IDB_E_BADARG, "idb_groupnorm: channels must be multiples of 4 and divisible by groups (<= 64)");
+  if (C / 4 > 1024) return fail(IDB_E_BADARG, "idb_groupnorm: C too large");
+  GnParams p;
+  p.x0 = a->x0, p.x1 = a->x1, p.c0 = a->c0, p.c1 = a->x1 ? a->c1 : 0, p.C = C, p.CQ = C / 4;
+  p.PY = p.CQ >= 256 ? 1 : 256 / p.CQ;
+  p.hw = a->hw, p.groups = a->groups, p.cpg = C / a->groups, p.eps = a->eps;
+  int nchunks = a->hw / 32;
+  if (nchunks < 1) nchunks = 1;
+  if (nchunks > GN_MAX_CHUNKS) nchunks = GN_MAX_CHUNKS;
+  p.pix_per_chunk = (a->hw + nchunks - 1) / nchunks;
+  p.nchunks = (a->hw + p.pix_per_chunk - 1) / p.pix_per_chunk;
+  p.gamma = a->gamma, p.beta = a->beta, p.silu = a->silu;
+  p.out_norm = static_cast<__nv_bfloat16*>(a->out_norm);
+  p.out_raw = static_cast<__nv_bfloat16*>(a->out_raw);
+  p.partials = a->partials;
+  int threads = p.CQ * p.PY;
+  threads = (threads + 31) / 32 * 32;
+  if (threads < 64) threads = 64;  // the first 64 threads zero / publish the group slots
+  dim3 grid(p.nchunks, a->batch);
+  gn_stats_kernel<<<grid, threads, 0, stream>>>(p);
+  IDB_CHECK_LAUNCH("gn_stats");
+  gn_apply_kernel<<<grid, threads, 0, stream>>>(p);
+  IDB_CHECK_LAUNCH("gn_apply");
+  return IDB_OK;
+}
+
+extern "C" int idb_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16, int64_t rows,
+                             int32_t c, float eps, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = require_sm100()) return rc;
+  if (!x || !gamma || !beta || !out_bf16) return fail(IDB_E_BADARG, "idb_layernorm: null pointer");
+  if (c % 4 || c <= 0 || c > 2048) return fail(IDB_E_BADARG, "idb_layernorm: C must be a multiple of 4, <= 2048");
+  const int warps = 8;
+  const int grid = static_cast<int>((rows + warps - 1) / warps);
+  layernorm_kernel<16><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, static_cast<__nv_bfloat16*>(out_bf16), rows, c, eps);
+  IDB_CHECK_LAUNCH("layernorm");
+  return IDB_OK;
+}
+
+extern "C" int idb_softmax_rows(const float* s, void* p_bf16, int64_t rows, int32_t cols, float scale, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = require_sm100()) return rc;
+  if (!s || !p_bf16 || cols % 4 || rows <= 0) return fail(IDB_E_BADARG, "idb_softmax_rows: bad arguments");
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(s, static_cast<__nv_bfloat16*>(p_bf16), cols, scale);
+  IDB_CHECK_LAUNCH("softmax_rows");
+  return IDB_OK;
+}
+
+extern "C" int idb_time_embed(const idb_time_embed_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (a == nullptr) return fail(IDB_E_BADARG, "idb_time_embed: null args");
+  if (int rc = require_sm100()) return rc;
+  if (a->dim_sin % 4 || a->dim_emb % 4 || a->batch <= 0) return fail(IDB_E_BADARG, "idb_time_embed: bad dims");
+  float* sin_buf = a->scratch;
+  float* h1 = sin_buf + static_cast<long long>(a->batch) * a->dim_sin;
+  float* se = h1 + static_cast<long long>(a->batch) * a->dim_emb;
+  const int half_total = a->batch * a->dim_sin / 2;
+  sinusoid_kernel<<<(half_total + 127) / 128, 128, 0, stream>>>(a->timesteps, sin_buf, a->batch, a->dim_sin);
+  IDB_CHECK_LAUNCH("sinusoid");
+  const int wpb = 8;
+  skinny_linear_kernel<<<(a->dim_emb + wpb - 1) / wpb, wpb * 32, 0, stream>>>(sin_buf, a->w1, a->b1, h1, a->batch,
+                                                                              a->dim_sin, a->dim_emb, 1);
+  IDB_CHECK_LAUNCH("time linear_1");
+  skinny_linear_kernel<<<(a->dim_emb + wpb - 1) / wpb, wpb * 32, 0, stream>>>(h1, a->w2, a->b2, se, a->batch, a->dim_emb,
+                                                                              a->dim_emb, 1);
+  IDB_CHECK_LAUNCH("time linear_2");
+  skinny_linear_kernel<<<(a->n_all + wpb - 1) / wpb, wpb * 32, 0, stream>>>(se, a->w_all, a->b_all, a->proj_out, a->batch,
+                                                                            a->dim_emb, a->n_all, 0);
+  IDB_CHECK_LAUNCH("time_emb_proj");
+  return IDB_OK;
+}
+
+extern "C" int idb_conv3x3_small_cin(const float* x, int32_t x_nchw, const float* w, const float* bias, float* out_f32,
+                                     void* out_bf16, int32_t batch, int32_t h, int32_t wd, int32_t cin, int32_t cout,
+                                     void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = require_sm100()) return rc;
+  if (!x || !w || (!out_f32 && !out_bf16)) return fail(IDB_E_BADARG, "idb_conv3x3_small_cin: null pointer");
+  if (cin != 4 || cout % 4) return fail(IDB_E_UNSUPPORTED, "idb_conv3x3_small_cin: Cin must be 4, Cout % 4 == 0");
+  const long long total = static_cast<long long>(batch) * h * wd * (cout / 4);
+  conv_small_cin_kernel<4><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+      x, x_nchw, w, bias, out_f32, static_cast<__nv_bfloat16*>(out_bf16), batch, h, wd, cout);
+  IDB_CHECK_LAUNCH("conv_small_cin");
+  return IDB_OK;
+}
+
+extern "C" int idb_conv3x3_small_cout(const void* x_bf16, const float* w, const float* bias, float* out,
+                                      int32_t postprocess, int32_t batch, int32_t h, int32_t wd, int32_t cin,
+                                      int32_t cout, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = require_sm100()) return rc;
+  if (!x_bf16 || !w || !out) return fail(IDB_E_BADARG, "idb_conv3x3_small_cout: null pointer");
+  if (cin % 4 || (cout != 3 && cout != 4)) return fail(IDB_E_UNSUPPORTED, "idb_conv3x3_small_cout: Cout in {3,4}, Cin % 4 == 0");
+  const size_t smem = static_cast<size_t>(cout) * 9 * cin * sizeof(float);
+  if (smem > 48 * 1024) return fail(IDB_E_UNSUPPORTED, "idb_conv3x3_small_cout: weights exceed 48 KiB of shared memory");
+  const long long npix = static_cast<long long>(batch) * h * wd;
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((npix + wpb - 1) / wpb);
+  const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x_bf16);
+  if (cout == 4)
+    conv_small_cout_kernel<4><<<grid, wpb * 32, smem, stream>>>(xb, w, bias, out, postprocess, batch, h, wd, cin);
+  else
+    conv_small_cout_kernel<3><<<grid, wpb * 32, smem, stream>>>(xb, w, bias, out, postprocess, batch, h, wd, cin);
+  IDB_CHECK_LAUNCH("conv_small_cout");
+  return IDB_OK;
+}
+
+extern "C" int idb_upsample2x(const float* x, void* out_bf16, int32_t batch, int32_t h, int32_t wd, int32_t c,
+                              void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = require_sm100()) return rc;
+  if (!x || !out_bf16 || c % 4) return fail(IDB_E_BADARG, "idb_upsample2x: bad arguments");
+  const long long total = static_cast<long long>(batch) * 4 * h * wd * (c / 4);
+  upsample2x_kernel<<<grid_for(total, 256, num_sms() * 16), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(out_bf16),
+                                                                               batch, h, wd, c);
+  IDB_CHECK_LAUNCH("upsample2x");
+  return IDB_OK;
+}
+
+extern "C" int idb_cast_bf16(const float* x, void* out_bf16, int64_t n, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = require_sm100()) return rc;
+  if (!x || !out_bf16 || n % 4) return fail(IDB_E_BADARG, "idb_cast_bf16: bad arguments");
+  cast_bf16_kernel<<<grid_for(n / 4, 256, num_sms() * 16), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(out_bf16), n / 4);
+  IDB_CHECK_LAUNCH("cast_bf16");
+  return IDB_OK;
+}
+
+extern "C" int idb_vae_latent_prep(const float* z_nchw, const float* w, const float* bias, float inv_scaling,
+                                   float* out_nhwc, int32_t batch, int32_t hw, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = require_sm100()) return rc;
+  if (!z_nchw || !w || !bias || !out_nhwc) return fail(IDB_E_BADARG, "idb_vae_latent_prep: null pointer");
+  const long long total = static_cast<long long>(batch) * hw;
+  vae_latent_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(z_nchw, w, bias, inv_scaling,
+                                                                                         out_nhwc, batch, hw);
+  IDB_CHECK_LAUNCH("vae_latent_prep");
+  return IDB_OK;
+}
+
+extern "C" int idb_cfg_ddpm_step(const float* eps2, const float* x, const float* noise, const float* coef,
+                                 float guidance_scale, int32_t use_cfg, int32_t v_prediction, float* x_prev,
+                                 float* x0_out, int64_t n_per_branch, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = require_sm100()) return rc;
+  if (!eps2 || !x || !coef || !x_prev) return fail(IDB_E_BADARG, "idb_cfg_ddpm_step: null pointer");
+  if (n_per_branch <= 0 || n_per_branch % 4) return fail(IDB_E_BADARG, "idb_cfg_ddpm_step: n must be a positive multiple of 4");
+  cfg_ddpm_step_kernel<<<grid_for(n_per_branch / 4, 256, num_sms() * 8), 256, 0, stream>>>(
+      eps2, x, noise, coef, guidance_scale, use_cfg, v_prediction, x_prev, x0_out, n_per_branch);
+  IDB_CHECK_LAUNCH("cfg_ddpm_step");
+  return IDB_OK;
+}

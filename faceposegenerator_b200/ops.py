@@ -1,0 +1,228 @@
+"""Tensor-level wrappers over the C ABI (include/idb.h).  Each wrapper only validates
+dtype / layout / device, fills the POD argument struct with raw device pointers and
+launches on torch's current CUDA stream.  Outputs are caller-provided (or allocated
+with torch when omitted) -- the library itself never allocates.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import A_1X1, A_3X3, A_3X3_S2, EPI_GEGLU  # noqa: F401  (re-exported)
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _chk(t: Optional[torch.Tensor], dtype, name: str, allow_none: bool = False):
+    if t is None:
+        if allow_none:
+            return
+        raise ValueError(f"{name} is required")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optional[torch.Tensor] = None,
+              bias=None, rowvec=None, residual=None, lora_down=None, lora_up=None, lora_seg_n: int = 0,
+              geglu: bool = False, out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
+              want_f32: bool = False, want_bf16: bool = False, k_splits: int = 1,
+              workspace: Optional[torch.Tensor] = None):
+    """a0: bf16 [B,H,W,C0] (or [M,K] for a Linear); w: bf16 [N, Ktot].  Returns (out_f32, out_bf16)."""
+    _chk(a0, bf16, "a0"); _chk(w, bf16, "w")
+    if a0.dim() == 2:
+        B, H, W_, C0 = 1, 1, a0.shape[0], a0.shape[1]
+    else:
+        B, H, W_, C0 = a0.shape
+    N = w.shape[0]
+    Ho, Wo = (H // 2, W_ // 2) if mode == A_3X3_S2 else (H, W_)
+    M = B * Ho * Wo
+    taps = 1 if mode == A_1X1 else 9
+    c1 = 0
+    if a1 is not None:
+        _chk(a1, bf16, "a1")
+        c1 = a1.shape[-1]
+        if a1.numel() != M * c1:
+            raise ValueError("a1 must have the output geometry")
+    if w.shape[1] != taps * C0 + c1:
+        raise ValueError(f"w has K={w.shape[1]}, expected {taps * C0 + c1}")
+    n_out = N // 2 if geglu else N
+    for t, nm in ((bias, "bias"), (rowvec, "rowvec"), (residual, "residual"), (lora_up, "lora_up")):
+        _chk(t, f32, nm, allow_none=True)
+    _chk(lora_down, bf16, "lora_down", allow_none=True)
+    if residual is not None and residual.numel() != M * n_out:
+        raise ValueError("residual must be [M, N_out]")
+    if rowvec is not None and rowvec.numel() != B * N:
+        raise ValueError("rowvec must be [batch, N]")
+    if out_f32 is None and want_f32:
+        out_f32 = torch.empty((M, n_out), dtype=f32, device=a0.device)
+    if out_bf16 is None and (want_bf16 or (out_f32 is None)):
+        out_bf16 = torch.empty((M, n_out), dtype=bf16, device=a0.device)
+    _chk(out_f32, f32, "out_f32", allow_none=True); _chk(out_bf16, bf16, "out_bf16", allow_none=True)
+    if k_splits > 1 and workspace is None:
+        workspace = torch.empty((k_splits, M, N), dtype=f32, device=a0.device)
+    args = _lib.GemmConvArgs(
+        a0=a0.data_ptr(), a0_mode=mode, c0=C0, a1=_lib.ptr(a1), c1=c1, batch=B, height=H, width=W_,
+        w=w.data_ptr(), n=N, bias=_lib.ptr(bias), rowvec=_lib.ptr(rowvec), residual=_lib.ptr(residual),
+        lora_down=_lib.ptr(lora_down), lora_up=_lib.ptr(lora_up),
+        lora_rank_pad=0 if lora_up is None else lora_up.shape[1], lora_seg_n=lora_seg_n,
+        flags=EPI_GEGLU if geglu else 0, out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
+        k_splits=k_splits, workspace=_lib.ptr(workspace))
+    _lib.call("idb_gemm_conv", C.byref(args), _lib.stream_ptr())
+    if k_splits > 1:
+        _lib.launch_count += 1
+    return out_f32, out_bf16
+
+
+def attention(q, k, v, out=None, *, batch: int, heads: int, t_q: int, t_kv: int, scale: float,
+              col0_q: int = 0, col0_k: int = 0, col0_v: int = 0):
+    """q: bf16 [B*Tq, ld_q]; k, v: bf16 [B*Tkv, ld]; head h lives at columns col0 + h*64."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _chk(t, bf16, nm)
+    if out is None:
+        out = torch.empty((batch * t_q, heads * 64), dtype=bf16, device=q.device)
+    _chk(out, bf16, "out")
+    args = _lib.AttentionArgs(q=q.data_ptr(), ld_q=q.shape[-1], col0_q=col0_q, k=k.data_ptr(), ld_k=k.shape[-1],
+                              col0_k=col0_k, v=v.data_ptr(), ld_v=v.shape[-1], col0_v=col0_v, out=out.data_ptr(),
+                              ld_out=out.shape[-1], batch=batch, heads=heads, t_q=t_q, t_kv=t_kv, scale=scale)
+    _lib.call("idb_attention", C.byref(args), _lib.stream_ptr())
+    return out
+
+
+def groupnorm_workspace(batch: int, groups: int, device) -> torch.Tensor:
+    n = _lib.load().idb_groupnorm_workspace_bytes(batch, groups)
+    return torch.empty(n // 4, dtype=f32, device=device)
+
+
+def groupnorm(x0, gamma, beta, *, groups: int, eps: float, silu: bool, x1=None, out_norm=None, out_raw=None,
+              want_raw: bool = False, partials=None):
+    """x0: fp32 [B, HW.., C0] NHWC (+ optional x1 [B, HW.., C1] concatenated on channels)."""
+    _chk(x0, f32, "x0"); _chk(x1, f32, "x1", allow_none=True)
+    _chk(gamma, f32, "gamma"); _chk(beta, f32, "beta")
+    B, c0 = x0.shape[0], x0.shape[-1]
+    hw = x0.numel() // (B * c0)
+    c1 = 0 if x1 is None else x1.shape[-1]
+    Ct = c0 + c1
+    shape = tuple(x0.shape[:-1]) + (Ct,)
+    if out_norm is None:
+        out_norm = torch.empty(shape, dtype=bf16, device=x0.device)
+    if out_raw is None and want_raw:
+        out_raw = torch.empty(shape, dtype=bf16, device=x0.device)
+    if partials is None:
+        partials = groupnorm_workspace(B, groups, x0.device)
+    args = _lib.GroupNormArgs(x0=x0.data_ptr(), c0=c0, x1=_lib.ptr(x1), c1=c1, batch=B, hw=hw, groups=groups, eps=eps,
+                              gamma=gamma.data_ptr(), beta=beta.data_ptr(), silu=int(silu),
+                              out_norm=out_norm.data_ptr(), out_raw=_lib.ptr(out_raw), partials=partials.data_ptr())
+    _lib.call("idb_groupnorm", C.byref(args), _lib.stream_ptr())
+    return out_norm, out_raw
+
+
+def layernorm(x, gamma, beta, out=None, eps: float = 1e-5):
+    _chk(x, f32, "x"); _chk(gamma, f32, "gamma"); _chk(beta, f32, "beta")
+    c = x.shape[-1]
+    rows = x.numel() // c
+    if out is None:
+        out = torch.empty(x.shape, dtype=bf16, device=x.device)
+    _lib.call("idb_layernorm", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), out.data_ptr(), rows, c, eps,
+              _lib.stream_ptr())
+    return out
+
+
+def softmax_rows(s, scale: float, out=None):
+    _chk(s, f32, "s")
+    cols = s.shape[-1]
+    rows = s.numel() // cols
+    if out is None:
+        out = torch.empty(s.shape, dtype=bf16, device=s.device)
+    _lib.call("idb_softmax_rows", s.data_ptr(), out.data_ptr(), rows, cols, scale, _lib.stream_ptr())
+    return out
+
+
+def time_embed(timesteps, w1, b1, w2, b2, w_all, b_all, proj_out=None, scratch=None):
+    """timesteps fp32 [B] -> proj_out fp32 [B, n_all] (all time_emb_proj outputs of the UNet)."""
+    for t, nm in ((timesteps, "timesteps"), (w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2"), (w_all, "w_all"), (b_all, "b_all")):
+        _chk(t, f32, nm)
+    B = timesteps.shape[0]
+    dim_emb, dim_sin = w1.shape
+    n_all = w_all.shape[0]
+    if proj_out is None:
+        proj_out = torch.empty((B, n_all), dtype=f32, device=timesteps.device)
+    if scratch is None:
+        scratch = torch.empty((B, 2 * dim_emb + dim_sin), dtype=f32, device=timesteps.device)
+    args = _lib.TimeEmbedArgs(timesteps=timesteps.data_ptr(), batch=B, dim_sin=dim_sin, dim_emb=dim_emb,
+                              w1=w1.data_ptr(), b1=b1.data_ptr(), w2=w2.data_ptr(), b2=b2.data_ptr(),
+                              w_all=w_all.data_ptr(), b_all=b_all.data_ptr(), n_all=n_all,
+                              proj_out=proj_out.data_ptr(), scratch=scratch.data_ptr())
+    _lib.call("idb_time_embed", C.byref(args), _lib.stream_ptr())
+    return proj_out
+
+
+def conv3x3_small_cin(x, w, bias, *, nchw: bool, out_f32=None, out_bf16=None):
+    """x fp32 [B,4,H,W] (nchw) or [B,H,W,4]; w fp32 [Cout,3,3,4] -> NHWC fp32 (and/or bf16)."""
+    _chk(x, f32, "x"); _chk(w, f32, "w"); _chk(bias, f32, "bias", allow_none=True)
+    if nchw:
+        B, cin, H, W_ = x.shape
+    else:
+        B, H, W_, cin = x.shape
+    cout = w.shape[0]
+    if out_f32 is None and out_bf16 is None:
+        out_f32 = torch.empty((B, H, W_, cout), dtype=f32, device=x.device)
+    _lib.call("idb_conv3x3_small_cin", x.data_ptr(), int(nchw), w.data_ptr(), _lib.ptr(bias), _lib.ptr(out_f32),
+              _lib.ptr(out_bf16), B, H, W_, cin, cout, _lib.stream_ptr())
+    return out_f32, out_bf16
+
+
+def conv3x3_small_cout(x, w, bias, *, postprocess: bool = False, out=None):
+    """x bf16 [B,H,W,Cin]; w fp32 [Cout,3,3,Cin] -> fp32 NCHW [B,Cout,H,W] (or NHWC image in [0,1])."""
+    _chk(x, bf16, "x"); _chk(w, f32, "w"); _chk(bias, f32, "bias", allow_none=True)
+    B, H, W_, cin = x.shape
+    cout = w.shape[0]
+    if out is None:
+        out = torch.empty((B, H, W_, cout) if postprocess else (B, cout, H, W_), dtype=f32, device=x.device)
+    _lib.call("idb_conv3x3_small_cout", x.data_ptr(), w.data_ptr(), _lib.ptr(bias), out.data_ptr(), int(postprocess),
+              B, H, W_, cin, cout, _lib.stream_ptr())
+    return out
+
+
+def upsample2x(x, out=None):
+    _chk(x, f32, "x")
+    B, H, W_, c = x.shape
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W_, c), dtype=bf16, device=x.device)
+    _lib.call("idb_upsample2x", x.data_ptr(), out.data_ptr(), B, H, W_, c, _lib.stream_ptr())
+    return out
+
+
+def cast_bf16(x, out=None):
+    _chk(x, f32, "x")
+    if out is None:
+        out = torch.empty(x.shape, dtype=bf16, device=x.device)
+    _lib.call("idb_cast_bf16", x.data_ptr(), out.data_ptr(), x.numel(), _lib.stream_ptr())
+    return out
+
+
+def vae_latent_prep(z, w, bias, inv_scaling: float, out=None):
+    _chk(z, f32, "z"); _chk(w, f32, "w"); _chk(bias, f32, "bias")
+    B, c, H, W_ = z.shape
+    if out is None:
+        out = torch.empty((B, H, W_, 4), dtype=f32, device=z.device)
+    _lib.call("idb_vae_latent_prep", z.data_ptr(), w.data_ptr(), bias.data_ptr(), inv_scaling, out.data_ptr(), B, H * W_,
+              _lib.stream_ptr())
+    return out
+
+
+def cfg_ddpm_step(eps2, x, noise, coef, *, guidance_scale: float, use_cfg: bool, v_prediction: bool = False,
+                  x_prev=None, x0_out=None):
+    """eps2 fp32 [2n or n, ...], x fp32 [n, ...], coef fp32[5] on device."""
+    _chk(eps2, f32, "eps2"); _chk(x, f32, "x"); _chk(noise, f32, "noise", allow_none=True); _chk(coef, f32, "coef")
+    if x_prev is None:
+        x_prev = torch.empty_like(x)
+    _lib.call("idb_cfg_ddpm_step", eps2.data_ptr(), x.data_ptr(), _lib.ptr(noise), coef.data_ptr(), guidance_scale,
+              int(use_cfg), int(v_prediction), x_prev.data_ptr(), _lib.ptr(x0_out), x.numel(), _lib.stream_ptr())
+    return x_prev

@@ -1,0 +1,64 @@
+"""One-time weight repacking into the layouts the kernels consume (done at load, into
+caller-owned tensors; base weights are never modified afterwards).
+
+ - conv weights [Cout, Cin, kh, kw] (diffusers) -> K-major [Cout, kh*kw*Cin], tap-major /
+   channel-minor, optionally with the 1x1 conv_shortcut appended on K;
+ - GEGLU `ff.net.0.proj` rows interleaved in 16-blocks [a | g] so `a * gelu(g)` is local
+   to one 32-column epilogue chunk;
+ - LoRA A zero-padded to 16 rows per adapter (16 extra UMMA N-columns), B*scale as fp32
+   [N, rank_pad].
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def pack_conv_weight(w: torch.Tensor, shortcut: Optional[torch.Tensor] = None, device=None) -> torch.Tensor:
+    """[Cout, Cin, kh, kw] (+ optional [Cout, Cs, 1, 1]) -> bf16 [Cout, kh*kw*Cin (+Cs)]."""
+    p = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+    if shortcut is not None:
+        p = torch.cat([p, shortcut.reshape(shortcut.shape[0], -1)], dim=1)
+    return p.to(device=device, dtype=bf16).contiguous()
+
+
+def pack_edge_conv_weight(w: torch.Tensor, device=None) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] -> fp32 [Cout, 3, 3, Cin] for the tiny-Cin / tiny-Cout SIMT kernels."""
+    return w.permute(0, 2, 3, 1).to(device=device, dtype=f32).contiguous()
+
+
+def interleave_geglu(w: torch.Tensor, bias: Optional[torch.Tensor]):
+    """w [2*H, K] = [value rows | gate rows] -> rows ordered [v(16) g(16) v(16) g(16) ...]."""
+    H = w.shape[0] // 2
+    assert H % 16 == 0
+    idx = torch.arange(2 * H, device=w.device).view(2, H // 16, 16).permute(1, 0, 2).reshape(-1)
+    wi = w.index_select(0, idx).contiguous()
+    bi = bias.index_select(0, idx).contiguous() if bias is not None else None
+    return wi, bi
+
+
+def pack_lora(adapters: Sequence[Optional[Tuple[torch.Tensor, torch.Tensor, float]]], device=None,
+              seg_n: Optional[int] = None, k: Optional[int] = None):
+    """adapters: one (down [r, K], up [seg_n, r], scale) per N-segment of a fused projection
+    (None = segment without adapter).  Returns (down bf16 [nseg*16, K], up fp32 [nseg*seg_n, rank_pad])."""
+    live = [a for a in adapters if a is not None]
+    if not live:
+        return None, None
+    r = max(a[0].shape[0] for a in live)
+    if r > 16:
+        raise ValueError("fused LoRA supports rank <= 16")
+    rank_pad = (r + 3) // 4 * 4
+    k = k or live[0][0].shape[1]
+    seg_n = seg_n or live[0][1].shape[0]
+    down = torch.zeros((len(adapters) * 16, k), dtype=f32)
+    up = torch.zeros((len(adapters) * seg_n, rank_pad), dtype=f32)
+    for s, a in enumerate(adapters):
+        if a is None:
+            continue
+        d, u, scale = a
+        down[s * 16:s * 16 + d.shape[0]] = d.float().cpu()
+        up[s * seg_n:(s + 1) * seg_n, :u.shape[1]] = u.float().cpu() * float(scale)
+    return down.to(device=device, dtype=bf16).contiguous(), up.to(device=device).contiguous()

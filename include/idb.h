@@ -1,0 +1,209 @@
+/* idb.h -- C ABI of libidb_b200.so: the B200 (sm_100a) kernels behind the ID-Booth
+ * Stable Diffusion 2.1 denoising hot path.
+ *
+ * The reference (rangasaishreyas/FacePoseGenerator) is pure Python and reaches this
+ * arithmetic through torch ops inside diffusers==0.32.2 (requirements.txt:4); it has
+ * no FFI of its own.  Each entry point below therefore names the reference call site
+ * (file:line under /root/reference) and the diffusers module whose torch-op sequence
+ * it replaces.  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless noted;
+ *    the caller owns every buffer (including workspaces) -- the library never
+ *    allocates or frees device memory and keeps no reference past return.
+ *  - every function enqueues on `stream` (a cudaStream_t passed as void*), never
+ *    synchronises, and is CUDA-graph capturable.
+ *  - return 0 on success, a negative IDB_E_* code on error; idb_last_error() gives
+ *    the message of the calling thread's last failure.  No C++ exception crosses
+ *    the ABI.  A device that is not sm_100 is an error, never a fallback.
+ *  - activations: NHWC.  "stream" tensors (the residual stream) are fp32, GEMM/conv
+ *    operands are bf16.  Weights are pre-packed once at load (see each call).
+ */
+#ifndef IDB_H_
+#define IDB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IDB_VERSION 100
+
+enum {
+  IDB_OK = 0,
+  IDB_E_BADARG = -1,   /* shape / alignment / null pointer */
+  IDB_E_ARCH = -2,     /* device is not compute capability 10.x */
+  IDB_E_CUDA = -3,     /* CUDA runtime / driver error at launch */
+  IDB_E_UNSUPPORTED = -4
+};
+
+int idb_version(void);
+/* Copies the calling thread's last error message (NUL-terminated) into buf. */
+int idb_last_error(char* buf, size_t n);
+/* 0 if the current device is sm_100 (B200), IDB_E_ARCH otherwise. */
+int idb_device_check(void);
+int idb_num_sms(void);
+
+/* ------------------------------------------------------------------------------------------
+ * idb_gemm_conv: D[M,N] = epilogue( sum_seg im2col(A_seg)[M,K_seg] . W[N, K]^T )
+ * tcgen05/TMEM implicit GEMM fed by TMA.  One kernel covers
+ *   - nn.Linear            (diffusers Attention.to_q/k/v/to_out, FeedForward, proj_in/out;
+ *                           reached from inference_ID-Booth.py:138)
+ *   - peft lora.Linear     (unmerged rank-r delta fused in; inference_ID-Booth.py:107,
+ *                           train_ID-Booth.py:672-678)
+ *   - nn.Conv2d 3x3 s1/s2, 1x1 (ResnetBlock2D.conv1/conv2/conv_shortcut, Down/Upsample2D)
+ * A operands are bf16 NHWC images [B,H,W,C] (a Linear is the 1x1 "image" [1,1,M,K]);
+ * up to two K segments are concatenated (segment 1 is always a 1x1 tap: the fused
+ * conv_shortcut, or nothing).  W is bf16 [N, K_total] row-major with K ordered
+ * (tap-major, channel-minor) per segment.  C of every segment must be a multiple of 64,
+ * N a multiple of 32.
+ * ---------------------------------------------------------------------------------------- */
+enum { IDB_A_1X1 = 0, IDB_A_3X3 = 1, IDB_A_3X3_S2 = 2 };
+enum {
+  IDB_EPI_GEGLU = 1 /* W rows interleaved in 16-blocks [a(16) | g(16)]; out[:, j] = a_j * gelu_erf(g_j); N_out = N/2 */
+};
+
+typedef struct {
+  /* segment 0 */
+  const void* a0;      /* bf16 [B, H, W, C0] */
+  int32_t a0_mode;     /* IDB_A_* */
+  int32_t c0;
+  /* segment 1 (optional, 1x1, same OUTPUT geometry) */
+  const void* a1;      /* bf16 [B, Ho, Wo, C1] or NULL */
+  int32_t c1;
+  /* geometry of the INPUT image of segment 0 */
+  int32_t batch, height, width;
+  /* weights */
+  const void* w;       /* bf16 [N, K_total], K_total = taps0*C0 + C1 */
+  int32_t n;
+  /* epilogue inputs (all optional) */
+  const float* bias;    /* [N] */
+  const float* rowvec;  /* [batch, N]  added per image (ResnetBlock2D time_emb_proj term) */
+  const float* residual;/* fp32 [M, N_out] */
+  /* fused LoRA (optional): down is bf16 [n_seg*16, K] (each adapter's A zero-padded to 16
+   * rows; segment s = column / lora_seg_n), up is fp32 [N, lora_rank_pad] (B * scale,
+   * rank zero-padded to a multiple of 4, <= 16). */
+  const void* lora_down;
+  const float* lora_up;
+  int32_t lora_rank_pad;
+  int32_t lora_seg_n;
+  int32_t flags;        /* IDB_EPI_* */
+  /* outputs: row-major [M, N_out] with M = batch*Ho*Wo in (b, y, x) raster order */
+  float* out_f32;       /* or NULL */
+  void* out_bf16;       /* or NULL */
+  /* split-K: k_splits > 1 writes raw partial sums to workspace (fp32 [k_splits, M, N]) and a
+   * second kernel applies the epilogue.  workspace may be NULL when k_splits <= 1. */
+  int32_t k_splits;
+  float* workspace;
+} idb_gemm_conv_args;
+
+int idb_gemm_conv(const idb_gemm_conv_args* args, void* stream);
+/* Bytes of workspace idb_gemm_conv needs for (M, N, k_splits). */
+size_t idb_gemm_conv_workspace_bytes(int64_t m, int64_t n, int32_t k_splits);
+
+/* ------------------------------------------------------------------------------------------
+ * idb_attention: O = softmax(Q K^T * scale) V per (batch, head), flash-style on tcgen05
+ * (S and O accumulators in TMEM, online softmax in fp32).  Replaces AttnProcessor2_0 ->
+ * F.scaled_dot_product_attention (diffusers Attention, self- and cross-; head_dim 64).
+ * q/k/v: bf16 row-major token matrices; row (b, t) at ptr + ((b*T + t)*ld + col0 + head*64).
+ * out: bf16 [B*Tq, heads*64] (ld_out).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* q; int64_t ld_q; int32_t col0_q;
+  const void* k; int64_t ld_k; int32_t col0_k;
+  const void* v; int64_t ld_v; int32_t col0_v;
+  void* out;     int64_t ld_out;
+  int32_t batch, heads, t_q, t_kv;
+  float scale;
+} idb_attention_args;
+int idb_attention(const idb_attention_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * GroupNorm (+SiLU) over NHWC, fp32 statistics.  Replaces F.group_norm + F.silu in
+ * ResnetBlock2D.norm1/norm2, Transformer2DModel.norm, conv_norm_out.  Reads the logical
+ * channel-concatenation [x0 | x1] (UpBlock skip `torch.cat([h, skip], 1)`) without
+ * materialising it.  Inputs fp32 (stream) ; outputs bf16 [B,H,W,C0+C1]:
+ *   out_norm = act(GN(x))        out_raw (optional) = bf16(x)   (operand of conv_shortcut)
+ * partials: fp32 workspace of idb_groupnorm_workspace_bytes().
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* x0; int32_t c0;
+  const float* x1; int32_t c1;      /* NULL / 0 when there is no concat */
+  int32_t batch, hw, groups;
+  float eps;
+  const float* gamma; const float* beta;   /* [C0+C1] */
+  int32_t silu;
+  void* out_norm;                    /* bf16 */
+  void* out_raw;                     /* bf16 or NULL */
+  float* partials;
+} idb_groupnorm_args;
+int idb_groupnorm(const idb_groupnorm_args* args, void* stream);
+size_t idb_groupnorm_workspace_bytes(int32_t batch, int32_t groups);
+
+/* LayerNorm over the last dim (eps 1e-5, affine): fp32 [rows, C] -> bf16 [rows, C].
+ * Replaces BasicTransformerBlock.norm1/2/3. C % 4 == 0, C <= 2048. */
+int idb_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16,
+                  int64_t rows, int32_t c, float eps, void* stream);
+
+/* Row softmax for the VAE mid-block attention (1 head, d = 512): fp32 [rows, cols] * scale ->
+ * bf16 probabilities [rows, cols]. */
+int idb_softmax_rows(const float* s, void* p_bf16, int64_t rows, int32_t cols, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small / bandwidth-bound pieces
+ * ---------------------------------------------------------------------------------------- */
+/* Timesteps(320, flip_sin_to_cos, shift 0) -> linear_1 -> SiLU -> linear_2 -> SiLU (the SiLU
+ * that every ResnetBlock2D applies before time_emb_proj), then ALL time_emb_proj layers at
+ * once: proj_out[b, :] = W_all . silu(emb[b]) + b_all  with W_all = row-concat of the 22
+ * time_emb_proj weights.  fp32 weights.  scratch: fp32 [batch, 2*dim_emb + dim_sin]. */
+typedef struct {
+  const float* timesteps;            /* [batch] */
+  int32_t batch, dim_sin, dim_emb;   /* 320, 1280 */
+  const float* w1; const float* b1;  /* [dim_emb, dim_sin] */
+  const float* w2; const float* b2;  /* [dim_emb, dim_emb] */
+  const float* w_all; const float* b_all; int32_t n_all;   /* [n_all, dim_emb] */
+  float* proj_out;                   /* [batch, n_all] */
+  float* scratch;
+} idb_time_embed_args;
+int idb_time_embed(const idb_time_embed_args* args, void* stream);
+
+/* 3x3 pad-1 conv with tiny Cin (<= 8): conv_in of the UNet (4->320) and of the VAE decoder
+ * (4->512).  x fp32, NCHW when x_nchw else NHWC; w fp32 [Cout, 3, 3, Cin]; out fp32 NHWC
+ * and/or bf16 NHWC. */
+int idb_conv3x3_small_cin(const float* x, int32_t x_nchw, const float* w, const float* bias,
+                          float* out_f32, void* out_bf16,
+                          int32_t batch, int32_t h, int32_t wd, int32_t cin, int32_t cout, void* stream);
+/* 3x3 pad-1 conv with tiny Cout (<= 4): conv_out of the UNet (320->4) and VAE (128->3).
+ * x bf16 NHWC (already GroupNorm+SiLU'd); w fp32 [Cout, 3, 3, Cin]; out fp32 NCHW, or when
+ * postprocess != 0 NHWC with (v*0.5+0.5).clamp(0,1) (VaeImageProcessor.postprocess "np"). */
+int idb_conv3x3_small_cout(const void* x_bf16, const float* w, const float* bias, float* out,
+                           int32_t postprocess, int32_t batch, int32_t h, int32_t wd,
+                           int32_t cin, int32_t cout, void* stream);
+/* nearest-neighbour 2x upsample, NHWC: fp32 in -> bf16 out (Upsample2D's F.interpolate). */
+int idb_upsample2x(const float* x, void* out_bf16, int32_t batch, int32_t h, int32_t wd, int32_t c, void* stream);
+/* fp32 -> bf16 cast (operand staging for Downsample2D). */
+int idb_cast_bf16(const float* x, void* out_bf16, int64_t n, void* stream);
+/* VAE front: z/scaling_factor -> post_quant_conv 1x1 (4->4): NCHW fp32 -> NHWC fp32. */
+int idb_vae_latent_prep(const float* z_nchw, const float* w, const float* bias, float inv_scaling,
+                        float* out_nhwc, int32_t batch, int32_t hw, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * idb_cfg_ddpm_step: classifier-free-guidance combine + DDPMScheduler.step in ONE launch.
+ * Replaces `eps_u + s*(eps_c - eps_u)` and diffusers DDPMScheduler.step (pipeline loop behind
+ * inference_ID-Booth.py:138; guidance_scale from :49).  All tensors fp32 NCHW [n, ...]:
+ *   eps = cfg ? eps2[0:n] + s*(eps2[n:2n] - eps2[0:n]) : eps2[0:n]
+ *   x0  = epsilon: (x - sqrt_1m_acp*eps)/sqrt_acp ; v-pred: sqrt_acp*x - sqrt_1m_acp*eps
+ *   x_prev = c_x0*x0 + c_xt*x + sigma*noise           (noise may be NULL when sigma == 0)
+ * coef: DEVICE fp32[5] = {sqrt_acp, sqrt_1m_acp, c_x0, c_xt, sigma} (a row of the per-step
+ * table the scheduler uploads at set_timesteps -- no host sync inside the loop).
+ * ---------------------------------------------------------------------------------------- */
+int idb_cfg_ddpm_step(const float* eps2, const float* x, const float* noise, const float* coef,
+                      float guidance_scale, int32_t use_cfg, int32_t v_prediction,
+                      float* x_prev, float* x0_out /* or NULL */, int64_t n_per_branch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDB_H_ */

@@ -1,0 +1,307 @@
+"""T1 op parity: every C-ABI kernel vs the fp32 torch op it replaces (same bf16-rounded
+operands, fp32 math, TF32 off).  Tolerances: fp32 outputs rel-L2 <= 2e-5 (accumulation
+order only), bf16 outputs <= 4e-3 (one bf16 rounding)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def rb(t):  # bf16 round trip
+    return t.to(torch.bfloat16)
+
+
+def pack_conv_w(w):  # [Cout, Cin, 3, 3] -> [Cout, 9*Cin] tap-major
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_dev):
+    from faceposegenerator_b200 import ops
+    return ops
+
+
+# ------------------------------------------------------------------ Linear family
+@pytest.mark.parametrize("M,K,N", [(256, 128, 128), (4096, 320, 320), (1024, 640, 2560), (154, 1024, 640),
+                                   (8192, 1280, 1280), (300, 64, 32), (2048, 5120, 1280)])
+def test_linear_plain(ops, cuda_dev, M, K, N):
+    g = torch.Generator(device="cuda").manual_seed(M + K + N)
+    x = rb(torch.randn(M, K, device=cuda_dev, generator=g))
+    w = rb(torch.randn(N, K, device=cuda_dev, generator=g) / math.sqrt(K))
+    o32, o16 = ops.gemm_conv(x, w, want_f32=True, want_bf16=True)
+    ref = x.float() @ w.float().t()
+    torch.cuda.synchronize()
+    assert rel(o32, ref) < 2e-5, rel(o32, ref)
+    assert rel(o16.float(), ref) < 4e-3
+
+
+def test_linear_bias_residual_rowvec(ops, cuda_dev):
+    M, K, N = 2048, 640, 640
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = rb(torch.randn(M, K, device=cuda_dev, generator=g))
+    w = rb(torch.randn(N, K, device=cuda_dev, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=cuda_dev, generator=g)
+    res = torch.randn(M, N, device=cuda_dev, generator=g)
+    o32, o16 = ops.gemm_conv(x, w, bias=bias, residual=res, want_f32=True, want_bf16=True)
+    ref = x.float() @ w.float().t() + bias + res
+    assert rel(o32, ref) < 2e-5
+    assert rel(o16.float(), ref) < 4e-3
+
+
+def test_linear_geglu(ops, cuda_dev):
+    M, K, C4 = 1024, 320, 1280
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = rb(torch.randn(M, K, device=cuda_dev, generator=g))
+    w = rb(torch.randn(2 * C4, K, device=cuda_dev, generator=g) / math.sqrt(K))
+    bias = 0.1 * torch.randn(2 * C4, device=cuda_dev, generator=g)
+    from faceposegenerator_b200.packing import interleave_geglu
+    wi, bi = interleave_geglu(w, bias)
+    _, o16 = ops.gemm_conv(x, wi, bias=bi, geglu=True, want_bf16=True)
+    y = x.float() @ w.float().t() + bias
+    a, gate = y.chunk(2, dim=-1)
+    ref = a * F.gelu(gate)
+    assert o16.shape == (M, C4)
+    assert rel(o16.float(), ref) < 4e-3
+
+
+@pytest.mark.parametrize("C,Kin,nseg", [(320, 320, 3), (640, 1024, 2), (1280, 1280, 1)])
+def test_linear_fused_lora(ops, cuda_dev, C, Kin, nseg):
+    """Fused q/k/v (or k/v, or single) projection with one rank-4 adapter per segment:
+    y_s = x W_s^T + (x A_s^T) B_s^T -- peft lora.Linear, unmerged."""
+    from faceposegenerator_b200.packing import pack_lora
+    M, r = 1024, 4
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = rb(torch.randn(M, Kin, device=cuda_dev, generator=g))
+    ws = [rb(torch.randn(C, Kin, device=cuda_dev, generator=g) / math.sqrt(Kin)) for _ in range(nseg)]
+    downs = [torch.randn(r, Kin, device=cuda_dev, generator=g) / r for _ in range(nseg)]
+    ups = [torch.randn(C, r, device=cuda_dev, generator=g) * 0.05 for _ in range(nseg)]
+    bias = torch.randn(nseg * C, device=cuda_dev, generator=g)
+    w = torch.cat(ws, 0).contiguous()
+    ld, lu = pack_lora(list(zip(downs, ups, [1.0] * nseg)), device=cuda_dev)
+    o32, _ = ops.gemm_conv(x, w, bias=bias, lora_down=ld, lora_up=lu, lora_seg_n=C, want_f32=True)
+    refs = []
+    for s in range(nseg):
+        base = x.float() @ ws[s].float().t()
+        t = x.float() @ rb(downs[s]).float().t()
+        refs.append(base + t @ ups[s].t())
+    ref = torch.cat(refs, 1) + bias
+    assert rel(o32, ref) < 3e-5, rel(o32, ref)
+    # the adapter really contributes
+    assert rel(o32, torch.cat([x.float() @ wsi.float().t() for wsi in ws], 1) + bias) > 1e-3
+
+
+@pytest.mark.parametrize("M,K,N,splits", [(512, 11520, 1280, 4), (128, 23040, 1280, 8), (2048, 640, 640, 3)])
+def test_linear_split_k(ops, cuda_dev, M, K, N, splits):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = rb(torch.randn(M, K, device=cuda_dev, generator=g))
+    w = rb(torch.randn(N, K, device=cuda_dev, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=cuda_dev, generator=g)
+    res = torch.randn(M, N, device=cuda_dev, generator=g)
+    o32, o16 = ops.gemm_conv(x, w, bias=bias, residual=res, want_f32=True, want_bf16=True, k_splits=splits)
+    ref = x.float() @ w.float().t() + bias + res
+    assert rel(o32, ref) < 2e-5
+    assert rel(o16.float(), ref) < 4e-3
+
+
+# ------------------------------------------------------------------ convolutions
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 128), (2, 64, 64, 320, 320), (3, 8, 8, 1280, 1280),
+                                            (1, 32, 32, 640, 640), (2, 24, 24, 64, 128), (1, 128, 128, 128, 128),
+                                            (1, 12, 20, 64, 64)])
+def test_conv3x3(ops, cuda_dev, B, H, W, Cin, Cout):
+    g = torch.Generator(device="cuda").manual_seed(B * H + Cin)
+    x = rb(torch.randn(B, H, W, Cin, device=cuda_dev, generator=g))
+    w = rb(torch.randn(Cout, Cin, 3, 3, device=cuda_dev, generator=g) / math.sqrt(9 * Cin))
+    bias = torch.randn(Cout, device=cuda_dev, generator=g)
+    rowvec = torch.randn(B, Cout, device=cuda_dev, generator=g)
+    o32, _ = ops.gemm_conv(x, pack_conv_w(w), mode=ops.A_3X3, bias=bias, rowvec=rowvec, want_f32=True)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1) + rowvec[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+    assert rel(o32, ref) < 2e-5, rel(o32, ref)
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 64, 64, 320), (2, 16, 16, 1280), (1, 8, 8, 64)])
+def test_conv3x3_stride2(ops, cuda_dev, B, H, W, C):
+    g = torch.Generator(device="cuda").manual_seed(H)
+    x = rb(torch.randn(B, H, W, C, device=cuda_dev, generator=g))
+    w = rb(torch.randn(C, C, 3, 3, device=cuda_dev, generator=g) / math.sqrt(9 * C))
+    bias = torch.randn(C, device=cuda_dev, generator=g)
+    o32, _ = ops.gemm_conv(x, pack_conv_w(w), mode=ops.A_3X3_S2, bias=bias, want_f32=True)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, stride=2, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, C)
+    assert rel(o32, ref) < 2e-5, rel(o32, ref)
+
+
+def test_conv3x3_plus_shortcut_segment(ops, cuda_dev):
+    """ResnetBlock2D tail: conv2(h) + conv_shortcut(x) + x-independent bias, as ONE GEMM
+    whose K axis is [9*Cout | Cin]."""
+    B, H, W, Cin, Cout = 2, 32, 32, 960, 640
+    g = torch.Generator(device="cuda").manual_seed(5)
+    h = rb(torch.randn(B, H, W, Cout, device=cuda_dev, generator=g))
+    x = rb(torch.randn(B, H, W, Cin, device=cuda_dev, generator=g))
+    w2 = rb(torch.randn(Cout, Cout, 3, 3, device=cuda_dev, generator=g) / math.sqrt(9 * Cout))
+    ws = rb(torch.randn(Cout, Cin, 1, 1, device=cuda_dev, generator=g) / math.sqrt(Cin))
+    b2 = torch.randn(Cout, device=cuda_dev, generator=g)
+    wcat = torch.cat([pack_conv_w(w2), ws.reshape(Cout, Cin)], 1).contiguous()
+    o32, _ = ops.gemm_conv(h, wcat, mode=ops.A_3X3, a1=x, bias=b2, want_f32=True)
+    ref = F.conv2d(h.float().permute(0, 3, 1, 2), w2.float(), b2, padding=1) + \
+        F.conv2d(x.float().permute(0, 3, 1, 2), ws.float())
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, Cout)
+    assert rel(o32, ref) < 2e-5, rel(o32, ref)
+
+
+# ------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,heads,Tq,Tkv", [(2, 5, 4096, 4096), (2, 10, 1024, 1024), (2, 20, 256, 256), (3, 20, 64, 64),
+                                            (2, 5, 4096, 77), (1, 20, 64, 77), (1, 2, 200, 333)])
+def test_attention(ops, cuda_dev, B, heads, Tq, Tkv):
+    C = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(Tq + Tkv)
+    # q/k/v live in fused buffers, as the pipeline lays them out
+    qkv = rb(torch.randn(B * Tq, 3 * C, device=cuda_dev, generator=g))
+    kv = rb(torch.randn(B * Tkv, 2 * C, device=cuda_dev, generator=g))
+    if Tq == Tkv:
+        out = ops.attention(qkv, qkv, qkv, batch=B, heads=heads, t_q=Tq, t_kv=Tkv, scale=0.125,
+                            col0_q=0, col0_k=C, col0_v=2 * C)
+        q, k, v = qkv.float().view(B, Tq, 3, heads, 64).unbind(2)
+    else:
+        out = ops.attention(qkv, kv, kv, batch=B, heads=heads, t_q=Tq, t_kv=Tkv, scale=0.125,
+                            col0_q=0, col0_k=0, col0_v=C)
+        q = qkv.float().view(B, Tq, 3, heads, 64)[:, :, 0]
+        k, v = kv.float().view(B, Tkv, 2, heads, 64).unbind(2)
+    ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))
+    ref = ref.transpose(1, 2).reshape(B * Tq, C)
+    e = rel(out.float(), ref)
+    assert e < 6e-3, e
+
+
+# ------------------------------------------------------------------ norms
+@pytest.mark.parametrize("B,HW,C0,C1,silu,eps", [(2, 4096, 320, 0, True, 1e-5), (2, 1024, 640, 320, True, 1e-5),
+                                                (3, 64, 1280, 1280, True, 1e-5), (2, 256, 1280, 640, False, 1e-6),
+                                                (1, 16384, 128, 0, True, 1e-6), (2, 4096, 320, 0, False, 1e-6)])
+def test_groupnorm(ops, cuda_dev, B, HW, C0, C1, silu, eps):
+    g = torch.Generator(device="cuda").manual_seed(HW + C0)
+    x0 = torch.randn(B, HW, C0, device=cuda_dev, generator=g) * 2 + 0.5
+    x1 = torch.randn(B, HW, C1, device=cuda_dev, generator=g) if C1 else None
+    C = C0 + C1
+    gamma = 1 + 0.1 * torch.randn(C, device=cuda_dev, generator=g)
+    beta = 0.1 * torch.randn(C, device=cuda_dev, generator=g)
+    yn, yr = ops.groupnorm(x0, gamma, beta, groups=32, eps=eps, silu=silu, x1=x1, want_raw=True)
+    xc = torch.cat([x0, x1], -1) if C1 else x0
+    ref = F.group_norm(xc.permute(0, 2, 1), 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1)
+    assert rel(yn.float(), ref) < 4e-3
+    assert rel(yr.float(), xc) < 4e-3
+    # statistics themselves are fp32-exact: compare against the bf16 rounding of the reference
+    assert (yn.float() - ref.to(torch.bfloat16).float()).abs().max() < 0.07
+
+
+@pytest.mark.parametrize("rows,C", [(8192, 320), (2048, 640), (512, 1280), (77, 1024)])
+def test_layernorm(ops, cuda_dev, rows, C):
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = torch.randn(rows, C, device=cuda_dev, generator=g) * 3 + 1
+    gamma = 1 + 0.1 * torch.randn(C, device=cuda_dev, generator=g)
+    beta = 0.1 * torch.randn(C, device=cuda_dev, generator=g)
+    y = ops.layernorm(x, gamma, beta)
+    ref = F.layer_norm(x, (C,), gamma, beta, 1e-5)
+    assert rel(y.float(), ref) < 4e-3
+    assert (y.float() - ref.to(torch.bfloat16).float()).abs().max() < 0.04
+
+
+def test_softmax_rows(ops, cuda_dev):
+    s = torch.randn(1024, 4096, device=cuda_dev) * 20
+    p = ops.softmax_rows(s, 1 / math.sqrt(512))
+    ref = torch.softmax(s / math.sqrt(512), -1)
+    assert rel(p.float(), ref) < 4e-3
+
+
+# ------------------------------------------------------------------ small pieces
+def test_time_embed(ops, cuda_dev):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B = 5
+    t = torch.tensor([958.0, 925.0, 1.0, 0.0, 496.0], device=cuda_dev)
+    w1 = torch.randn(1280, 320, device=cuda_dev, generator=g) / math.sqrt(320)
+    b1 = 0.02 * torch.randn(1280, device=cuda_dev, generator=g)
+    w2 = torch.randn(1280, 1280, device=cuda_dev, generator=g) / math.sqrt(1280)
+    b2 = 0.02 * torch.randn(1280, device=cuda_dev, generator=g)
+    wa = torch.randn(2000, 1280, device=cuda_dev, generator=g) / math.sqrt(1280)
+    ba = 0.02 * torch.randn(2000, device=cuda_dev, generator=g)
+    out = ops.time_embed(t, w1, b1, w2, b2, wa, ba)
+    k = torch.arange(160, device=cuda_dev, dtype=torch.float32)
+    f = torch.exp(-math.log(10000.0) * k / 160)
+    a = t[:, None] * f[None]
+    sin = torch.cat([a.cos(), a.sin()], -1)
+    emb = F.linear(F.silu(F.linear(sin, w1, b1)), w2, b2)
+    ref = F.linear(F.silu(emb), wa, ba)
+    assert rel(out, ref) < 2e-4, rel(out, ref)
+
+
+@pytest.mark.parametrize("nchw", [True, False])
+def test_conv_small_cin(ops, cuda_dev, nchw):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, H, W, Cout = 2, 64, 64, 320
+    x = torch.randn(B, 4, H, W, device=cuda_dev, generator=g)
+    w = torch.randn(Cout, 4, 3, 3, device=cuda_dev, generator=g) / 6
+    bias = torch.randn(Cout, device=cuda_dev, generator=g)
+    xin = x if nchw else x.permute(0, 2, 3, 1).contiguous()
+    o32, _ = ops.conv3x3_small_cin(xin, w.permute(0, 2, 3, 1).contiguous(), bias, nchw=nchw)
+    ref = F.conv2d(x, w, bias, padding=1).permute(0, 2, 3, 1)
+    assert rel(o32, ref) < 1e-5
+
+
+@pytest.mark.parametrize("Cin,Cout,post", [(320, 4, False), (128, 3, True)])
+def test_conv_small_cout(ops, cuda_dev, Cin, Cout, post):
+    g = torch.Generator(device="cuda").manual_seed(12)
+    B, H, W = 2, 64, 64
+    x = rb(torch.randn(B, H, W, Cin, device=cuda_dev, generator=g))
+    w = torch.randn(Cout, Cin, 3, 3, device=cuda_dev, generator=g) / math.sqrt(9 * Cin)
+    bias = torch.randn(Cout, device=cuda_dev, generator=g)
+    out = ops.conv3x3_small_cout(x, w.permute(0, 2, 3, 1).contiguous(), bias, postprocess=post)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w, bias, padding=1)
+    if post:
+        ref = (ref * 0.5 + 0.5).clamp(0, 1).permute(0, 2, 3, 1)
+    assert rel(out, ref) < 1e-5
+
+
+def test_upsample_cast_latent_prep(ops, cuda_dev):
+    x = torch.randn(2, 8, 8, 64, device=cuda_dev)
+    up = ops.upsample2x(x)
+    ref = F.interpolate(x.permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up, ref.to(torch.bfloat16))
+    assert torch.equal(ops.cast_bf16(x), x.to(torch.bfloat16))
+    z = torch.randn(2, 4, 16, 16, device=cuda_dev)
+    w = torch.randn(4, 4, device=cuda_dev)
+    b = torch.randn(4, device=cuda_dev)
+    o = ops.vae_latent_prep(z, w, b, 1 / 0.18215)
+    ref = F.conv2d(z / 0.18215, w[:, :, None, None], b).permute(0, 2, 3, 1)
+    assert rel(o, ref) < 1e-5
+
+
+@pytest.mark.parametrize("use_cfg,vpred", [(True, False), (False, False), (True, True)])
+def test_cfg_ddpm_step_vs_oracle(ops, cuda_dev, use_cfg, vpred):
+    """K7 vs the restated DDPMScheduler.step + CFG combine (oracle/sd21.py)."""
+    from oracle.sd21 import DDPMSchedulerRef
+    sch = DDPMSchedulerRef(prediction_type="v_prediction" if vpred else "epsilon")
+    sch.set_timesteps(30)
+    n = 3
+    g = torch.Generator().manual_seed(0)
+    for t in (958, 496, 1):
+        eps2 = torch.randn(2 * n if use_cfg else n, 4, 64, 64, generator=g)
+        x = torch.randn(n, 4, 64, 64, generator=g)
+        noise = torch.randn(n, 4, 64, 64, generator=g)
+        e = eps2[:n] + 5.0 * (eps2[n:] - eps2[:n]) if use_cfg else eps2
+        ref_prev, ref_x0 = sch.step(e.double(), t, x.double(), noise.double())
+        coef = torch.tensor(sch.coefficients(t), dtype=torch.float32, device=cuda_dev)
+        x0 = torch.empty(n, 4, 64, 64, device=cuda_dev)
+        prev = ops.cfg_ddpm_step(eps2.to(cuda_dev), x.to(cuda_dev), noise.to(cuda_dev), coef, guidance_scale=5.0,
+                                 use_cfg=use_cfg, v_prediction=vpred, x0_out=x0)
+        assert rel(prev.cpu(), ref_prev) < 2e-6
+        assert rel(x0.cpu(), ref_x0) < 2e-6
