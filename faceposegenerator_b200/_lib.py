@@ -26,11 +26,11 @@ class GemmConvArgs(C.Structure):
         ("a1", c_void_p), ("c1", c_int32),
         ("batch", c_int32), ("height", c_int32), ("width", c_int32),
         ("w", c_void_p), ("n", c_int32),
-        ("bias", c_void_p), ("rowvec", c_void_p), ("residual", c_void_p),
+        ("bias", c_void_p), ("rowvec", c_void_p), ("rowvec_ld", c_int64), ("residual", c_void_p),
         ("lora_down", c_void_p), ("lora_up", c_void_p), ("lora_rank_pad", c_int32), ("lora_seg_n", c_int32),
         ("flags", c_int32),
         ("out_f32", c_void_p), ("out_bf16", c_void_p),
-        ("k_splits", c_int32), ("workspace", c_void_p),
+        ("k_splits", c_int32), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
     ]
 
 

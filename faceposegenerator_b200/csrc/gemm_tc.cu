@@ -40,6 +40,7 @@ struct GemmParams {
   long long M;
   const float* bias;
   const float* rowvec;
+  long long rowvec_ld;
   const float* residual;
   const float* lora_up;
   int lora_rank_pad, lora_seg_n;
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
         }
         if (p.rowvec != nullptr) {
-          const float4* rp = reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(b) * p.N + col);
+          const float4* rp = reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(b) * p.rowvec_ld + col);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 rv = __ldg(rp + j);
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 // ---------------------------------------------------------------------------------------- split-K finalize
 __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int k_splits, long long M, int N, int hw,
                                        const float* __restrict__ bias, const float* __restrict__ rowvec,
+                                       long long rowvec_ld,
                                        const float* __restrict__ residual, float* __restrict__ out_f32,
                                        __nv_bfloat16* __restrict__ out_bf16) {
   const long long total4 = M * N / 4;
@@ -355,7 +357,7 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int k_split
       a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
     }
     if (rowvec) {
-      const float4 v = *reinterpret_cast<const float4*>(rowvec + (row / hw) * N + col);
+      const float4 v = *reinterpret_cast<const float4*>(rowvec + (row / hw) * rowvec_ld + col);
       a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
     }
     if (residual) {
@@ -446,26 +448,50 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   const int tiles_b = (B + p.BB - 1) / p.BB;
   p.n_tiles_m = p.tiles_x * p.tiles_y * tiles_b;
 
-  // N tile
-  int block_n;
-  if (lora) block_n = 160;
-  else if (a->n % 256 == 0) block_n = 256;
-  else if (a->n % 160 == 0) block_n = 160;
-  else if (a->n % 128 == 0) block_n = 128;
-  else block_n = (a->n > 160) ? 256 : (a->n > 128 ? 160 : 128);
-  if (geglu && block_n % 32) return fail(IDB_E_BADARG, "idb_gemm_conv: GEGLU tile");
+  // N tile: minimise waves x per-tile MMA time (~ block_n at M = 128); ties go to the wider tile
+  const int sms = num_sms();
+  int block_n = 0;
+  if (lora) {
+    block_n = 160;
+  } else {
+    long long best = -1;
+    const int cands[3] = {256, 160, 128};
+    for (int ci = 0; ci < 3; ++ci) {
+      const int bn = cands[ci];
+      if (a->n % bn) continue;
+      const long long tiles = static_cast<long long>(p.n_tiles_m) * (a->n / bn);
+      const long long cost = ((tiles + sms - 1) / sms) * (bn + 24);
+      if (best < 0 || cost < best) best = cost, block_n = bn;
+    }
+    if (block_n == 0) block_n = (a->n > 160) ? 256 : (a->n > 128 ? 160 : 128);
+  }
   p.n_tiles_n = (a->n + block_n - 1) / block_n;
 
   const int nkb = p.nkb0 + p.nkb1;
-  int ksp = a->k_splits > 1 ? a->k_splits : 1;
+  int ksp = a->k_splits;
+  if (ksp == 0) {  // auto: split K when the tile grid leaves most SMs idle
+    ksp = 1;
+    const long long tiles = static_cast<long long>(p.n_tiles_m) * p.n_tiles_n;
+    if (!lora && !geglu && a->workspace && tiles * 2 <= sms && nkb >= 16) {
+      long long want = sms / tiles;
+      if (want > nkb / 8) want = nkb / 8;
+      const size_t per_split = static_cast<size_t>(p.M) * a->n * sizeof(float);
+      if (per_split * want > a->workspace_bytes) want = static_cast<long long>(a->workspace_bytes / per_split);
+      if (want > 1) ksp = static_cast<int>(want);
+    }
+  }
+  if (ksp < 1) ksp = 1;
   if (ksp > 1 && (lora || geglu)) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: split-K with LoRA / GEGLU");
   if (ksp > nkb) ksp = nkb;
   p.kb_per_split = (nkb + ksp - 1) / ksp;
   p.k_splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;
-  if (p.k_splits > 1 && !a->workspace) return fail(IDB_E_BADARG, "idb_gemm_conv: split-K needs a workspace");
+  if (p.k_splits > 1 && (!a->workspace || (a->k_splits > 1 && a->workspace_bytes != 0 &&
+                                           idb_gemm_conv_workspace_bytes(p.M, a->n, p.k_splits) > a->workspace_bytes)))
+    return fail(IDB_E_BADARG, "idb_gemm_conv: split-K needs a (large enough) workspace");
 
   p.bias = a->bias;
   p.rowvec = a->rowvec;
+  p.rowvec_ld = a->rowvec_ld > 0 ? a->rowvec_ld : a->n;
   p.residual = a->residual;
   p.lora_up = a->lora_up;
   p.lora_rank_pad = a->lora_rank_pad;
@@ -511,7 +537,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   }
 
   const int total_tiles = p.n_tiles_m * p.n_tiles_n * p.k_splits;
-  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  const int grid = total_tiles < sms ? total_tiles : sms;
   int rc;
   if (lora) rc = launch_gemm<160, 5, true>(p, grid, stream);
   else if (block_n == 256) rc = launch_gemm<256, 4, false>(p, grid, stream);
@@ -524,7 +550,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     int blocks = static_cast<int>((total4 + 255) / 256);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     splitk_finalize_kernel<<<blocks, 256, 0, stream>>>(p.workspace, p.k_splits, p.M, p.N, p.Ho * p.Wo, p.bias, p.rowvec,
-                                                       p.residual, p.out_f32, p.out_bf16);
+                                                       p.rowvec_ld, p.residual, p.out_f32, p.out_bf16);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("splitk_finalize launch: ") + cudaGetErrorString(e));
   }

@@ -30,7 +30,7 @@ def _chk(t: Optional[torch.Tensor], dtype, name: str, allow_none: bool = False):
 
 
 def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optional[torch.Tensor] = None,
-              bias=None, rowvec=None, residual=None, lora_down=None, lora_up=None, lora_seg_n: int = 0,
+              bias=None, rowvec=None, rowvec_ld: int = 0, residual=None, lora_down=None, lora_up=None, lora_seg_n: int = 0,
               geglu: bool = False, out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
               want_f32: bool = False, want_bf16: bool = False, k_splits: int = 1,
               workspace: Optional[torch.Tensor] = None):
@@ -58,7 +58,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
     _chk(lora_down, bf16, "lora_down", allow_none=True)
     if residual is not None and residual.numel() != M * n_out:
         raise ValueError("residual must be [M, N_out]")
-    if rowvec is not None and rowvec.numel() != B * N:
+    if rowvec is not None and rowvec_ld == 0 and rowvec.numel() != B * N:
         raise ValueError("rowvec must be [batch, N]")
     if out_f32 is None and want_f32:
         out_f32 = torch.empty((M, n_out), dtype=f32, device=a0.device)
@@ -69,14 +69,13 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
         workspace = torch.empty((k_splits, M, N), dtype=f32, device=a0.device)
     args = _lib.GemmConvArgs(
         a0=a0.data_ptr(), a0_mode=mode, c0=C0, a1=_lib.ptr(a1), c1=c1, batch=B, height=H, width=W_,
-        w=w.data_ptr(), n=N, bias=_lib.ptr(bias), rowvec=_lib.ptr(rowvec), residual=_lib.ptr(residual),
+        w=w.data_ptr(), n=N, bias=_lib.ptr(bias), rowvec=_lib.ptr(rowvec), rowvec_ld=rowvec_ld, residual=_lib.ptr(residual),
         lora_down=_lib.ptr(lora_down), lora_up=_lib.ptr(lora_up),
         lora_rank_pad=0 if lora_up is None else lora_up.shape[1], lora_seg_n=lora_seg_n,
         flags=EPI_GEGLU if geglu else 0, out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
-        k_splits=k_splits, workspace=_lib.ptr(workspace))
+        k_splits=k_splits, workspace=_lib.ptr(workspace),
+        workspace_bytes=0 if workspace is None else workspace.numel() * 4)
     _lib.call("idb_gemm_conv", C.byref(args), _lib.stream_ptr())
-    if k_splits > 1:
-        _lib.launch_count += 1
     return out_f32, out_bf16
 
 

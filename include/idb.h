@@ -81,6 +81,7 @@ typedef struct {
   /* epilogue inputs (all optional) */
   const float* bias;    /* [N] */
   const float* rowvec;  /* [batch, N]  added per image (ResnetBlock2D time_emb_proj term) */
+  int64_t rowvec_ld;    /* elements between consecutive images of rowvec (0 => N) */
   const float* residual;/* fp32 [M, N_out] */
   /* fused LoRA (optional): down is bf16 [n_seg*16, K] (each adapter's A zero-padded to 16
    * rows; segment s = column / lora_seg_n), up is fp32 [N, lora_rank_pad] (B * scale,
@@ -93,10 +94,12 @@ typedef struct {
   /* outputs: row-major [M, N_out] with M = batch*Ho*Wo in (b, y, x) raster order */
   float* out_f32;       /* or NULL */
   void* out_bf16;       /* or NULL */
-  /* split-K: k_splits > 1 writes raw partial sums to workspace (fp32 [k_splits, M, N]) and a
-   * second kernel applies the epilogue.  workspace may be NULL when k_splits <= 1. */
+  /* split-K: writes raw partial sums to workspace (fp32 [k_splits, M, N]) and a second kernel
+   * applies the epilogue.  k_splits: 1 = off, >1 = forced, 0 = auto (library picks a split that
+   * fills the SMs, limited by workspace_bytes).  workspace may be NULL when k_splits == 1. */
   int32_t k_splits;
   float* workspace;
+  size_t workspace_bytes;
 } idb_gemm_conv_args;
 
 int idb_gemm_conv(const idb_gemm_conv_args* args, void* stream);
