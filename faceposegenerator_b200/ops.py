@@ -53,8 +53,13 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
     if w.shape[1] != taps * C0 + c1:
         raise ValueError(f"w has K={w.shape[1]}, expected {taps * C0 + c1}")
     n_out = N // 2 if geglu else N
-    for t, nm in ((bias, "bias"), (rowvec, "rowvec"), (residual, "residual"), (lora_up, "lora_up")):
+    for t, nm in ((bias, "bias"), (residual, "residual"), (lora_up, "lora_up")):
         _chk(t, f32, nm, allow_none=True)
+    if rowvec is not None:  # may be a column slice of a wider [batch, ld] table (rowvec_ld = ld)
+        if not rowvec.is_cuda or rowvec.dtype != f32 or rowvec.stride(-1) != 1:
+            raise ValueError("rowvec must be a CUDA fp32 tensor with unit inner stride")
+        if rowvec_ld and rowvec.dim() == 2 and rowvec.stride(0) != rowvec_ld:
+            raise ValueError("rowvec_ld does not match the row stride of rowvec")
     _chk(lora_down, bf16, "lora_down", allow_none=True)
     if residual is not None and residual.numel() != M * n_out:
         raise ValueError("residual must be [M, N_out]")

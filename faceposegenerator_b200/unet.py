@@ -1,0 +1,323 @@
+"""Host side of `UNet2DConditionModel` (diffusers 0.32.2 semantics, SD2.1-base config) on the
+hand-written sm_100a kernels.  Same call surface as the reference uses
+(`/root/reference/train_ID-Booth.py:1040-1046`): `unet(sample, timestep,
+encoder_hidden_states, class_labels=None, return_dict=False)[0]`, `.config.in_channels`.
+
+Data layout in HBM: activations NHWC; the residual stream is fp32, every GEMM / conv operand
+is a bf16 tensor produced by the preceding norm (GroupNorm+SiLU / LayerNorm) or epilogue.
+`torch.cat([h, skip], 1)` is never materialised in fp32: GroupNorm reads both sources and
+writes the concatenated bf16 operand(s).  ResnetBlock2D.conv_shortcut is folded into conv2's
+GEMM as extra K columns; the 22 `time_emb_proj` layers run as one batched kernel; LoRA
+adapters are fused (unmerged) into the q/k/v/out projection GEMMs.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .packing import interleave_geglu, pack_conv_weight, pack_edge_conv_weight, pack_lora
+from .weights import UNET_CONFIG, random_state_dict, unet_manifest
+
+bf16, f32 = torch.bfloat16, torch.float32
+HEAD_DIM = 64
+WORKSPACE_BYTES = 96 << 20
+
+
+class UNetOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]
+
+
+class _Resnet:
+    __slots__ = ("cin", "cout", "g1", "b1", "w1", "bias1", "temb_off", "g2", "b2", "w2", "bias2", "shortcut")
+
+
+class _Transformer:
+    pass
+
+
+class UNet2DConditionModel:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], config: dict = UNET_CONFIG, device="cuda:0"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("UNet2DConditionModel runs on CUDA (sm_100a) only; there is no CPU fallback")
+        self.cfg = dict(config)
+        self.config = SimpleNamespace(**self.cfg)
+        self.dtype = bf16
+        self.groups = self.cfg["norm_num_groups"]
+        self.eps = self.cfg["norm_eps"]
+        self._lora_version = 0
+        self._kv_cache = None
+        self._workspace = None
+        self._pack(state_dict)
+        self.set_lora(None)
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_random(cls, seed: int = 0, config: dict = UNET_CONFIG, device="cuda:0"):
+        return cls(random_state_dict(unet_manifest(config), seed), config, device)
+
+    def _dev(self, t, dtype=f32):
+        return t.to(device=self.device, dtype=dtype).contiguous()
+
+    def _pack_resnet(self, sd, p: str, temb_rows: List[torch.Tensor], temb_bias: List[torch.Tensor]) -> _Resnet:
+        r = _Resnet()
+        w1 = sd[p + ".conv1.weight"]
+        r.cout, r.cin = w1.shape[0], w1.shape[1]
+        r.g1, r.b1 = self._dev(sd[p + ".norm1.weight"]), self._dev(sd[p + ".norm1.bias"])
+        r.w1 = pack_conv_weight(w1, device=self.device)
+        r.bias1 = self._dev(sd[p + ".conv1.bias"])
+        r.temb_off = sum(t.shape[0] for t in temb_rows)
+        temb_rows.append(sd[p + ".time_emb_proj.weight"])
+        temb_bias.append(sd[p + ".time_emb_proj.bias"])
+        r.g2, r.b2 = self._dev(sd[p + ".norm2.weight"]), self._dev(sd[p + ".norm2.bias"])
+        sc = sd.get(p + ".conv_shortcut.weight")
+        r.shortcut = sc is not None
+        r.w2 = pack_conv_weight(sd[p + ".conv2.weight"], shortcut=sc, device=self.device)
+        b2 = sd[p + ".conv2.bias"].float()
+        if r.shortcut:
+            b2 = b2 + sd[p + ".conv_shortcut.bias"].float()
+        r.bias2 = self._dev(b2)
+        return r
+
+    def _pack_transformer(self, sd, p: str) -> _Transformer:
+        t = _Transformer()
+        t.path = p
+        tb = p + ".transformer_blocks.0"
+        t.c = sd[p + ".proj_in.weight"].shape[0]
+        t.heads = t.c // HEAD_DIM
+        t.gn_g, t.gn_b = self._dev(sd[p + ".norm.weight"]), self._dev(sd[p + ".norm.bias"])
+        t.w_in, t.b_in = self._dev(sd[p + ".proj_in.weight"], bf16), self._dev(sd[p + ".proj_in.bias"])
+        t.w_out, t.b_out = self._dev(sd[p + ".proj_out.weight"], bf16), self._dev(sd[p + ".proj_out.bias"])
+        t.ln = [(self._dev(sd[f"{tb}.norm{i}.weight"]), self._dev(sd[f"{tb}.norm{i}.bias"])) for i in (1, 2, 3)]
+        a1, a2 = tb + ".attn1", tb + ".attn2"
+        t.w_qkv = self._dev(torch.cat([sd[a1 + ".to_q.weight"], sd[a1 + ".to_k.weight"], sd[a1 + ".to_v.weight"]], 0), bf16)
+        t.w_o1, t.b_o1 = self._dev(sd[a1 + ".to_out.0.weight"], bf16), self._dev(sd[a1 + ".to_out.0.bias"])
+        t.w_q2 = self._dev(sd[a2 + ".to_q.weight"], bf16)
+        t.w_kv2 = self._dev(torch.cat([sd[a2 + ".to_k.weight"], sd[a2 + ".to_v.weight"]], 0), bf16)
+        t.w_o2, t.b_o2 = self._dev(sd[a2 + ".to_out.0.weight"], bf16), self._dev(sd[a2 + ".to_out.0.bias"])
+        wi, bi = interleave_geglu(sd[tb + ".ff.net.0.proj.weight"], sd[tb + ".ff.net.0.proj.bias"])
+        t.w_ff1, t.b_ff1 = self._dev(wi, bf16), self._dev(bi)
+        t.w_ff2, t.b_ff2 = self._dev(sd[tb + ".ff.net.2.weight"], bf16), self._dev(sd[tb + ".ff.net.2.bias"])
+        t.lora = {}
+        return t
+
+    def _pack(self, sd):
+        cfg = self.cfg
+        ch = tuple(cfg["block_out_channels"])
+        n = len(ch)
+        temb_rows, temb_bias = [], []
+        self.w_conv_in = pack_edge_conv_weight(sd["conv_in.weight"], self.device)
+        self.b_conv_in = self._dev(sd["conv_in.bias"])
+        self.t_w1, self.t_b1 = self._dev(sd["time_embedding.linear_1.weight"]), self._dev(sd["time_embedding.linear_1.bias"])
+        self.t_w2, self.t_b2 = self._dev(sd["time_embedding.linear_2.weight"]), self._dev(sd["time_embedding.linear_2.bias"])
+        self.down, self.up = [], []
+        for i in range(n):
+            attn = cfg["down_block_types"][i].startswith("CrossAttn")
+            blk = SimpleNamespace(resnets=[], attns=[], down=None)
+            for j in range(cfg["layers_per_block"]):
+                blk.resnets.append(self._pack_resnet(sd, f"down_blocks.{i}.resnets.{j}", temb_rows, temb_bias))
+                if attn:
+                    blk.attns.append(self._pack_transformer(sd, f"down_blocks.{i}.attentions.{j}"))
+            if i < n - 1:
+                q = f"down_blocks.{i}.downsamplers.0.conv"
+                blk.down = (pack_conv_weight(sd[q + ".weight"], device=self.device), self._dev(sd[q + ".bias"]))
+            self.down.append(blk)
+        self.mid = SimpleNamespace(
+            res0=self._pack_resnet(sd, "mid_block.resnets.0", temb_rows, temb_bias),
+            attn=self._pack_transformer(sd, "mid_block.attentions.0"),
+            res1=self._pack_resnet(sd, "mid_block.resnets.1", temb_rows, temb_bias))
+        for i in range(n):
+            attn = cfg["up_block_types"][i].startswith("CrossAttn")
+            blk = SimpleNamespace(resnets=[], attns=[], up=None)
+            for j in range(cfg["layers_per_block"] + 1):
+                blk.resnets.append(self._pack_resnet(sd, f"up_blocks.{i}.resnets.{j}", temb_rows, temb_bias))
+                if attn:
+                    blk.attns.append(self._pack_transformer(sd, f"up_blocks.{i}.attentions.{j}"))
+            if i < n - 1:
+                q = f"up_blocks.{i}.upsamplers.0.conv"
+                blk.up = (pack_conv_weight(sd[q + ".weight"], device=self.device), self._dev(sd[q + ".bias"]))
+            self.up.append(blk)
+        self.t_w_all = self._dev(torch.cat(temb_rows, 0))
+        self.t_b_all = self._dev(torch.cat(temb_bias, 0))
+        self.out_g, self.out_b = self._dev(sd["conv_norm_out.weight"]), self._dev(sd["conv_norm_out.bias"])
+        self.w_conv_out = pack_edge_conv_weight(sd["conv_out.weight"], self.device)
+        self.b_conv_out = self._dev(sd["conv_out.bias"])
+        self.transformers: List[_Transformer] = [a for b in self.down for a in b.attns] + [self.mid.attn] + \
+            [a for b in self.up for a in b.attns]
+        self.cross_dim = cfg["cross_attention_dim"]
+
+    # ------------------------------------------------------------------ LoRA (peft lora.Linear, unmerged)
+    def set_lora(self, lora: Optional[dict]) -> None:
+        """lora: {module_path: (down [r,in], up [out,r], scale)} or None.  Only the small packed
+        adapter tensors change; base weights stay bit-identical (adapter hot-swap)."""
+        known = set()
+        for t in self.transformers:
+            tb = t.path + ".transformer_blocks.0"
+            get = (lambda k: lora.get(k)) if lora else (lambda k: None)
+            a1, a2 = tb + ".attn1", tb + ".attn2"
+            known.update(f"{a}.{m}" for a in (a1, a2) for m in ("to_q", "to_k", "to_v", "to_out.0"))
+            t.lora = {
+                "qkv": pack_lora([get(a1 + ".to_q"), get(a1 + ".to_k"), get(a1 + ".to_v")], self.device, seg_n=t.c, k=t.c),
+                "o1": pack_lora([get(a1 + ".to_out.0")], self.device, seg_n=t.c, k=t.c),
+                "q2": pack_lora([get(a2 + ".to_q")], self.device, seg_n=t.c, k=t.c),
+                "kv2": pack_lora([get(a2 + ".to_k"), get(a2 + ".to_v")], self.device, seg_n=t.c, k=self.cross_dim),
+                "o2": pack_lora([get(a2 + ".to_out.0")], self.device, seg_n=t.c, k=t.c),
+            }
+        if lora:
+            unknown = set(lora) - known
+            if unknown:
+                raise KeyError(f"LoRA targets not present in this UNet: {sorted(unknown)[:4]} ...")
+        self._lora_version += 1
+        self._kv_cache = None
+
+    # ------------------------------------------------------------------ helpers
+    def _ws(self):
+        if self._workspace is None:
+            self._workspace = torch.empty(WORKSPACE_BYTES // 4, dtype=f32, device=self.device)
+        return self._workspace
+
+    def _gemm(self, a0, w, **kw):
+        return ops.gemm_conv(a0, w, k_splits=0, workspace=self._ws(), **kw)
+
+    def _lin_lora(self, a0, w, lo, seg_n, **kw):
+        ld, lu = lo
+        if ld is None:
+            return self._gemm(a0, w, **kw)
+        return self._gemm(a0, w, lora_down=ld, lora_up=lu, lora_seg_n=seg_n, **kw)
+
+    def _resnet(self, r: _Resnet, h, skip, temb, gnws):
+        B, H, W = h.shape[0], h.shape[1], h.shape[2]
+        n1, raw = ops.groupnorm(h, r.g1, r.b1, groups=self.groups, eps=self.eps, silu=True, x1=skip,
+                                want_raw=r.shortcut, partials=gnws)
+        t1, _ = self._gemm(n1, r.w1, mode=ops.A_3X3, bias=r.bias1, rowvec=temb[:, r.temb_off:],
+                           rowvec_ld=temb.shape[1], want_f32=True)
+        t1 = t1.view(B, H, W, r.cout)
+        n2, _ = ops.groupnorm(t1, r.g2, r.b2, groups=self.groups, eps=self.eps, silu=True, partials=gnws)
+        if r.shortcut:
+            o, _ = self._gemm(n2, r.w2, mode=ops.A_3X3, a1=raw, bias=r.bias2, want_f32=True)
+        else:
+            o, _ = self._gemm(n2, r.w2, mode=ops.A_3X3, bias=r.bias2, residual=h, want_f32=True)
+        return o.view(B, H, W, r.cout)
+
+    def _context_kv(self, t: _Transformer, ctx_bf16):
+        _, kv = self._lin_lora(ctx_bf16, t.w_kv2, t.lora["kv2"], t.c, want_bf16=True)
+        return kv
+
+    def _transformer(self, t: _Transformer, h, kv, n_ctx, gnws):
+        B, H, W, Cc = h.shape
+        M, T = B * H * W, H * W
+        n, _ = ops.groupnorm(h, t.gn_g, t.gn_b, groups=self.groups, eps=1e-6, silu=False, partials=gnws)
+        x0, _ = self._gemm(n.view(M, Cc), t.w_in, bias=t.b_in, want_f32=True)
+        # self-attention
+        a = ops.layernorm(x0, *t.ln[0])
+        _, qkv = self._lin_lora(a, t.w_qkv, t.lora["qkv"], Cc, want_bf16=True)
+        o = ops.attention(qkv, qkv, qkv, batch=B, heads=t.heads, t_q=T, t_kv=T, scale=HEAD_DIM ** -0.5,
+                          col0_q=0, col0_k=Cc, col0_v=2 * Cc)
+        x1, _ = self._lin_lora(o, t.w_o1, t.lora["o1"], Cc, bias=t.b_o1, residual=x0, want_f32=True)
+        # cross-attention over the (step-invariant) projected context
+        a = ops.layernorm(x1, *t.ln[1])
+        _, q = self._lin_lora(a, t.w_q2, t.lora["q2"], Cc, want_bf16=True)
+        o = ops.attention(q, kv, kv, batch=B, heads=t.heads, t_q=T, t_kv=n_ctx, scale=HEAD_DIM ** -0.5,
+                          col0_q=0, col0_k=0, col0_v=Cc)
+        x2, _ = self._lin_lora(o, t.w_o2, t.lora["o2"], Cc, bias=t.b_o2, residual=x1, want_f32=True)
+        # GEGLU feed-forward
+        a = ops.layernorm(x2, *t.ln[2])
+        _, g = self._gemm(a, t.w_ff1, bias=t.b_ff1, geglu=True, want_bf16=True)
+        _, x3 = self._gemm(g, t.w_ff2, bias=t.b_ff2, residual=x2, want_bf16=True)
+        out, _ = self._gemm(x3, t.w_out, bias=t.b_out, residual=h.view(M, Cc), want_f32=True)
+        return out.view(B, H, W, Cc)
+
+    # ------------------------------------------------------------------ step-invariant context projections
+    def encode_context(self, encoder_hidden_states: torch.Tensor):
+        """Cross-attention K/V projections (incl. their LoRA deltas) of the text context: they do
+        not depend on the timestep, so the pipeline computes them once per prompt batch."""
+        B, S, D = encoder_hidden_states.shape
+        ctx = encoder_hidden_states.to(device=self.device, dtype=bf16).reshape(B * S, D).contiguous()
+        return SimpleNamespace(kv=[self._context_kv(t, ctx) for t in self.transformers], n_ctx=S, batch=B,
+                               lora_version=self._lora_version)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, sample, timestep, encoder_hidden_states=None, class_labels=None, return_dict: bool = True,
+                context=None, taps: Optional[dict] = None):
+        if class_labels is not None:
+            raise NotImplementedError("SD2.1-base has no class embedding")
+        in_dtype = sample.dtype
+        x = sample.to(device=self.device, dtype=f32).contiguous()
+        B, Cin, H, W = x.shape
+        if H % 8 or W % 8:
+            raise ValueError("latent height/width must be multiples of 8 (three stride-2 stages)")
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([float(timestep)], dtype=f32, device=self.device)
+        t = timestep.to(device=self.device, dtype=f32).reshape(-1)
+        if t.numel() == 1:
+            t = t.expand(B)
+        t = t.contiguous()
+        if context is None:
+            context = self.encode_context(encoder_hidden_states)
+        if context.lora_version != self._lora_version or context.batch != B:
+            raise RuntimeError("stale / mismatched encode_context() result")
+        kvs = iter(context.kv)
+        gnws = ops.groupnorm_workspace(B, self.groups, self.device)
+        temb = ops.time_embed(t, self.t_w1, self.t_b1, self.t_w2, self.t_b2, self.t_w_all, self.t_b_all)
+
+        def tap(name, v):
+            if taps is not None:
+                taps[name] = v.permute(0, 3, 1, 2).float().clone()
+
+        h, _ = ops.conv3x3_small_cin(x, self.w_conv_in, self.b_conv_in, nchw=True)
+        tap("conv_in", h)
+        skips = [h]
+        for i, blk in enumerate(self.down):
+            for j, r in enumerate(blk.resnets):
+                h = self._resnet(r, h, None, temb, gnws)
+                tap(f"down_blocks.{i}.resnets.{j}", h)
+                if blk.attns:
+                    h = self._transformer(blk.attns[j], h, next(kvs), context.n_ctx, gnws)
+                    tap(f"down_blocks.{i}.attentions.{j}", h)
+                skips.append(h)
+            if blk.down is not None:
+                hb = ops.cast_bf16(h)
+                o, _ = self._gemm(hb, blk.down[0], mode=ops.A_3X3_S2, bias=blk.down[1], want_f32=True)
+                h = o.view(B, h.shape[1] // 2, h.shape[2] // 2, h.shape[3])
+                skips.append(h)
+        h = self._resnet(self.mid.res0, h, None, temb, gnws)
+        h = self._transformer(self.mid.attn, h, next(kvs), context.n_ctx, gnws)
+        h = self._resnet(self.mid.res1, h, None, temb, gnws)
+        tap("mid_block", h)
+        for i, blk in enumerate(self.up):
+            for j, r in enumerate(blk.resnets):
+                h = self._resnet(r, h, skips.pop(), temb, gnws)
+                if blk.attns:
+                    h = self._transformer(blk.attns[j], h, next(kvs), context.n_ctx, gnws)
+                tap(f"up_blocks.{i}.{j}", h)
+            if blk.up is not None:
+                hu = ops.upsample2x(h)
+                o, _ = self._gemm(hu, blk.up[0], mode=ops.A_3X3, bias=blk.up[1], want_f32=True)
+                h = o.view(B, hu.shape[1], hu.shape[2], h.shape[3])
+        n, _ = ops.groupnorm(h, self.out_g, self.out_b, groups=self.groups, eps=self.eps, silu=True, partials=gnws)
+        eps = ops.conv3x3_small_cout(n, self.w_conv_out, self.b_conv_out)
+        if in_dtype != f32:
+            eps = eps.to(in_dtype)
+        return UNetOutput(eps) if return_dict else (eps,)
+
+    __call__ = forward
+
+    # diffusers-compat no-ops
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    def train(self, mode: bool = True):
+        return self  # dropout p = 0: train-mode forward is the same arithmetic (train_ID-Booth.py:989)
+
+    def requires_grad_(self, flag: bool = False):
+        return self

@@ -1,0 +1,187 @@
+"""`AutoencoderKL.decode` (diffusers 0.32.2, SD2.1-base VAE) on the same sm_100a kernels as the
+UNet: `vae.decode(z).sample` / `.config.scaling_factor`
+(`/root/reference/train_ID-Booth.py:410-412,435-437`; pipeline tail behind
+`inference_ID-Booth.py:138`).  NHWC, fp32 residual stream, bf16 GEMM/conv operands.
+
+Mid-block attention (1 head, d = 512, 4096 tokens) is expressed with the tcgen05 GEMM:
+S = Q K^T (fp32), row softmax, O = P V with V^T produced directly by a swapped-operand GEMM
+(V^T = W_v X^T); the to_v bias is folded into to_out's bias (softmax rows sum to 1).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .packing import pack_conv_weight, pack_edge_conv_weight
+from .weights import VAE_CONFIG, random_state_dict, vae_decoder_manifest
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+class DecoderOutput:
+    def __init__(self, sample):
+        self.sample = sample
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]
+
+
+class AutoencoderKL:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], config: dict = VAE_CONFIG, device="cuda:0"):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("AutoencoderKL runs on CUDA (sm_100a) only; there is no CPU fallback")
+        self.cfg = dict(config)
+        self.config = SimpleNamespace(**self.cfg)
+        self.dtype = bf16
+        self.groups = self.cfg["norm_num_groups"]
+        self.eps = 1e-6
+        self._workspace = None
+        self._pack(state_dict)
+
+    @classmethod
+    def from_random(cls, seed: int = 0, config: dict = VAE_CONFIG, device="cuda:0"):
+        return cls(random_state_dict(vae_decoder_manifest(config), seed), config, device)
+
+    def _dev(self, t, dtype=f32):
+        return t.to(device=self.device, dtype=dtype).contiguous()
+
+    def _pack_resnet(self, sd, p):
+        r = SimpleNamespace()
+        w1 = sd[p + ".conv1.weight"]
+        r.cout, r.cin = w1.shape[0], w1.shape[1]
+        r.g1, r.b1 = self._dev(sd[p + ".norm1.weight"]), self._dev(sd[p + ".norm1.bias"])
+        r.w1, r.bias1 = pack_conv_weight(w1, device=self.device), self._dev(sd[p + ".conv1.bias"])
+        r.g2, r.b2 = self._dev(sd[p + ".norm2.weight"]), self._dev(sd[p + ".norm2.bias"])
+        sc = sd.get(p + ".conv_shortcut.weight")
+        r.shortcut = sc is not None
+        r.w2 = pack_conv_weight(sd[p + ".conv2.weight"], shortcut=sc, device=self.device)
+        b2 = sd[p + ".conv2.bias"].float()
+        if r.shortcut:
+            b2 = b2 + sd[p + ".conv_shortcut.bias"].float()
+        r.bias2 = self._dev(b2)
+        return r
+
+    def _pack(self, sd):
+        sd = dict(sd)
+        a = "decoder.mid_block.attentions.0"
+        for old, new in (("query", "to_q"), ("key", "to_k"), ("value", "to_v"), ("proj_attn", "to_out.0")):
+            for suf in (".weight", ".bias"):  # legacy checkpoint spelling (App. A.4)
+                key = f"{a}.{old}{suf}"
+                if key in sd:
+                    t = sd.pop(key)
+                    sd[f"{a}.{new}{suf}"] = t.reshape(t.shape[0], t.shape[1]) if suf == ".weight" else t
+        self.pq_w = self._dev(sd["post_quant_conv.weight"].reshape(4, 4))
+        self.pq_b = self._dev(sd["post_quant_conv.bias"])
+        self.w_in = pack_edge_conv_weight(sd["decoder.conv_in.weight"], self.device)
+        self.b_in = self._dev(sd["decoder.conv_in.bias"])
+        self.mid0 = self._pack_resnet(sd, "decoder.mid_block.resnets.0")
+        self.mid1 = self._pack_resnet(sd, "decoder.mid_block.resnets.1")
+        at = SimpleNamespace()
+        at.g, at.b = self._dev(sd[a + ".group_norm.weight"]), self._dev(sd[a + ".group_norm.bias"])
+        at.wq, at.bq = self._dev(sd[a + ".to_q.weight"], bf16), self._dev(sd[a + ".to_q.bias"])
+        at.wk, at.bk = self._dev(sd[a + ".to_k.weight"], bf16), self._dev(sd[a + ".to_k.bias"])
+        at.wv = self._dev(sd[a + ".to_v.weight"], bf16)
+        wo = sd[a + ".to_out.0.weight"].float()
+        at.wo = self._dev(wo, bf16)
+        # out = W_o (P V0 + b_v) + b_o  (softmax rows sum to one)
+        at.bo = self._dev(sd[a + ".to_out.0.bias"].float() + wo @ sd[a + ".to_v.bias"].float())
+        at.c = wo.shape[0]
+        self.attn = at
+        n = len(self.cfg["block_out_channels"])
+        self.up = []
+        for i in range(n):
+            blk = SimpleNamespace(resnets=[self._pack_resnet(sd, f"decoder.up_blocks.{i}.resnets.{j}")
+                                           for j in range(self.cfg["layers_per_block"] + 1)], up=None)
+            if i < n - 1:
+                q = f"decoder.up_blocks.{i}.upsamplers.0.conv"
+                blk.up = (pack_conv_weight(sd[q + ".weight"], device=self.device), self._dev(sd[q + ".bias"]))
+            self.up.append(blk)
+        self.out_g, self.out_b = self._dev(sd["decoder.conv_norm_out.weight"]), self._dev(sd["decoder.conv_norm_out.bias"])
+        self.w_out = pack_edge_conv_weight(sd["decoder.conv_out.weight"], self.device)
+        self.b_out = self._dev(sd["decoder.conv_out.bias"])
+
+    def _ws(self):
+        if self._workspace is None:
+            self._workspace = torch.empty((96 << 20) // 4, dtype=f32, device=self.device)
+        return self._workspace
+
+    def _gemm(self, a0, w, **kw):
+        return ops.gemm_conv(a0, w, k_splits=0, workspace=self._ws(), **kw)
+
+    def _resnet(self, r, h, gnws):
+        B, H, W = h.shape[:3]
+        n1, raw = ops.groupnorm(h, r.g1, r.b1, groups=self.groups, eps=self.eps, silu=True, want_raw=r.shortcut,
+                                partials=gnws)
+        t1, _ = self._gemm(n1, r.w1, mode=ops.A_3X3, bias=r.bias1, want_f32=True)
+        n2, _ = ops.groupnorm(t1.view(B, H, W, r.cout), r.g2, r.b2, groups=self.groups, eps=self.eps, silu=True,
+                              partials=gnws)
+        if r.shortcut:
+            o, _ = self._gemm(n2, r.w2, mode=ops.A_3X3, a1=raw, bias=r.bias2, want_f32=True)
+        else:
+            o, _ = self._gemm(n2, r.w2, mode=ops.A_3X3, bias=r.bias2, residual=h, want_f32=True)
+        return o.view(B, H, W, r.cout)
+
+    def _attention(self, h, gnws):
+        at = self.attn
+        B, H, W, Cc = h.shape
+        T = H * W
+        n, _ = ops.groupnorm(h, at.g, at.b, groups=self.groups, eps=self.eps, silu=False, partials=gnws)
+        n2 = n.view(B * T, Cc)
+        _, q = self._gemm(n2, at.wq, bias=at.bq, want_bf16=True)
+        _, k = self._gemm(n2, at.wk, bias=at.bk, want_bf16=True)
+        o = torch.empty((B * T, Cc), dtype=bf16, device=h.device)
+        s = torch.empty((T, T), dtype=f32, device=h.device)
+        p = torch.empty((T, T), dtype=bf16, device=h.device)
+        vt = torch.empty((Cc, T), dtype=bf16, device=h.device)
+        for b in range(B):
+            sl = slice(b * T, (b + 1) * T)
+            self._gemm(at.wv, n2[sl], out_bf16=vt)             # V^T = W_v X^T  [C, T]
+            self._gemm(q[sl], k[sl], out_f32=s)                # S = Q K^T      [T, T]
+            ops.softmax_rows(s, Cc ** -0.5, out=p)
+            self._gemm(p, vt, out_bf16=o[sl])                  # O = P V        [T, C]
+        out, _ = self._gemm(o, at.wo, bias=at.bo, residual=h.view(B * T, Cc), want_f32=True)
+        return out.view(B, H, W, Cc)
+
+    def decode(self, z, return_dict: bool = True, generator=None, output_image: bool = False,
+               taps: Optional[dict] = None):
+        """z: [n, 4, h, w] latents ALREADY divided by scaling_factor -> [n, 3, 8h, 8w] in ~[-1, 1].
+        `output_image=True` instead returns the post-processed NHWC fp32 image in [0, 1]
+        (VaeImageProcessor.postprocess "np" fused into the conv_out kernel)."""
+        in_dtype = z.dtype
+        z = z.to(device=self.device, dtype=f32).contiguous()
+        B = z.shape[0]
+        gnws = ops.groupnorm_workspace(B, self.groups, self.device)
+        x = ops.vae_latent_prep(z, self.pq_w, self.pq_b, 1.0)
+        h, _ = ops.conv3x3_small_cin(x, self.w_in, self.b_in, nchw=False)
+        h = self._resnet(self.mid0, h, gnws)
+        h = self._attention(h, gnws)
+        h = self._resnet(self.mid1, h, gnws)
+        if taps is not None:
+            taps["mid"] = h.permute(0, 3, 1, 2).clone()
+        for i, blk in enumerate(self.up):
+            for r in blk.resnets:
+                h = self._resnet(r, h, gnws)
+            if blk.up is not None:
+                hu = ops.upsample2x(h)
+                o, _ = self._gemm(hu, blk.up[0], mode=ops.A_3X3, bias=blk.up[1], want_f32=True)
+                h = o.view(B, hu.shape[1], hu.shape[2], h.shape[3])
+            if taps is not None:
+                taps[f"up{i}"] = h.permute(0, 3, 1, 2).clone()
+        n, _ = ops.groupnorm(h, self.out_g, self.out_b, groups=self.groups, eps=self.eps, silu=True, partials=gnws)
+        img = ops.conv3x3_small_cout(n, self.w_out, self.b_out, postprocess=output_image)
+        if not output_image and in_dtype != f32:
+            img = img.to(in_dtype)
+        return DecoderOutput(img) if return_dict else (img,)
+
+    def to(self, *a, **k):
+        return self
+
+    def eval(self):
+        return self
+
+    def requires_grad_(self, flag: bool = False):
+        return self
