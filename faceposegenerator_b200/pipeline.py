@@ -65,6 +65,7 @@ class StableDiffusionPipeline:
         self._progress = {}
         self._graphs = {}
         self.use_cuda_graph = os.environ.get("IDB_CUDA_GRAPH", "1") != "0"
+        self.step_events = None    # set to a list to collect (start, end) CUDA events around every denoise step
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -179,7 +180,7 @@ class StableDiffusionPipeline:
             noise=torch.zeros((n, 4, h, w), dtype=f32, device=dev),
             x2=torch.zeros((rows, 4, h, w), dtype=f32, device=dev),
             t_dev=torch.zeros((rows,), dtype=f32, device=dev),
-            coef=torch.zeros((5,), dtype=f32, device=dev), graph=None)
+            coef=torch.zeros((5,), dtype=f32, device=dev), graph=None, launches_per_step=0)
 
     # ------------------------------------------------------------------ __call__
     @torch.no_grad()
@@ -251,11 +252,20 @@ class StableDiffusionPipeline:
                         st.latents.copy_(saved)
                         torch.cuda.synchronize(dev)
                         g = torch.cuda.CUDAGraph()
+                        from . import _lib
+                        n0 = _lib.launch_count
                         with torch.cuda.graph(g):
                             self._step_eager(st)
+                        st.launches_per_step = _lib.launch_count - n0
                         st.graph = g
                         st.latents.copy_(saved)
+                    if self.step_events is not None:
+                        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                        ev[0].record()
                     st.graph.replay()
+                    if self.step_events is not None:
+                        ev[1].record()
+                        self.step_events.append(ev)
                 else:
                     self._step_eager(st)
                 if collected is not None:

@@ -1,0 +1,286 @@
+"""T0 (CPU, no GPU): oracle vs known answers / golden vectors, host logic, C-ABI symbol check."""
+import math
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+TIMESTEPS_30 = [958, 925, 892, 859, 826, 793, 760, 727, 694, 661, 628, 595, 562, 529, 496, 463, 430, 397, 364, 331,
+                298, 265, 232, 199, 166, 133, 100, 67, 34, 1]
+# (t -> sqrt_acp, sqrt_1m_acp, c_x0, c_xt, sigma)
+COEF = {958: (0.08680304, 0.99622548, 0.03215177, 0.83015662, 0.55242407),
+        925: (0.10421189, 0.99455512, 0.03676465, 0.83679783, 0.54037559),
+        34: (0.98380959, 0.17921701, 0.94775540, 0.05223803, 0.04020363),
+        1: (0.99914765, 0.04127926, 1.0, 0.0, 1.0e-10)}
+
+
+def test_parameter_counts():
+    from faceposegenerator_b200 import weights as w
+    assert sum(math.prod(s) for _, s in w.unet_manifest()) == 865_910_724
+    assert sum(math.prod(s) for _, s in w.vae_decoder_manifest()) == 49_490_199
+    lm = w.lora_manifest()
+    assert len(lm) == 128 and sum(4 * (a + b) for _, a, b in lm) == 829_952
+    from faceposegenerator_b200.text import text_manifest
+    assert sum(math.prod(s) for _, s in text_manifest()) == 340_387_840
+    names = [n for n, _ in w.unet_manifest()]
+    assert len(names) == len(set(names))
+    assert sum(1 for n in names if re.search(r"resnets\.\d+\.conv1\.weight$", n)) == 22
+    assert sum(1 for n in names if n.endswith("proj_in.weight")) == 16
+
+
+@pytest.mark.parametrize("which", ["oracle", "product"])
+def test_scheduler_known_answers(which):
+    if which == "oracle":
+        from oracle.sd21 import DDPMSchedulerRef
+        s = DDPMSchedulerRef()
+        s.set_timesteps(30)
+    else:
+        from faceposegenerator_b200 import DDPMScheduler
+        s = DDPMScheduler.from_pretrained("stabilityai/stable-diffusion-2-1-base", subfolder="scheduler")
+        s.set_timesteps(30)
+    assert s.timesteps.tolist() == TIMESTEPS_30
+    assert abs(float(s.betas[0]) - 0.00085) < 1e-9 and abs(float(s.betas[999]) - 0.012) < 1e-8
+    for t, a in ((0, 0.99914998), (1, 0.99829602), (34, 0.96788126), (925, 0.01086012), (958, 0.00753477), (999, 0.00466010)):
+        assert abs(float(s.alphas_cumprod[t]) - a) < 2e-7
+    for t, ref in COEF.items():
+        got = s.coefficients(t)
+        for g, r in zip(got, ref):
+            assert abs(g - r) < 2e-7 * max(1.0, abs(r)) + 1e-12, (t, got, ref)
+    assert s.previous_timestep(958) == 925 and s.previous_timestep(1) == -1
+    s2 = type(s)()
+    assert s2.previous_timestep(500) == 499   # training use: no set_timesteps (train_ID-Booth.py:1081)
+
+
+def test_sinusoid_known_answers():
+    from oracle.sd21 import timestep_sinusoid
+    e = timestep_sinusoid(torch.tensor([958.0]))[0]
+    ref_cos = [-0.98279631, 0.93290263, 0.76819366, -0.23576230]
+    ref_sin = [0.18469287, -0.36012876, -0.64021748, 0.97181076]
+    assert torch.allclose(e[:4], torch.tensor(ref_cos), atol=2e-4)
+    assert torch.allclose(e[160:164], torch.tensor(ref_sin), atol=2e-4)
+
+
+def test_oracle_scheduler_step_matches_closed_form():
+    from oracle.sd21 import DDPMSchedulerRef
+    s = DDPMSchedulerRef()
+    s.set_timesteps(30)
+    g = torch.Generator().manual_seed(0)
+    x, eps, z = (torch.randn(2, 4, 8, 8, generator=g, dtype=torch.float64) for _ in range(3))
+    prev, x0 = s.step(eps, 958, x, z)
+    sa, sb, c0, ct, sg = COEF[958]
+    x0_ref = (x - sb * eps) / sa
+    assert torch.allclose(x0, x0_ref, rtol=1e-6)
+    assert torch.allclose(prev, c0 * x0_ref + ct * x + sg * z, rtol=1e-5, atol=1e-6)
+    # add_noise / training-mode previous timestep
+    n = s.add_noise(x.float(), z.float(), torch.tensor([10, 900]))
+    a = s.alphas_cumprod[torch.tensor([10, 900])].view(2, 1, 1, 1)
+    assert torch.allclose(n, a.sqrt() * x.float() + (1 - a).sqrt() * z.float(), atol=1e-6)
+
+
+TINY = dict(in_channels=4, out_channels=4, block_out_channels=(32, 64, 64, 64), down_attn=(True, True, True, False),
+            up_attn=(False, True, True, True), layers_per_block=2, head_dim=8, cross_attention_dim=48,
+            norm_num_groups=8, norm_eps=1e-5, time_embed_in=32)
+TINY_M = dict(sample_size=8, in_channels=4, out_channels=4, block_out_channels=(32, 64, 64, 64),
+              down_block_types=("CrossAttnDownBlock2D",) * 3 + ("DownBlock2D",),
+              up_block_types=("UpBlock2D",) + ("CrossAttnUpBlock2D",) * 3, layers_per_block=2,
+              cross_attention_dim=48, norm_num_groups=8, norm_eps=1e-5)
+
+
+def _tiny():
+    from faceposegenerator_b200 import weights as w
+    sd = {k: v.double() for k, v in w.random_state_dict(w.unet_manifest(TINY_M), 3).items()}
+    lora = {k: (d.double(), (u * 20).double(), s) for k, (d, u, s) in w.random_lora(TINY_M, seed=3).items()}
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 4, 16, 16, generator=g, dtype=torch.float64)
+    ctx = torch.randn(2, 5, 48, generator=g, dtype=torch.float64)
+    return sd, lora, x, ctx
+
+
+def test_oracle_lora_metamorphic_fp64():
+    """merged == unmerged (peft semantics); B == 0 is an exact no-op; rows are independent."""
+    from oracle import sd21
+    sd, lora, x, ctx = _tiny()
+    with torch.no_grad():
+        base = sd21.unet_forward(sd, x, 500, ctx, None, TINY)
+        un = sd21.unet_forward(sd, x, 500, ctx, lora, TINY)
+        me = sd21.unet_forward(sd21.merge_lora(sd, lora), x, 500, ctx, None, TINY)
+        zero = {k: (d, torch.zeros_like(u), s) for k, (d, u, s) in lora.items()}
+        z = sd21.unet_forward(sd, x, 500, ctx, zero, TINY)
+        row0 = sd21.unet_forward(sd, x[:1], 500, ctx[:1], lora, TINY)
+    assert (un - me).abs().max() < 1e-10
+    assert (un - base).abs().max() > 1e-4
+    assert torch.equal(z, base)
+    assert (row0 - un[:1]).abs().max() < 1e-10
+
+
+def test_oracle_cfg_scale_one_is_conditional_branch():
+    from oracle import sd21
+    sd, lora, _, _ = _tiny()
+    sd = {k: v.float() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(1)
+    tape = torch.randn(4, 1, 4, 16, 16, generator=g)
+    pe, ne = torch.randn(1, 5, 48, generator=g), torch.randn(1, 5, 48, generator=g)
+    with torch.no_grad():
+        lat, eps = sd21.denoise_loop(sd, None, pe, ne, tape, num_steps=3, guidance_scale=1.0, cfg=TINY)
+        cond = sd21.unet_forward(sd, tape[0], 667, pe, None, TINY)
+    assert torch.allclose(eps[0], cond, atol=1e-5)
+    assert lat.shape == (4, 1, 4, 16, 16)
+
+
+def test_iresnet_oracle_vs_reference_golden():
+    """The one PINNED oracle: outputs of /root/reference/ArcFace_files/backbones/iresnet.py itself
+    (fixture made by tests/golden/make_iresnet_golden.py)."""
+    from oracle.iresnet import iresnet_forward, keyed_state_dict
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "iresnet100_golden.pt"))
+    # rebuild the key/shape set without importing the reference: shapes follow iresnet.py:67-162
+    shapes = {}
+
+    def bn(p, c):
+        shapes.update({p + ".weight": (c,), p + ".bias": (c,), p + ".running_mean": (c,), p + ".running_var": (c,),
+                       p + ".num_batches_tracked": ()})
+    shapes["conv1.weight"] = (64, 3, 3, 3)
+    bn("bn1", 64)
+    shapes["prelu.weight"] = (64,)
+    inp = 64
+    for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), (3, 13, 30, 3)), start=1):
+        for b in range(nblk):
+            p = f"layer{li}.{b}"
+            bn(p + ".bn1", inp)
+            shapes[p + ".conv1.weight"] = (planes, inp, 3, 3)
+            bn(p + ".bn2", planes)
+            shapes[p + ".prelu.weight"] = (planes,)
+            shapes[p + ".conv2.weight"] = (planes, planes, 3, 3)
+            bn(p + ".bn3", planes)
+            if b == 0:
+                shapes[p + ".downsample.0.weight"] = (planes, inp, 1, 1)
+                bn(p + ".downsample.1", planes)
+            inp = planes
+    bn("bn2", 512)
+    shapes["fc.weight"], shapes["fc.bias"] = (512, 25088), (512,)
+    bn("features", 512)
+    assert len(shapes) == gold["n_state"] == 925
+    sd = keyed_state_dict({k: torch.zeros(s, dtype=torch.long if k.endswith("tracked") else torch.float32)
+                           for k, s in shapes.items()}, seed=0)
+    assert sum(v.numel() for k, v in sd.items() if "running" not in k and "tracked" not in k) == gold["n_params"] == 65_156_160
+    x = torch.randn(2, 3, 112, 112, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        y = iresnet_forward(sd, x)
+    assert torch.allclose(y, gold["embedding"], rtol=1e-4, atol=1e-3 * float(gold["embedding"].abs().mean()))
+
+
+def test_lora_file_round_trip(tmp_path):
+    from faceposegenerator_b200 import weights as w
+    lora = w.random_lora(seed=5)
+    d = tmp_path / "checkpoint-31-6400"
+    w.save_lora_weights(str(d), lora)
+    back = w.load_lora_state(str(d))
+    assert set(back) == set(lora) and len(back) == 128
+    for k in lora:
+        assert torch.equal(back[k][0], lora[k][0]) and torch.equal(back[k][1], lora[k][1]) and back[k][2] == 1.0
+    # peft / legacy spellings and alpha scaling
+    from safetensors.torch import save_file
+    k0 = "down_blocks.0.attentions.0.transformer_blocks.0.attn1"
+    t = {f"unet.{k0}.to_q.lora_A.weight": torch.ones(4, 320), f"unet.{k0}.to_q.lora_B.weight": torch.ones(320, 4),
+         f"unet.{k0}.to_q.alpha": torch.tensor(8.0),
+         f"unet.{k0}.processor.to_k_lora.down.weight": torch.ones(4, 320),
+         f"unet.{k0}.processor.to_k_lora.up.weight": torch.ones(320, 4),
+         f"unet.{k0}.to_out.0.lora.down.weight": torch.ones(4, 320), f"unet.{k0}.to_out.0.lora.up.weight": torch.ones(320, 4),
+         "text_encoder.text_model.encoder.layers.0.self_attn.q_proj.lora.down.weight": torch.ones(4, 8)}
+    save_file(t, str(tmp_path / "alt.safetensors"))
+    alt = w.load_lora_state(str(tmp_path / "alt.safetensors"))
+    assert set(alt) == {k0 + ".to_q", k0 + ".to_k", k0 + ".to_out.0"}
+    assert alt[k0 + ".to_q"][2] == 2.0 and alt[k0 + ".to_k"][2] == 1.0
+    with pytest.raises(FileNotFoundError):
+        w.load_lora_state(str(tmp_path / "missing"))
+
+
+def test_packing_layouts():
+    from faceposegenerator_b200.packing import interleave_geglu, pack_conv_weight, pack_lora
+    w = torch.arange(64 * 2 * 3 * 3, dtype=torch.float32).reshape(2, 64, 3, 3) / 1000
+    p = pack_conv_weight(w)
+    assert p.shape == (2, 576) and p.dtype == torch.bfloat16
+    assert torch.equal(p[1, 5 * 64 + 7], w[1, 7, 1, 2].to(torch.bfloat16))   # tap (dy=1,dx=2) = 5
+    wg = torch.arange(64.0)[:, None].repeat(1, 4)
+    wi, bi = interleave_geglu(wg, torch.arange(64.0))
+    assert wi[:, 0].tolist()[:48] == list(range(16)) + list(range(32, 48)) + list(range(16, 32))
+    assert torch.equal(bi, wi[:, 0])
+    ld, lu = pack_lora([(torch.ones(4, 64), torch.ones(320, 4), 2.0), None], seg_n=320, k=64)
+    assert ld.shape == (32, 64) and lu.shape == (640, 4)
+    assert float(ld[:4].float().sum()) == 256 and float(ld[4:].float().abs().sum()) == 0
+    assert float(lu[:320].sum()) == 2.0 * 320 * 4 and float(lu[320:].abs().sum()) == 0
+    assert pack_lora([None, None]) == (None, None)
+
+
+def test_reference_script_imports_resolve():
+    """Every import at /root/reference/inference_ID-Booth.py:1-15 resolves through compat/ (no
+    GPU needed), and the pipeline object refuses to run without CUDA instead of falling back."""
+    import subprocess
+    code = ("from diffusers import StableDiffusionPipeline, DPMSolverMultistepScheduler, DDPMScheduler, "
+            "AutoPipelineForText2Image\nfrom accelerate.utils import set_seed\nimport torch\n"
+            "from torchvision.utils import save_image\nset_seed(0)\n"
+            "p = StableDiffusionPipeline.from_pretrained('stabilityai/stable-diffusion-2-1-base', torch_dtype=torch.float16)\n"
+            "p.scheduler = DDPMScheduler.from_pretrained('stabilityai/stable-diffusion-2-1-base', subfolder='scheduler')\n"
+            "p.set_progress_bar_config(disable=True)\nprint('ok', type(p.scheduler).__name__)\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "compat"), ROOT]), CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and "ok DDPMScheduler" in r.stdout, r.stderr[-2000:]
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    from faceposegenerator_b200 import StableDiffusionPipeline, ops
+    p = StableDiffusionPipeline.from_pretrained("stabilityai/stable-diffusion-2-1-base")
+    with pytest.raises(RuntimeError):
+        p.to("cuda:0")
+    with pytest.raises(RuntimeError):
+        p(prompt="x")
+    with pytest.raises(RuntimeError):
+        ops.layernorm(torch.zeros(4, 8), torch.ones(8), torch.zeros(8))
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """include/idb.h <-> libidb_b200.so <-> the ctypes binding agree (no compute calls)."""
+    import ctypes
+    from faceposegenerator_b200 import _lib
+    from faceposegenerator_b200.csrc import build
+    lib_path = build.build()
+    header = open(os.path.join(ROOT, "include", "idb.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|size_t)\s+(idb_\w+)\s*\(", header, flags=re.M))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().idb_version() == 100
+    # struct layouts: what gcc computes from include/idb.h == what the ctypes binding assumes
+    import subprocess
+    import tempfile
+    structs = {"idb_gemm_conv_args": _lib.GemmConvArgs, "idb_attention_args": _lib.AttentionArgs,
+               "idb_groupnorm_args": _lib.GroupNormArgs, "idb_time_embed_args": _lib.TimeEmbedArgs}
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "idb.h"\nint main(void){\n'
+    for cname, cls in structs.items():
+        prog += f'printf("{cname} %zu\\n", sizeof({cname}));\n'
+        for fname, _ in cls._fields_:
+            prog += f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));\n'
+    prog += "return 0;}\n"
+    with tempfile.TemporaryDirectory() as td:
+        src, exe = os.path.join(td, "l.c"), os.path.join(td, "l")
+        open(src, "w").write(prog)
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        got = dict(line.split() for line in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_oracle_is_not_imported_by_the_product():
+    pkg = os.path.join(ROOT, "faceposegenerator_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py") and fn != "selfcheck.py":
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn

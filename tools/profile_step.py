@@ -1,0 +1,27 @@
+"""One eager UNet forward (B=8 rows, 64x64 latent, LoRA) for ncu: 2 warm-up forwards, then 1 profiled.
+Kernel launches before the profiled forward: 16 (encode_context) + 2 * L, printed on stderr."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from faceposegenerator_b200 import _lib  # noqa: E402
+from faceposegenerator_b200.unet import UNet2DConditionModel  # noqa: E402
+from faceposegenerator_b200.weights import random_lora  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+dev = torch.device("cuda:0")
+unet = UNet2DConditionModel.from_random(0, device=dev)
+unet.set_lora(random_lora(seed=0))
+x = torch.randn(B, 4, 64, 64, device=dev)
+ctx = torch.randn(B, 77, 1024, device=dev)
+t = torch.full((B,), 500.0, device=dev)
+context = unet.encode_context(ctx)
+n0 = _lib.launch_count
+for i in range(3):
+    unet.forward(x, t, context=context)
+    torch.cuda.synchronize()
+    if i == 0:
+        print(f"launches per forward: {_lib.launch_count - n0}; before profiled forward: {n0 + 2 * (_lib.launch_count - n0)}",
+              file=sys.stderr)
