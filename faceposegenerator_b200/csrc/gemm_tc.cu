@@ -13,6 +13,12 @@
 // [B, H/2, 2, W/2, 2*C] of the same tensor.  A Linear is the 1x1 "image" [1, 1, M, K].
 // A fused rank-r LoRA rides along as 16 extra UMMA N-columns (x A^T kept in TMEM) and is
 // applied as 4-16 FMAs per output in the epilogue -- base weights are never touched.
+//
+// CG = 2 (`cta_group::2`): two CTAs of a cluster (an SM pair) share one 256 x BLOCK_N tile.  Each CTA
+// TMA-loads its own 128 A rows and HALF of the B tile; the leader issues tcgen05.mma.cta_group::2
+// which reads both CTAs' smem and writes rows 0-127 / 128-255 of D into the two CTAs' TMEM.  Operand
+// bytes per MAC drop by (128 + N/2) / (128 + N): the big convs are L2->SM bandwidth bound otherwise.
+#include <cstdlib>
 #include <string>
 
 #include "../../include/idb.h"
@@ -28,9 +34,12 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int TMEM_BUF_STRIDE = 256;
+constexpr int EPI_STG_F32 = 32 * 32 * 4;                            // per-warp fp32 staging chunk (SWIZZLE_128B rows of 128 B)
+constexpr int EPI_STG_B16 = 32 * 32 * 2;                            // per-warp bf16 staging chunk (dense rows of 64 B)
+constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * (EPI_STG_F32 + EPI_STG_B16);  // 49,152 B
 
 struct GemmParams {
-  CUtensorMap tmA0, tmA1, tmW, tmL;
+  CUtensorMap tmA0, tmA1, tmW, tmL, tmOutF, tmOutB;   // tmOut*: 4-D [N_out, Wo, Ho, B] store maps (32-row boxes)
   int mode0, cpb0, c0, nkb0, nkb1;
   int Ho, Wo, B;
   int BW, BH, BB;
@@ -45,17 +54,22 @@ struct GemmParams {
   const float* lora_up;
   int lora_rank_pad, lora_seg_n;
   int flags;
+  int debug;  // profiling only (IDB_GEMM_DEBUG): 1 = no MMA issue, 2 = no TMA loads
   float* out_f32;
   __nv_bfloat16* out_bf16;
   float* workspace;
 };
 
-template <int BLOCK_N, int STAGES, bool LORA>
+template <int BLOCK_N, int STAGES, bool LORA, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
-  constexpr int B_TILE_BYTES = UMMA_N * BLOCK_K * 2;
+  constexpr int B_ROWS = UMMA_N / CG;                 // B rows this CTA stages (half the tile in a pair)
+  constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-  constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, UMMA_N, 0, 0);
+  constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M * CG, UMMA_N, 0, 0);
+  static_assert(CG == 1 || !LORA, "fused LoRA runs on the 1-CTA kernel");
+  static_assert(B_ROWS % 8 == 0, "B tile must be whole 8-row swizzle groups");
+  constexpr int STG_OFFSET = STAGES * STAGE_BYTES + 1024;   // barriers live in the first 1 KiB after the ring (keeps 1024-B alignment)
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
   static_assert(UMMA_N <= TMEM_BUF_STRIDE, "accumulator does not fit its TMEM buffer");
   static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment for SWIZZLE_128B");
@@ -70,6 +84,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;   // 0 = leader of the pair
+  const int unit = blockIdx.x / CG;                            // CTA (CG=1) or CTA pair (CG=2) index
+  const int num_units = gridDim.x / CG;
 
   if (warp == NUM_EPI_WARPS && lane == 0) {
     tma_prefetch_desc(&p.tmA0);
@@ -77,70 +94,100 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     if (p.nkb1 > 0) tma_prefetch_desc(&p.tmA1);
     if (LORA) tma_prefetch_desc(&p.tmL);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], CG);     // one producer arrival per CTA of the pair (leader's barrier is the one used)
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[b], NUM_EPI_WARPS * CG);
     }
     mbar_fence_init();
   }
-  if (warp == NUM_EPI_WARPS + 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == NUM_EPI_WARPS + 1) {
+    if (CG == 2) tmem_alloc2<TMEM_COLS>(tmem_slot);
+    else tmem_alloc<TMEM_COLS>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // peer barriers must be initialised before remote arrives / multicast commits
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int total_tiles = p.n_tiles_m * p.n_tiles_n * p.k_splits;
+  const int m_units = (p.n_tiles_m + CG - 1) / CG;   // M tiles per unit: a pair covers 2 consecutive M blocks
+  const int total_tiles = m_units * p.n_tiles_n * p.k_splits;
   const int nkb_total = p.nkb0 + p.nkb1;
 
   if (warp == NUM_EPI_WARPS) {
     // ================================================================ TMA producer
-    if (lane == 0) {
+    // The whole warp runs the loop convergently on warp-uniform values (so addresses / coordinates
+    // live in uniform registers); one elected lane issues the TMA and barrier operations.
+    {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const uint32_t smem_base = smem_u32(smem);
+      for (int tile = unit; tile < total_tiles; tile += num_units) {
         int t = tile;
         const int n_blk = t % p.n_tiles_n;
         t /= p.n_tiles_n;
         const int ks = t % p.k_splits;
-        const int m_blk = t / p.k_splits;
+        const int m_blk = (t / p.k_splits) * CG + rank;
         const int tx = m_blk % p.tiles_x;
         const int ty = (m_blk / p.tiles_x) % p.tiles_y;
-        const int tb = m_blk / (p.tiles_x * p.tiles_y);
+        const int tb = m_blk / (p.tiles_x * p.tiles_y);   // >= number of batch tiles for a padding block: TMA zero-fills
         const int x0 = tx * p.BW, y0 = ty * p.BH, b0 = tb * p.BB;
-        const int n0 = n_blk * BLOCK_N;
+        const int n0 = n_blk * BLOCK_N + rank * B_ROWS;
         const int kb_begin = ks * p.kb_per_split;
         const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
+        // running (tap, channel-block) counters instead of a division per k-block
+        int tap = (kb_begin < p.nkb0) ? kb_begin / p.cpb0 : 0;
+        int cbi = (kb_begin < p.nkb0) ? kb_begin - tap * p.cpb0 : 0;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          uint8_t* sb = sa + A_TILE_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          if (kb < p.nkb0) {
-            const int tap = kb / p.cpb0;
-            const int cb = (kb - tap * p.cpb0) * BLOCK_K;
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint32_t sb = sa + A_TILE_BYTES;
+          const uint32_t fb = smem_base + STAGES * STAGE_BYTES + stage * 8;   // &full_bar[stage]
+          int c0, c1, c2, c3, c4 = 0;
+          bool five = false;
+          const bool seg1 = kb >= p.nkb0;
+          if (!seg1) {
+            const int cb = cbi * BLOCK_K;
             if (p.mode0 == IDB_A_1X1) {
-              tma_load_4d(sa, &p.tmA0, &full_bar[stage], cb, x0, y0, b0);
+              c0 = cb, c1 = x0, c2 = y0, c3 = b0;
             } else {
-              const int dy = tap / 3, dx = tap - dy * 3;
+              const int dy = (tap * 11) >> 5, dx = tap - dy * 3;   // tap / 3 for tap in [0, 9)
               if (p.mode0 == IDB_A_3X3) {
-                tma_load_4d(sa, &p.tmA0, &full_bar[stage], cb, x0 + dx - 1, y0 + dy - 1, b0);
+                c0 = cb, c1 = x0 + dx - 1, c2 = y0 + dy - 1, c3 = b0;
               } else {  // stride 2: input (2*yo + dy - 1, 2*xo + dx - 1) in the [B, H/2, 2, W/2, 2C] view
                 const int px = (dx == 1) ? 0 : 1, py = (dy == 1) ? 0 : 1;
                 const int ox = (dx == 0) ? -1 : 0, oy = (dy == 0) ? -1 : 0;
-                tma_load_5d(sa, &p.tmA0, &full_bar[stage], px * p.c0 + cb, x0 + ox, py, y0 + oy, b0);
+                five = true;
+                c0 = px * p.c0 + cb, c1 = x0 + ox, c2 = py, c3 = y0 + oy, c4 = b0;
               }
             }
+            if (++cbi == p.cpb0) cbi = 0, ++tap;
           } else {
-            tma_load_4d(sa, &p.tmA1, &full_bar[stage], (kb - p.nkb0) * BLOCK_K, x0, y0, b0);
+            c0 = (kb - p.nkb0) * BLOCK_K, c1 = x0, c2 = y0, c3 = b0;
           }
-          tma_load_2d(sb, &p.tmW, &full_bar[stage], kb * BLOCK_K, n0);
-          if (LORA) {
-            const int seg = n0 / p.lora_seg_n;
-            tma_load_2d(sb + BLOCK_N * BLOCK_K * 2, &p.tmL, &full_bar[stage], kb * BLOCK_K, seg * 16);
+          const CUtensorMap* tmA = seg1 ? &p.tmA1 : &p.tmA0;
+          if (elect_one()) {
+            if (p.debug == 2 || p.debug == 3) {  // feed-rate experiment: signal the stage without moving data
+              if (CG == 1 || rank == 0) mbar_expect_tx_a(fb, 0);
+              else mbar_arrive_remote_a(fb, 0);
+            } else if (CG == 1) {
+              mbar_expect_tx_a(fb, STAGE_BYTES);
+              if (five) tma_load_5d_a(sa, tmA, fb, c0, c1, c2, c3, c4);
+              else tma_load_4d_a(sa, tmA, fb, c0, c1, c2, c3);
+              tma_load_2d_a(sb, &p.tmW, fb, kb * BLOCK_K, n0);
+              if (LORA) tma_load_2d_a(sb + BLOCK_N * BLOCK_K * 2, &p.tmL, fb, kb * BLOCK_K, (n0 / p.lora_seg_n) * 16);
+            } else {
+              if (five) tma2_load_5d_a(sa, tmA, fb, c0, c1, c2, c3, c4);
+              else tma2_load_4d_a(sa, tmA, fb, c0, c1, c2, c3);
+              tma2_load_2d_a(sb, &p.tmW, fb, kb * BLOCK_K, n0);
+              if (rank == 0) mbar_expect_tx_a(fb, 2 * STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
+              else mbar_arrive_remote_a(fb, 0);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -149,56 +196,86 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       }
     }
   } else if (warp == NUM_EPI_WARPS + 1) {
-    // ================================================================ MMA issuer
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int ks = (tile / p.n_tiles_n) % p.k_splits;
-      const int kb_begin = ks * p.kb_per_split;
-      const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
-      const int buf = it & 1;
-      mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + buf * TMEM_BUF_STRIDE;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
+    // ================================================================ MMA issuer (leader CTA only in a pair)
+    if (rank == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      const uint32_t smem_base = smem_u32(smem);
+      const uint64_t desc_hi = umma_smem_desc_sw128(0);
+      for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
+        const int ks = (tile / p.n_tiles_n) % p.k_splits;
+        const int kb_begin = ks * p.kb_per_split;
+        const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
+        const int buf = it & 1;
+        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        if (lane == 0) {  // a single fixed thread issues every MMA and commit of this CTA
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t adesc = umma_smem_desc_sw128(sa);
-          const uint64_t bdesc = umma_smem_desc_sw128(sa + A_TILE_BYTES);
-#pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // +32 bytes (>>4 = 2) per UMMA_K=16 step inside the 128B swizzle atom
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb > kb_begin || k > 0) ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base + buf * TMEM_BUF_STRIDE;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          // descriptors are built convergently from warp-uniform values; one elected lane issues
+          const uint32_t sa = smem_base + stage * STAGE_BYTES;
+          const uint64_t adesc = desc_hi | static_cast<uint64_t>((sa >> 4) & 0x3FFF);
+          const uint64_t bdesc = desc_hi | static_cast<uint64_t>(((sa + A_TILE_BYTES) >> 4) & 0x3FFF);
+          const uint32_t eb = smem_base + STAGES * STAGE_BYTES + (STAGES + stage) * 8;        // &empty_bar[stage]
+          const uint32_t tf = smem_base + STAGES * STAGE_BYTES + (2 * STAGES + buf) * 8;      // &tmem_full[buf]
+          const uint32_t acc0 = (kb > kb_begin) ? 1u : 0u;
+          if (elect_one()) {
+            if (p.debug != 1 && p.debug != 3) {
+              if (CG == 1) {
+                umma_bf16(d_tmem, adesc, bdesc, IDESC, acc0);
+                umma_bf16(d_tmem, adesc + 2, bdesc + 2, IDESC, 1u);   // +32 B per UMMA_K=16 step in the swizzle atom
+                umma_bf16(d_tmem, adesc + 4, bdesc + 4, IDESC, 1u);
+                umma_bf16(d_tmem, adesc + 6, bdesc + 6, IDESC, 1u);
+              } else {
+                umma2_bf16(d_tmem, adesc, bdesc, IDESC, acc0);
+                umma2_bf16(d_tmem, adesc + 2, bdesc + 2, IDESC, 1u);
+                umma2_bf16(d_tmem, adesc + 4, bdesc + 4, IDESC, 1u);
+                umma2_bf16(d_tmem, adesc + 6, bdesc + 6, IDESC, 1u);
+              }
+            }
+            if (CG == 1) {
+              umma_commit_a(eb);  // frees the smem slot once these MMAs retire
+              if (kb == kb_end - 1) umma_commit_a(tf);
+            } else {
+              umma2_commit_mc_a(eb);  // ... in both CTAs of the pair
+              if (kb == kb_end - 1) umma2_commit_mc_a(tf);
+            }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-          if (kb == kb_end - 1) umma_commit(&tmem_full[buf]);
-        }
-        __syncwarp();
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
   } else {
     // ================================================================ epilogue warps
+    // lane = accumulator row.  TMEM -> registers -> (bias, time-embedding row vector, LoRA up-projection,
+    // GEGLU, fp32 residual) -> per-warp smem staging chunk (32 rows x 32 columns) -> ONE TMA store per
+    // chunk (4-D box over the NHWC output; rows outside the image are clipped by the TMA unit).
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int half = warp >> 2;    // which interleaved set of 32-column chunks
     const int r = quarter * 32 + lane;
     const int rx = r % p.BW;
     const int ry = (r / p.BW) % p.BH;
     const int rb = r / (p.BW * p.BH);
+    const int r0 = quarter * 32;   // first row of this warp's box inside the tile rectangle
+    const int bx0 = r0 % p.BW, by0 = (r0 / p.BW) % p.BH, bb0 = r0 / (p.BW * p.BH);
     const bool geglu = (p.flags & IDB_EPI_GEGLU) != 0;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t stg_f = smem_base + STG_OFFSET + warp * EPI_STG_F32;
+    const uint32_t stg_b = smem_base + STG_OFFSET + NUM_EPI_WARPS * EPI_STG_F32 + warp * EPI_STG_B16;
+    const int sw = lane & 7;       // SWIZZLE_128B phase of this lane's 128-byte fp32 staging row
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
       int t = tile;
       const int n_blk = t % p.n_tiles_n;
       t /= p.n_tiles_n;
       const int ks = t % p.k_splits;
-      const int m_blk = t / p.k_splits;
+      const int m_blk = (t / p.k_splits) * CG + rank;
       const int tx = m_blk % p.tiles_x;
       const int ty = (m_blk / p.tiles_x) % p.tiles_y;
       const int tb = m_blk / (p.tiles_x * p.tiles_y);
@@ -224,19 +301,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       for (int chunk = half; chunk < BLOCK_N / 32; chunk += 2) {
         const int col = n0 + chunk * 32;
         uint32_t v[32];
-        __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-row predicated body
+        if (p.debug == 5) continue;   // profiling: no TMEM read, no stores
         IDB_TMEM_LD_X32(t_row + chunk * 32, v);
         tmem_ld_wait();
-        if (row_ok && col < p.N) {
+        if (col >= p.N || p.debug == 4) continue;   // warp-uniform (debug 4: TMEM read only)
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
 
-        if (p.k_splits > 1) {  // raw partial sums; the finalize kernel applies the epilogue
-          float4* dst = reinterpret_cast<float4*>(p.workspace + (static_cast<long long>(ks) * p.M + orow) * p.N + col);
+        if (p.k_splits > 1) {  // raw partial sums (tiny-M layers only); the finalize kernel applies the epilogue
+          if (row_ok) {
+            float4* dst = reinterpret_cast<float4*>(p.workspace + (static_cast<long long>(ks) * p.M + orow) * p.N + col);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        } else {
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+          }
+          continue;
+        }
         if (p.bias != nullptr) {
           const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
@@ -245,7 +325,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             acc[4 * j] += bv.x, acc[4 * j + 1] += bv.y, acc[4 * j + 2] += bv.z, acc[4 * j + 3] += bv.w;
           }
         }
-        if (p.rowvec != nullptr) {
+        if (p.rowvec != nullptr && row_ok) {
           const float4* rp = reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(b) * p.rowvec_ld + col);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -256,8 +336,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         if (LORA) {
           const float* up = p.lora_up + static_cast<long long>(col) * p.lora_rank_pad;
           for (int r4 = 0; r4 < p.lora_rank_pad; r4 += 4) {
-            // lt[] index must be compile-time to stay in registers: unrolled select over r4
-            float t0, t1, t2, t3;
+            float t0, t1, t2, t3;  // lt[] index must be compile-time to stay in registers
             if (r4 == 0) t0 = lt[0], t1 = lt[1], t2 = lt[2], t3 = lt[3];
             else if (r4 == 4) t0 = lt[4], t1 = lt[5], t2 = lt[6], t3 = lt[7];
             else if (r4 == 8) t0 = lt[8], t1 = lt[9], t2 = lt[10], t3 = lt[11];
@@ -269,69 +348,79 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
           }
         }
-        if (geglu) {
-          // chunk = [a(16) | g(16)] -> 16 outputs at column col/2
-          const int ocol = col >> 1;
-          float o[16];
+        int nc = 32, ocol = col;
+        if (geglu) {  // chunk = [a(16) | g(16)] -> 16 outputs at column col/2
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = acc[j] * gelu_erf_f(acc[16 + j]);
-          if (p.residual != nullptr) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + orow * p.N_out + ocol);
+          for (int j = 0; j < 16; ++j) acc[j] = acc[j] * gelu_erf_f(acc[16 + j]);
+          nc = 16, ocol = col >> 1;
+        }
+        if (p.residual != nullptr && row_ok) {
+          const float4* rp = reinterpret_cast<const float4*>(p.residual + orow * p.N_out + ocol);
+          if (geglu) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float4 rv = __ldg(rp + j);
-              o[4 * j] += rv.x, o[4 * j + 1] += rv.y, o[4 * j + 2] += rv.z, o[4 * j + 3] += rv.w;
+              acc[4 * j] += rv.x, acc[4 * j + 1] += rv.y, acc[4 * j + 2] += rv.z, acc[4 * j + 3] += rv.w;
             }
-          }
-          if (p.out_f32 != nullptr) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32 + orow * p.N_out + ocol);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          }
-          if (p.out_bf16 != nullptr) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + orow * p.N_out + ocol);
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              dst[j] = make_uint4(pack_bf16x2(o[8 * j], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
-                                  pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
-          }
-        } else {
-          if (p.residual != nullptr) {
-            const float4* rp = reinterpret_cast<const float4*>(p.residual + orow * p.N_out + col);
+          } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 rv = __ldg(rp + j);
               acc[4 * j] += rv.x, acc[4 * j + 1] += rv.y, acc[4 * j + 2] += rv.z, acc[4 * j + 3] += rv.w;
             }
           }
-          if (p.out_f32 != nullptr) {
-            float4* dst = reinterpret_cast<float4*>(p.out_f32 + orow * p.N_out + col);
+        }
+        // ---- stage (previous TMA stores of this warp must have finished READING the staging chunk)
+        if (lane == 0) tma_store_wait_read();
+        __syncwarp();
+        if (p.out_f32 != nullptr) {   // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row `lane` lands at j ^ (lane & 7)
+          const uint32_t row = stg_f + lane * 128;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-          }
-          if (p.out_bf16 != nullptr) {
-            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + orow * p.N_out + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(pack_bf16x2(acc[8 * j], acc[8 * j + 1]), pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3]),
-                                  pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5]), pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]));
+          for (int j = 0; j < 8; ++j) {
+            if (j * 4 < nc)
+              asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((j ^ sw) << 4)), "f"(acc[4 * j]),
+                           "f"(acc[4 * j + 1]), "f"(acc[4 * j + 2]), "f"(acc[4 * j + 3])
+                           : "memory");
           }
         }
-        }  // !split-K
-        }  // row_ok
+        if (p.out_bf16 != nullptr) {  // dense rows of nc * 2 bytes
+          const uint32_t row = stg_b + lane * (nc * 2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (j * 8 < nc)
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (j << 4)),
+                           "r"(pack_bf16x2(acc[8 * j], acc[8 * j + 1])), "r"(pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3])),
+                           "r"(pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5])), "r"(pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]))
+                           : "memory");
+          }
+        }
+        fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          const int cx = tx * p.BW + bx0, cy = ty * p.BH + by0, cb = tb * p.BB + bb0;
+          if (p.out_f32 != nullptr) tma_store_4d(&p.tmOutF, stg_f, ocol, cx, cy, cb);
+          if (p.out_bf16 != nullptr) tma_store_4d(&p.tmOutB, stg_b, ocol, cx, cy, cb);
+          tma_store_commit();
+        }
       }
       // this warp is done reading the accumulator buffer
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (lane == 0) {
+        if (CG == 2 && rank != 0) mbar_arrive_remote(&tmem_empty[buf], 0);   // the leader's MMA warp waits on ITS barrier
+        else mbar_arrive(&tmem_empty[buf]);
+      }
     }
+    if (lane == 0) tma_store_wait_all();   // every output byte is written before the CTA retires
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer's smem / TMEM stay alive until every MMA and epilogue of the pair is done
+  else __syncthreads();
   if (warp == NUM_EPI_WARPS + 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (CG == 2) tmem_dealloc2<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -376,21 +465,39 @@ static int pow2_divisor(int v, int cap) {
   return d;
 }
 
-template <int BLOCK_N, int STAGES, bool LORA>
+template <int BLOCK_N, int STAGES, bool LORA, int CG>
 static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
   constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
-  constexpr int smem_bytes = STAGES * (A_TILE_BYTES + UMMA_N * BLOCK_K * 2) + 1024 + 256;
+  constexpr int smem_bytes = STAGES * (A_TILE_BYTES + (UMMA_N / CG) * BLOCK_K * 2) + 1024 + 1024 + EPI_STAGING_BYTES;
+  static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
+  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, LORA, CG>;
   static bool configured = false;  // per instantiation
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N, STAGES, LORA>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     configured = true;
   }
-  gemm_tc_kernel<BLOCK_N, STAGES, LORA><<<grid, NUM_THREADS, smem_bytes, stream>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("gemm_tc launch: ") + cudaGetErrorString(e));
   return IDB_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
 }
 
 }  // namespace idb
@@ -420,6 +527,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
                a->lora_seg_n <= 0 || a->lora_seg_n % 160 || a->n % a->lora_seg_n))
     return fail(IDB_E_BADARG, "idb_gemm_conv: bad LoRA arguments (rank_pad in {4,8,12,16}, seg_n % 160 == 0)");
   if (lora && (geglu || a->a1)) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: LoRA with GEGLU / second segment");
+  if (geglu && a->out_f32) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: GEGLU writes bf16 only");
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -448,22 +556,34 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   const int tiles_b = (B + p.BB - 1) / p.BB;
   p.n_tiles_m = p.tiles_x * p.tiles_y * tiles_b;
 
-  // N tile: minimise waves x per-tile MMA time (~ block_n at M = 128); ties go to the wider tile
+  // CTA pairs (cta_group::2) whenever there are at least two M blocks and no fused LoRA
+  static const int force_cg = env_int("IDB_GEMM_CG", 0);
+  int cg = (!lora && p.n_tiles_m >= 2) ? 2 : 1;
+  if (force_cg == 1 || force_cg == 2) cg = (lora ? 1 : force_cg);
+  // N tile: minimise  waves x per-tile MMA time / L2-feed efficiency.  The operand feed from L2 caps
+  // the tensor pipe at about 8 KB/clk chip-wide: eff = min(1, 8000 / (148 * bytes per clk per SM)).
   const int sms = num_sms();
+  const int units = sms / cg;
+  const int m_units = (p.n_tiles_m + cg - 1) / cg;
   int block_n = 0;
   if (lora) {
     block_n = 160;
   } else {
-    long long best = -1;
+    double best = -1.0;
     const int cands[3] = {256, 160, 128};
     for (int ci = 0; ci < 3; ++ci) {
       const int bn = cands[ci];
       if (a->n % bn) continue;
-      const long long tiles = static_cast<long long>(p.n_tiles_m) * (a->n / bn);
-      const long long cost = ((tiles + sms - 1) / sms) * (bn + 24);
+      const long long tiles = static_cast<long long>(m_units) * (a->n / bn);
+      const double bytes_per_clk = (128.0 + bn / static_cast<double>(cg)) * 128.0 / (128.0 * bn / 4096.0);
+      double eff = 8000.0 / (148.0 * bytes_per_clk);
+      if (eff > 1.0) eff = 1.0;
+      const double cost = static_cast<double>((tiles + units - 1) / units) * (bn + 24) / eff;
       if (best < 0 || cost < best) best = cost, block_n = bn;
     }
     if (block_n == 0) block_n = (a->n > 160) ? 256 : (a->n > 128 ? 160 : 128);
+    static const int force_bn = env_int("IDB_GEMM_BN", 0);   // profiling only
+    if (force_bn > 0 && a->n % force_bn == 0) block_n = force_bn;
   }
   p.n_tiles_n = (a->n + block_n - 1) / block_n;
 
@@ -471,9 +591,9 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   int ksp = a->k_splits;
   if (ksp == 0) {  // auto: split K when the tile grid leaves most SMs idle
     ksp = 1;
-    const long long tiles = static_cast<long long>(p.n_tiles_m) * p.n_tiles_n;
-    if (!lora && !geglu && a->workspace && tiles * 2 <= sms && nkb >= 16) {
-      long long want = sms / tiles;
+    const long long tiles = static_cast<long long>(m_units) * p.n_tiles_n;
+    if (!lora && !geglu && a->workspace && tiles * 2 <= units && nkb >= 16) {
+      long long want = units / tiles;
       if (want > nkb / 8) want = nkb / 8;
       const size_t per_split = static_cast<size_t>(p.M) * a->n * sizeof(float);
       if (per_split * want > a->workspace_bytes) want = static_cast<long long>(a->workspace_bytes / per_split);
@@ -497,6 +617,8 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   p.lora_rank_pad = a->lora_rank_pad;
   p.lora_seg_n = lora ? a->lora_seg_n : 1;
   p.flags = a->flags;
+  static const int dbg = env_int("IDB_GEMM_DEBUG", 0);
+  p.debug = dbg;
   p.out_f32 = a->out_f32;
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
   p.workspace = a->workspace;
@@ -522,12 +644,6 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     uint32_t box[4] = {64, uint32_t(p.BW), uint32_t(p.BH), uint32_t(p.BB)};
     if (int rc = make_tmap_bf16(&p.tmA1, a->a1, 4, dims, strides, box)) return rc;
   }
-  {
-    uint64_t dims[2] = {uint64_t(k_total), uint64_t(a->n)};
-    uint64_t strides[1] = {uint64_t(k_total) * 2};
-    uint32_t box[2] = {64, uint32_t(block_n)};
-    if (int rc = make_tmap_bf16(&p.tmW, a->w, 2, dims, strides, box)) return rc;
-  }
   if (lora) {
     const int nseg = a->n / a->lora_seg_n;
     uint64_t dims[2] = {uint64_t(k_total), uint64_t(nseg * 16)};
@@ -536,13 +652,46 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     if (int rc = make_tmap_bf16(&p.tmL, a->lora_down, 2, dims, strides, box)) return rc;
   }
 
-  const int total_tiles = p.n_tiles_m * p.n_tiles_n * p.k_splits;
-  const int grid = total_tiles < sms ? total_tiles : sms;
+  // W box: in a pair each CTA stages half of the N tile
+  {
+    const long long k_tot = static_cast<long long>(p.nkb0 + p.nkb1) * 64;
+    uint64_t dims[2] = {uint64_t(k_tot), uint64_t(a->n)};
+    uint64_t strides[1] = {uint64_t(k_tot) * 2};
+    uint32_t box[2] = {64, uint32_t(block_n / cg)};
+    if (int rc = make_tmap_bf16(&p.tmW, a->w, 2, dims, strides, box)) return rc;
+  }
+  // output store maps: 4-D [N_out, Wo, Ho, B], one box = the 32 tile rows a warp owns x 32 (16 for GEGLU) columns
+  {
+    const int bw32 = p.BW < 32 ? p.BW : 32;
+    const int bh32 = p.BH < 32 / bw32 ? p.BH : 32 / bw32;
+    const int bb32 = 32 / (bw32 * bh32);
+    const uint32_t nc = geglu ? 16 : 32;
+    const uint64_t No = uint64_t(p.N_out);
+    uint64_t dims[4] = {No, uint64_t(p.Wo), uint64_t(p.Ho), uint64_t(B)};
+    uint32_t box[4] = {nc, uint32_t(bw32), uint32_t(bh32), uint32_t(bb32)};
+    if (a->out_f32) {
+      uint64_t strides[3] = {No * 4, uint64_t(p.Wo) * No * 4, uint64_t(p.Ho) * p.Wo * No * 4};
+      if (int rc = make_tmap(&p.tmOutF, a->out_f32, 4, geglu ? 0 : 128, 4, dims, strides, box)) return rc;
+    }
+    if (a->out_bf16) {
+      uint64_t strides[3] = {No * 2, uint64_t(p.Wo) * No * 2, uint64_t(p.Ho) * p.Wo * No * 2};
+      if (int rc = make_tmap(&p.tmOutB, a->out_bf16, 2, 0, 4, dims, strides, box)) return rc;
+    }
+  }
+  const int total_tiles = m_units * p.n_tiles_n * p.k_splits;
+  const int grid = cg * (total_tiles < units ? total_tiles : units);
   int rc;
-  if (lora) rc = launch_gemm<160, 5, true>(p, grid, stream);
-  else if (block_n == 256) rc = launch_gemm<256, 4, false>(p, grid, stream);
-  else if (block_n == 160) rc = launch_gemm<160, 6, false>(p, grid, stream);
-  else rc = launch_gemm<128, 6, false>(p, grid, stream);
+  if (lora) rc = launch_gemm<160, 4, true, 1>(p, grid, stream);
+  else if (cg == 1 && block_n == 256) rc = launch_gemm<256, 3, false, 1>(p, grid, stream);
+  else if (cg == 1 && block_n == 160) rc = launch_gemm<160, 4, false, 1>(p, grid, stream);
+  else if (cg == 1 && block_n == 64) rc = launch_gemm<64, 7, false, 1>(p, grid, stream);
+  else if (cg == 1 && block_n == 96) rc = launch_gemm<96, 6, false, 1>(p, grid, stream);
+  else if (cg == 1 && block_n == 192) rc = launch_gemm<192, 4, false, 1>(p, grid, stream);
+  else if (cg == 1 && block_n == 224) rc = launch_gemm<224, 3, false, 1>(p, grid, stream);
+  else if (cg == 1) rc = launch_gemm<128, 5, false, 1>(p, grid, stream);
+  else if (block_n == 256) rc = launch_gemm<256, 5, false, 2>(p, grid, stream);
+  else if (block_n == 160) rc = launch_gemm<160, 6, false, 2>(p, grid, stream);
+  else rc = launch_gemm<128, 7, false, 2>(p, grid, stream);
   if (rc) return rc;
 
   if (p.k_splits > 1) {

@@ -19,5 +19,8 @@ int num_sms();
 // strides_bytes has rank-1 entries (stride of dims[1..]).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
+// general form: elem_bytes in {2 (bf16), 4 (fp32)}, swizzle_bytes in {0, 32, 64, 128}
+int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box);
 
 }  // namespace idb

@@ -40,41 +40,71 @@ __device__ __forceinline__ float4 gn_load(const GnParams& p, int b, int pix, int
   return *reinterpret_cast<const float4*>(p.x1 + (static_cast<long long>(b) * p.hw + pix) * p.c1 + (c - p.c0));
 }
 
+// Deterministic: per-thread partial sums go to smem and are combined in a fixed order (no float
+// atomics), so repeated runs / different GPUs give bit-identical statistics.
 __global__ void gn_stats_kernel(const GnParams p) {
-  __shared__ float gs[GN_MAX_GROUPS], gss[GN_MAX_GROUPS];
+  extern __shared__ float gn_sm[];  // [PY][C] sums, then [PY][C] sums of squares
   const int chunk = blockIdx.x, b = blockIdx.y;
   const int cq = threadIdx.x % p.CQ, py = threadIdx.x / p.CQ;
-  if (threadIdx.x < GN_MAX_GROUPS) gs[threadIdx.x] = 0.f, gss[threadIdx.x] = 0.f;
-  __syncthreads();
   const int pbeg = chunk * p.pix_per_chunk;
   const int pend = min(p.hw, pbeg + p.pix_per_chunk);
-  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
   if (py < p.PY) {
-    for (int pix = pbeg + py; pix < pend; pix += p.PY) {
+    float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    int pix = pbeg + py;
+    for (; pix + 3 * p.PY < pend; pix += 4 * p.PY) {  // 4 independent 16-byte loads in flight
+      const float4 v0 = gn_load(p, b, pix, cq), v1 = gn_load(p, b, pix + p.PY, cq);
+      const float4 v2 = gn_load(p, b, pix + 2 * p.PY, cq), v3 = gn_load(p, b, pix + 3 * p.PY, cq);
+      s[0] += (v0.x + v1.x) + (v2.x + v3.x), s[1] += (v0.y + v1.y) + (v2.y + v3.y);
+      s[2] += (v0.z + v1.z) + (v2.z + v3.z), s[3] += (v0.w + v1.w) + (v2.w + v3.w);
+      ss[0] += (v0.x * v0.x + v1.x * v1.x) + (v2.x * v2.x + v3.x * v3.x);
+      ss[1] += (v0.y * v0.y + v1.y * v1.y) + (v2.y * v2.y + v3.y * v3.y);
+      ss[2] += (v0.z * v0.z + v1.z * v1.z) + (v2.z * v2.z + v3.z * v3.z);
+      ss[3] += (v0.w * v0.w + v1.w * v1.w) + (v2.w * v2.w + v3.w * v3.w);
+    }
+    for (; pix < pend; pix += p.PY) {
       const float4 v = gn_load(p, b, pix, cq);
       s[0] += v.x, s[1] += v.y, s[2] += v.z, s[3] += v.w;
       ss[0] += v.x * v.x, ss[1] += v.y * v.y, ss[2] += v.z * v.z, ss[3] += v.w * v.w;
     }
-    const int c = cq * 4;
-    const int g0 = c / p.cpg, g3 = (c + 3) / p.cpg;
-    if (g0 == g3) {
-      atomicAdd(&gs[g0], (s[0] + s[1]) + (s[2] + s[3]));
-      atomicAdd(&gss[g0], (ss[0] + ss[1]) + (ss[2] + ss[3]));
-    } else {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int g = (c + i) / p.cpg;
-        atomicAdd(&gs[g], s[i]);
-        atomicAdd(&gss[g], ss[i]);
-      }
-    }
+    float* ds = gn_sm + py * p.C + cq * 4;
+    float* dss = gn_sm + (p.PY + py) * p.C + cq * 4;
+    *reinterpret_cast<float4*>(ds) = make_float4(s[0], s[1], s[2], s[3]);
+    *reinterpret_cast<float4*>(dss) = make_float4(ss[0], ss[1], ss[2], ss[3]);
   }
   __syncthreads();
-  if (threadIdx.x < p.groups) {
-    float* dst = p.partials + ((static_cast<long long>(b) * p.nchunks + chunk) * p.groups + threadIdx.x) * 2;
-    dst[0] = gs[threadIdx.x];
-    dst[1] = gss[threadIdx.x];
+  // fixed-order combine: warp w handles groups w, w+nw, ...; lanes stride the (py, channel) cells
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int g = warp; g < p.groups; g += nw) {
+    float a = 0.f, a2 = 0.f;
+    const int cells = p.PY * p.cpg;
+    for (int i = lane; i < cells; i += 32) {
+      const int yy = i / p.cpg, c = g * p.cpg + (i - yy * p.cpg);
+      a += gn_sm[yy * p.C + c];
+      a2 += gn_sm[(p.PY + yy) * p.C + c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+      float* dst = p.partials + ((static_cast<long long>(b) * p.nchunks + chunk) * p.groups + g) * 2;
+      dst[0] = a;
+      dst[1] = a2;
+    }
   }
+}
+
+__device__ __forceinline__ void gn_emit(const GnParams& p, int b, int pix, int c, const float4 v, const float* sc,
+                                        const float* sh) {
+  float y[4] = {v.x * sc[0] + sh[0], v.y * sc[1] + sh[1], v.z * sc[2] + sh[2], v.w * sc[3] + sh[3]};
+  if (p.silu) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) y[i] = silu_f(y[i]);
+  }
+  const long long o = (static_cast<long long>(b) * p.hw + pix) * p.C + c;
+  *reinterpret_cast<uint2*>(p.out_norm + o) = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
+  if (p.out_raw) *reinterpret_cast<uint2*>(p.out_raw + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
 
 __global__ void gn_apply_kernel(const GnParams p) {
@@ -108,17 +138,16 @@ __global__ void gn_apply_kernel(const GnParams p) {
   }
   const int pbeg = chunk * p.pix_per_chunk;
   const int pend = min(p.hw, pbeg + p.pix_per_chunk);
-  for (int pix = pbeg + py; pix < pend; pix += p.PY) {
-    const float4 v = gn_load(p, b, pix, cq);
-    float y[4] = {v.x * sc[0] + sh[0], v.y * sc[1] + sh[1], v.z * sc[2] + sh[2], v.w * sc[3] + sh[3]};
-    if (p.silu) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) y[i] = silu_f(y[i]);
-    }
-    const long long o = (static_cast<long long>(b) * p.hw + pix) * p.C + c;
-    *reinterpret_cast<uint2*>(p.out_norm + o) = make_uint2(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]));
-    if (p.out_raw) *reinterpret_cast<uint2*>(p.out_raw + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  int pix = pbeg + py;
+  for (; pix + 3 * p.PY < pend; pix += 4 * p.PY) {
+    const float4 v0 = gn_load(p, b, pix, cq), v1 = gn_load(p, b, pix + p.PY, cq);
+    const float4 v2 = gn_load(p, b, pix + 2 * p.PY, cq), v3 = gn_load(p, b, pix + 3 * p.PY, cq);
+    gn_emit(p, b, pix, c, v0, sc, sh);
+    gn_emit(p, b, pix + p.PY, c, v1, sc, sh);
+    gn_emit(p, b, pix + 2 * p.PY, c, v2, sc, sh);
+    gn_emit(p, b, pix + 3 * p.PY, c, v3, sc, sh);
   }
+  for (; pix < pend; pix += p.PY) gn_emit(p, b, pix, c, gn_load(p, b, pix, cq), sc, sh);
 }
 
 // ---------------------------------------------------------------------------------------- LayerNorm (warp per row)
@@ -254,49 +283,50 @@ __global__ void skinny_linear_kernel(const float* __restrict__ x, const float* _
 }
 
 // ---------------------------------------------------------------------------------------- edge convolutions
-// conv3x3 pad 1, tiny Cin: thread = (pixel, 4 output channels), patch held in registers.
-template <int CIN>
+// conv3x3 pad 1, Cin = 4: one CTA = 32 consecutive pixels of one image row; thread = output channel
+// with its 36 weights in registers; the 3 x 34 x 4 input patch sits in smem and is read as broadcast
+// float4s; stores are coalesced along the NHWC channel axis.
+constexpr int CIN_TILE_W = 32;
 __global__ void conv_small_cin_kernel(const float* __restrict__ x, int x_nchw, const float* __restrict__ w,
                                       const float* __restrict__ bias, float* __restrict__ out_f32,
                                       __nv_bfloat16* __restrict__ out_bf16, int B, int H, int W, int Cout) {
-  const int cq_n = Cout / 4;
-  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long total = static_cast<long long>(B) * H * W * cq_n;
-  if (idx >= total) return;
-  const int cq = static_cast<int>(idx % cq_n);
-  const long long pix = idx / cq_n;
-  const int xw = static_cast<int>(pix % W);
-  const int yh = static_cast<int>((pix / W) % H);
-  const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
-  float patch[9 * CIN];
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) {
-      const int yy = yh + dy - 1, xx = xw + dx - 1;
-      const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-#pragma unroll
-      for (int c = 0; c < CIN; ++c) {
-        float v = 0.f;
-        if (ok)
-          v = x_nchw ? x[((static_cast<long long>(b) * CIN + c) * H + yy) * W + xx]
-                     : x[((static_cast<long long>(b) * H + yy) * W + xx) * CIN + c];
-        patch[(dy * 3 + dx) * CIN + c] = v;
-      }
-    }
-  float o[4];
-#pragma unroll
-  for (int oc = 0; oc < 4; ++oc) {
-    const int co = cq * 4 + oc;
-    const float* wr = w + static_cast<long long>(co) * 9 * CIN;
-    float a = bias ? bias[co] : 0.f;
-#pragma unroll
-    for (int i = 0; i < 9 * CIN; ++i) a += patch[i] * __ldg(wr + i);
-    o[oc] = a;
+  __shared__ float4 patch[3][CIN_TILE_W + 2];
+  const int tiles_x = (W + CIN_TILE_W - 1) / CIN_TILE_W;
+  const int tx = blockIdx.x % tiles_x;
+  const int yh = (blockIdx.x / tiles_x) % H;
+  const int b = blockIdx.x / (tiles_x * H);
+  const int x0 = tx * CIN_TILE_W;
+  for (int i = threadIdx.x; i < 3 * (CIN_TILE_W + 2) * 4; i += blockDim.x) {
+    const int c = i & 3, col = (i >> 2) % (CIN_TILE_W + 2), r = (i >> 2) / (CIN_TILE_W + 2);
+    const int yy = yh + r - 1, xx = x0 + col - 1;
+    float v = 0.f;
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      v = x_nchw ? x[((static_cast<long long>(b) * 4 + c) * H + yy) * W + xx]
+                 : x[((static_cast<long long>(b) * H + yy) * W + xx) * 4 + c];
+    reinterpret_cast<float*>(&patch[r][col])[c] = v;
   }
-  const long long off = pix * Cout + cq * 4;
-  if (out_f32) *reinterpret_cast<float4*>(out_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
-  if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + off) = make_uint2(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]));
+  __syncthreads();
+  const int co = threadIdx.x;
+  if (co >= Cout) return;
+  float4 wr[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wr[t] = __ldg(reinterpret_cast<const float4*>(w + (static_cast<long long>(co) * 9 + t) * 4));
+  const float bv = bias ? bias[co] : 0.f;
+  const int npx = min(CIN_TILE_W, W - x0);
+  for (int px = 0; px < npx; ++px) {
+    float a = bv;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const float4 v = patch[dy][px + dx];
+        const float4 k = wr[dy * 3 + dx];
+        a += (v.x * k.x + v.y * k.y) + (v.z * k.z + v.w * k.w);
+      }
+    const long long off = ((static_cast<long long>(b) * H + yh) * W + x0 + px) * Cout + co;
+    if (out_f32) out_f32[off] = a;
+    if (out_bf16) out_bf16[off] = __float2bfloat16(a);
+  }
 }
 
 // conv3x3 pad 1, tiny Cout: one warp per output pixel, lanes stride the channel axis (8 B loads).
@@ -457,8 +487,10 @@ extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
   p.x0 = a->x0, p.x1 = a->x1, p.c0 = a->c0, p.c1 = a->x1 ? a->c1 : 0, p.C = C, p.CQ = C / 4;
   p.PY = p.CQ >= 256 ? 1 : 256 / p.CQ;
   p.hw = a->hw, p.groups = a->groups, p.cpg = C / a->groups, p.eps = a->eps;
-  int nchunks = a->hw / 32;
-  if (nchunks < 1) nchunks = 1;
+  // pixels per CTA: enough for >= 4 unrolled rounds of PY rows, while keeping >= ~4 CTAs per SM in flight
+  int ppc = 16 * p.PY;
+  while (ppc > 4 * p.PY && static_cast<long long>(a->batch) * ((a->hw + ppc - 1) / ppc) < 4LL * num_sms()) ppc /= 2;
+  int nchunks = (a->hw + ppc - 1) / ppc;
   if (nchunks > GN_MAX_CHUNKS) nchunks = GN_MAX_CHUNKS;
   p.pix_per_chunk = (a->hw + nchunks - 1) / nchunks;
   p.nchunks = (a->hw + p.pix_per_chunk - 1) / p.pix_per_chunk;
@@ -468,9 +500,10 @@ extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
   p.partials = a->partials;
   int threads = p.CQ * p.PY;
   threads = (threads + 31) / 32 * 32;
-  if (threads < 64) threads = 64;  // the first 64 threads zero / publish the group slots
+  if (threads < 64) threads = 64;  // the apply kernel's first `groups` threads publish mean / rstd
   dim3 grid(p.nchunks, a->batch);
-  gn_stats_kernel<<<grid, threads, 0, stream>>>(p);
+  const size_t stats_smem = static_cast<size_t>(2) * p.PY * C * sizeof(float);
+  gn_stats_kernel<<<grid, threads, stats_smem, stream>>>(p);
   IDB_CHECK_LAUNCH("gn_stats");
   gn_apply_kernel<<<grid, threads, 0, stream>>>(p);
   IDB_CHECK_LAUNCH("gn_apply");
@@ -485,7 +518,12 @@ extern "C" int idb_layernorm(const float* x, const float* gamma, const float* be
   if (c % 4 || c <= 0 || c > 2048) return fail(IDB_E_BADARG, "idb_layernorm: C must be a multiple of 4, <= 2048");
   const int warps = 8;
   const int grid = static_cast<int>((rows + warps - 1) / warps);
-  layernorm_kernel<16><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, static_cast<__nv_bfloat16*>(out_bf16), rows, c, eps);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
+  const int quads_per_lane = (c / 4 + 31) / 32;  // registers (and therefore occupancy) scale with this
+  if (quads_per_lane <= 3) layernorm_kernel<3><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, o, rows, c, eps);
+  else if (quads_per_lane <= 5) layernorm_kernel<5><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, o, rows, c, eps);
+  else if (quads_per_lane <= 10) layernorm_kernel<10><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, o, rows, c, eps);
+  else layernorm_kernel<16><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, o, rows, c, eps);
   IDB_CHECK_LAUNCH("layernorm");
   return IDB_OK;
 }
@@ -529,9 +567,10 @@ extern "C" int idb_conv3x3_small_cin(const float* x, int32_t x_nchw, const float
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = require_sm100()) return rc;
   if (!x || !w || (!out_f32 && !out_bf16)) return fail(IDB_E_BADARG, "idb_conv3x3_small_cin: null pointer");
-  if (cin != 4 || cout % 4) return fail(IDB_E_UNSUPPORTED, "idb_conv3x3_small_cin: Cin must be 4, Cout % 4 == 0");
-  const long long total = static_cast<long long>(batch) * h * wd * (cout / 4);
-  conv_small_cin_kernel<4><<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(
+  if (cin != 4 || cout > 1024) return fail(IDB_E_UNSUPPORTED, "idb_conv3x3_small_cin: Cin must be 4, Cout <= 1024");
+  const long long blocks = static_cast<long long>(batch) * h * ((wd + CIN_TILE_W - 1) / CIN_TILE_W);
+  const int threads = (cout + 31) / 32 * 32;
+  conv_small_cin_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
       x, x_nchw, w, bias, out_f32, static_cast<__nv_bfloat16*>(out_bf16), batch, h, wd, cout);
   IDB_CHECK_LAUNCH("conv_small_cin");
   return IDB_OK;
