@@ -32,6 +32,8 @@ struct GnParams {
   __nv_bfloat16* out_norm;
   __nv_bfloat16* out_raw;
   float* partials;  // [B, nchunks, groups, 2]
+  float* stats;     // [B, groups, 2] = (mean, rstd), written by the last stats CTA of each image
+  unsigned int* counters;  // [B] arrival tickets (zero on entry, reset to zero by the last CTA)
 };
 
 __device__ __forceinline__ float4 gn_load(const GnParams& p, int b, int pix, int cq) {
@@ -93,6 +95,38 @@ __global__ void gn_stats_kernel(const GnParams p) {
       dst[1] = a2;
     }
   }
+  // ---- the last CTA of image b to arrive folds the per-chunk partials (fixed order -> deterministic)
+  __shared__ unsigned int s_ticket;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.counters[b], 1u);
+  __syncthreads();
+  if (s_ticket != static_cast<unsigned int>(p.nchunks - 1)) return;
+  __threadfence();
+  for (int g = warp; g < p.groups; g += nw) {
+    double s = 0.0, ss = 0.0;
+    const float* src = p.partials + (static_cast<long long>(b) * p.nchunks * p.groups + g) * 2;
+    for (int i = lane; i < p.nchunks; i += 32) {
+      const float2 v = __ldcg(reinterpret_cast<const float2*>(src + static_cast<long long>(i) * p.groups * 2));
+      s += v.x;
+      ss += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane == 0) {
+      const double n = static_cast<double>(p.hw) * p.cpg;
+      const double mean = s / n;
+      double var = ss / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      float* dst = p.stats + (static_cast<long long>(b) * p.groups + g) * 2;
+      dst[0] = static_cast<float>(mean);
+      dst[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+    }
+  }
+  if (threadIdx.x == 0) p.counters[b] = 0u;   // ready for the next GroupNorm call on this workspace
 }
 
 __device__ __forceinline__ void gn_emit(const GnParams& p, int b, int pix, int c, const float4 v, const float* sc,
@@ -111,18 +145,9 @@ __global__ void gn_apply_kernel(const GnParams p) {
   __shared__ float g_mean[GN_MAX_GROUPS], g_rstd[GN_MAX_GROUPS];
   const int chunk = blockIdx.x, b = blockIdx.y;
   if (threadIdx.x < p.groups) {
-    double s = 0.0, ss = 0.0;
-    const float* src = p.partials + (static_cast<long long>(b) * p.nchunks * p.groups + threadIdx.x) * 2;
-    for (int i = 0; i < p.nchunks; ++i) {
-      s += src[static_cast<long long>(i) * p.groups * 2];
-      ss += src[static_cast<long long>(i) * p.groups * 2 + 1];
-    }
-    const double n = static_cast<double>(p.hw) * p.cpg;
-    const double mean = s / n;
-    double var = ss / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    g_mean[threadIdx.x] = static_cast<float>(mean);
-    g_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+    const float2 st = *reinterpret_cast<const float2*>(p.stats + (static_cast<long long>(b) * p.groups + threadIdx.x) * 2);
+    g_mean[threadIdx.x] = st.x;
+    g_rstd[threadIdx.x] = st.y;
   }
   __syncthreads();
   const int cq = threadIdx.x % p.CQ, py = threadIdx.x / p.CQ;
@@ -470,8 +495,10 @@ static int grid_for(long long work_items, int block, int max_blocks) {
 
 using namespace idb;
 
+// workspace = [partials: B*GN_MAX_CHUNKS*G*2 floats][stats: B*G*2 floats][counters: B uint32]
 extern "C" size_t idb_groupnorm_workspace_bytes(int32_t batch, int32_t groups) {
-  return static_cast<size_t>(batch) * GN_MAX_CHUNKS * groups * 2 * sizeof(float);
+  return (static_cast<size_t>(batch) * GN_MAX_CHUNKS * groups * 2 + static_cast<size_t>(batch) * groups * 2 + batch) *
+         sizeof(float);
 }
 
 extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
@@ -498,6 +525,8 @@ extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
   p.out_norm = static_cast<__nv_bfloat16*>(a->out_norm);
   p.out_raw = static_cast<__nv_bfloat16*>(a->out_raw);
   p.partials = a->partials;
+  p.stats = a->partials + static_cast<size_t>(a->batch) * GN_MAX_CHUNKS * a->groups * 2;
+  p.counters = reinterpret_cast<unsigned int*>(p.stats + static_cast<size_t>(a->batch) * a->groups * 2);
   int threads = p.CQ * p.PY;
   threads = (threads + 31) / 32 * 32;
   if (threads < 64) threads = 64;  // the apply kernel's first `groups` threads publish mean / rstd

@@ -101,7 +101,7 @@ def attention(q, k, v, out=None, *, batch: int, heads: int, t_q: int, t_kv: int,
 
 def groupnorm_workspace(batch: int, groups: int, device) -> torch.Tensor:
     n = _lib.load().idb_groupnorm_workspace_bytes(batch, groups)
-    return torch.empty(n // 4, dtype=f32, device=device)
+    return torch.zeros(n // 4, dtype=f32, device=device)   # arrival counters must start at zero
 
 
 def groupnorm(x0, gamma, beta, *, groups: int, eps: float, silu: bool, x1=None, out_norm=None, out_raw=None,

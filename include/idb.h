@@ -129,7 +129,9 @@ int idb_attention(const idb_attention_args* args, void* stream);
  * channel-concatenation [x0 | x1] (UpBlock skip `torch.cat([h, skip], 1)`) without
  * materialising it.  Inputs fp32 (stream) ; outputs bf16 [B,H,W,C0+C1]:
  *   out_norm = act(GN(x))        out_raw (optional) = bf16(x)   (operand of conv_shortcut)
- * partials: fp32 workspace of idb_groupnorm_workspace_bytes().
+ * partials: fp32 workspace of idb_groupnorm_workspace_bytes(); it must be ZERO-INITIALISED once by the caller
+ * (it holds arrival counters that every call leaves at zero again); calls sharing a workspace must be
+ * stream-ordered.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
   const float* x0; int32_t c0;
