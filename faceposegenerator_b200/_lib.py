@@ -31,6 +31,7 @@ class GemmConvArgs(C.Structure):
         ("flags", c_int32),
         ("out_f32", c_void_p), ("out_bf16", c_void_p),
         ("k_splits", c_int32), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
+        ("stats_partials", c_void_p),
     ]
 
 
@@ -55,6 +56,7 @@ class GroupNormArgs(C.Structure):
         ("silu", c_int32),
         ("out_norm", c_void_p), ("out_raw", c_void_p),
         ("partials", c_void_p),
+        ("x0_stats", c_void_p), ("x1_stats", c_void_p),
     ]
 
 
@@ -97,7 +99,7 @@ EXPORTS = {
 
 _lib: Optional[C.CDLL] = None
 launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"idb_groupnorm": 2, "idb_time_embed": 4}
+_LAUNCHES_PER_CALL = {"idb_groupnorm": 2, "idb_time_embed": 4}   # (a lower bound for split-K GEMMs)
 
 
 def load() -> C.CDLL:

@@ -283,7 +283,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
   return __int_as_float(__float_as_int(pl) + (__float_as_int(xf) << 23));
 }
 
-template <int POLY_MASK>   // elements with (i & mask) == mask take the polynomial exp2: 1 -> 1/2, 3 -> 1/4, 7 -> 1/8, 32 -> none
+template <int POLY_MASK, int PACKED>   // PACKED: 0 scalar, 1 ffma2+fadd2, 2 ffma2 only;  elements with (i & mask) == mask take the polynomial exp2: 1 -> 1/2, 3 -> 1/4, 7 -> 1/8, 32 -> none
 __global__ void __launch_bounds__(AT2_THREADS, 1) attention256_kernel(const __grid_constant__ AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -484,10 +484,16 @@ __global__ void __launch_bounds__(AT2_THREADS, 1) attention256_kernel(const __gr
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {   // masked keys: exp2(-inf) = 0 (MUFU) / 2^-126 (polynomial)
           float x0, x1;
-          ffma2(x0, x1, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]), c, c, neg_m, neg_m);   // one issue slot
+          if (PACKED) {
+            ffma2(x0, x1, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]), c, c, neg_m, neg_m);   // one issue slot
+          } else {
+            x0 = fmaf(__uint_as_float(sv[i]), c, neg_m);
+            x1 = fmaf(__uint_as_float(sv[i + 1]), c, neg_m);
+          }
           pv[i] = ((i & POLY_MASK) == POLY_MASK) ? exp2_poly(x0) : ex2(x0);
           pv[i + 1] = (((i + 1) & POLY_MASK) == POLY_MASK) ? exp2_poly(x1) : ex2(x1);
-          fadd2(l0, l1, l0, l1, pv[i], pv[i + 1]);
+          if (PACKED == 1) fadd2(l0, l1, l0, l1, pv[i], pv[i + 1]);
+          else l0 += pv[i], l1 += pv[i + 1];
         }
         uint8_t* base = prow + (ch >> 1) * ATT_TILE;
 #pragma unroll
@@ -592,9 +598,17 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
   static const int force_variant = getenv("IDB_ATTN_VARIANT") ? atoi(getenv("IDB_ATTN_VARIANT")) : 0;
   const bool use256 = force_variant ? (force_variant == 256) : (a->t_q >= 1024 && a->t_kv >= 512);
   if (use256) {   // two query tiles per CTA share the K/V stream (long sequences)
-    static const int poly = getenv("IDB_ATTN_POLY") ? atoi(getenv("IDB_ATTN_POLY")) : 32;
-    auto kern = poly == 1 ? attention256_kernel<1> : poly == 7 ? attention256_kernel<7> : poly == 3 ? attention256_kernel<3>
-                                                                                                     : attention256_kernel<32>;
+    static const int poly = getenv("IDB_ATTN_POLY") ? atoi(getenv("IDB_ATTN_POLY")) : 7;
+    static const int packed = getenv("IDB_ATTN_PACKED") ? atoi(getenv("IDB_ATTN_PACKED")) : 1;
+    void (*kern)(AttnParams) = attention256_kernel<7, 1>;
+    if (poly == 32 && packed == 0) kern = attention256_kernel<32, 0>;
+    else if (poly == 32 && packed == 1) kern = attention256_kernel<32, 1>;
+    else if (poly == 32) kern = attention256_kernel<32, 2>;
+    else if (poly == 7 && packed == 0) kern = attention256_kernel<7, 0>;
+    else if (poly == 7 && packed == 2) kern = attention256_kernel<7, 2>;
+    else if (poly == 3 && packed == 0) kern = attention256_kernel<3, 0>;
+    else if (poly == 3 && packed == 1) kern = attention256_kernel<3, 1>;
+    else if (poly == 3) kern = attention256_kernel<3, 2>;
     static bool configured2 = false;
     if (!configured2) {
       cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM);

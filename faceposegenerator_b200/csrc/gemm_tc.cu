@@ -58,6 +58,7 @@ struct GemmParams {
   float* out_f32;
   __nv_bfloat16* out_bf16;
   float* workspace;
+  float2* stats;   // optional [ceil(M/32)][N] (sum, sum of squares) over each 32-row block of the fp32 output
 };
 
 template <int BLOCK_N, int STAGES, bool LORA, int CG>
@@ -373,6 +374,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         // ---- stage (previous TMA stores of this warp must have finished READING the staging chunk)
         if (lane == 0) tma_store_wait_read();
         __syncwarp();
+        if (p.stats != nullptr && !row_ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+        }
         if (p.out_f32 != nullptr) {   // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row `lane` lands at j ^ (lane & 7)
           const uint32_t row = stg_f + lane * 128;
 #pragma unroll
@@ -393,6 +398,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                            "r"(pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5])), "r"(pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]))
                            : "memory");
           }
+        }
+        if (p.stats != nullptr) {
+          // GroupNorm statistics of the tensor being written, for free: lane c reduces column c of the
+          // staged 32 x 32 fp32 chunk (rows outside the image were staged as zeros)
+          __syncwarp();
+          float cs = 0.f, cs2 = 0.f;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stg_f + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + ((lane & 3) << 2)));
+            cs += v;
+            cs2 = fmaf(v, v, cs2);
+          }
+          const long long rowblock = static_cast<long long>(m_blk) * 4 + quarter;
+          if (ocol + lane < p.N_out) p.stats[rowblock * p.N_out + ocol + lane] = make_float2(cs, cs2);
         }
         fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
@@ -455,6 +475,25 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int k_split
     }
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + e) = a;
     if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + e) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+  }
+}
+
+// statistics of 32-row blocks of a finished fp32 [M, N] tensor (split-K path of tiny-M layers); the
+// row-block numbering matches the tile order of the fused epilogue only for raster-ordered tiles,
+// which is what the host guarantees before using this path (BW * BH multiple of 32 rows per image).
+__global__ void rowblock_stats_kernel(const float* __restrict__ x, long long M, int N, float2* __restrict__ stats) {
+  const long long rowblock = blockIdx.x;
+  for (int c = threadIdx.x; c < N; c += blockDim.x) {
+    float s = 0.f, s2 = 0.f;
+    for (int rr = 0; rr < 32; ++rr) {
+      const long long row = rowblock * 32 + rr;
+      if (row < M) {
+        const float v = x[row * N + c];
+        s += v;
+        s2 = fmaf(v, v, s2);
+      }
+    }
+    stats[rowblock * N + c] = make_float2(s, s2);
   }
 }
 
@@ -528,6 +567,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     return fail(IDB_E_BADARG, "idb_gemm_conv: bad LoRA arguments (rank_pad in {4,8,12,16}, seg_n % 160 == 0)");
   if (lora && (geglu || a->a1)) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: LoRA with GEGLU / second segment");
   if (geglu && a->out_f32) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: GEGLU writes bf16 only");
+  if (a->stats_partials && !a->out_f32) return fail(IDB_E_BADARG, "idb_gemm_conv: stats_partials needs the fp32 output");
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -555,6 +595,12 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   p.tiles_y = (p.Ho + p.BH - 1) / p.BH;
   const int tiles_b = (B + p.BB - 1) / p.BB;
   p.n_tiles_m = p.tiles_x * p.tiles_y * tiles_b;
+  if (a->stats_partials) {
+    // 32-row blocks of the (BW x BH x BB) tile rectangle must be raster-contiguous runs of one image
+    const bool raster = (p.BW == p.Wo) || (p.BH == 1 && p.BB == 1) || (p.Ho == 1 && B == 1);
+    if (!raster || (static_cast<long long>(p.Ho) * p.Wo) % 32 != 0)
+      return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: stats_partials needs power-of-two Wo (or Wo % 128 == 0) and Ho*Wo % 32 == 0");
+  }
 
   // CTA pairs (cta_group::2) whenever there are at least two M blocks and no fused LoRA
   static const int force_cg = env_int("IDB_GEMM_CG", 0);
@@ -622,6 +668,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   p.out_f32 = a->out_f32;
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
   p.workspace = a->workspace;
+  p.stats = reinterpret_cast<float2*>(a->stats_partials);
 
   // ---- tensor maps
   if (a->a0_mode == IDB_A_3X3_S2) {
@@ -678,20 +725,22 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
       if (int rc = make_tmap(&p.tmOutB, a->out_bf16, 2, 0, 4, dims, strides, box)) return rc;
     }
   }
+  GemmParams pk = p;
+  if (p.k_splits > 1) pk.stats = nullptr;   // statistics come from rowblock_stats_kernel after the finalize
   const int total_tiles = m_units * p.n_tiles_n * p.k_splits;
   const int grid = cg * (total_tiles < units ? total_tiles : units);
   int rc;
-  if (lora) rc = launch_gemm<160, 4, true, 1>(p, grid, stream);
-  else if (cg == 1 && block_n == 256) rc = launch_gemm<256, 3, false, 1>(p, grid, stream);
-  else if (cg == 1 && block_n == 160) rc = launch_gemm<160, 4, false, 1>(p, grid, stream);
-  else if (cg == 1 && block_n == 64) rc = launch_gemm<64, 7, false, 1>(p, grid, stream);
-  else if (cg == 1 && block_n == 96) rc = launch_gemm<96, 6, false, 1>(p, grid, stream);
-  else if (cg == 1 && block_n == 192) rc = launch_gemm<192, 4, false, 1>(p, grid, stream);
-  else if (cg == 1 && block_n == 224) rc = launch_gemm<224, 3, false, 1>(p, grid, stream);
-  else if (cg == 1) rc = launch_gemm<128, 5, false, 1>(p, grid, stream);
-  else if (block_n == 256) rc = launch_gemm<256, 5, false, 2>(p, grid, stream);
-  else if (block_n == 160) rc = launch_gemm<160, 6, false, 2>(p, grid, stream);
-  else rc = launch_gemm<128, 7, false, 2>(p, grid, stream);
+  if (lora) rc = launch_gemm<160, 4, true, 1>(pk, grid, stream);
+  else if (cg == 1 && block_n == 256) rc = launch_gemm<256, 3, false, 1>(pk, grid, stream);
+  else if (cg == 1 && block_n == 160) rc = launch_gemm<160, 4, false, 1>(pk, grid, stream);
+  else if (cg == 1 && block_n == 64) rc = launch_gemm<64, 7, false, 1>(pk, grid, stream);
+  else if (cg == 1 && block_n == 96) rc = launch_gemm<96, 6, false, 1>(pk, grid, stream);
+  else if (cg == 1 && block_n == 192) rc = launch_gemm<192, 4, false, 1>(pk, grid, stream);
+  else if (cg == 1 && block_n == 224) rc = launch_gemm<224, 3, false, 1>(pk, grid, stream);
+  else if (cg == 1) rc = launch_gemm<128, 5, false, 1>(pk, grid, stream);
+  else if (block_n == 256) rc = launch_gemm<256, 5, false, 2>(pk, grid, stream);
+  else if (block_n == 160) rc = launch_gemm<160, 6, false, 2>(pk, grid, stream);
+  else rc = launch_gemm<128, 7, false, 2>(pk, grid, stream);
   if (rc) return rc;
 
   if (p.k_splits > 1) {
@@ -702,6 +751,12 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
                                                        p.rowvec_ld, p.residual, p.out_f32, p.out_bf16);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("splitk_finalize launch: ") + cudaGetErrorString(e));
+    if (p.stats != nullptr) {
+      const unsigned nrb = static_cast<unsigned>((p.M + 31) / 32);
+      rowblock_stats_kernel<<<nrb, 256, 0, stream>>>(p.out_f32, p.M, p.N, p.stats);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("rowblock_stats launch: ") + cudaGetErrorString(e));
+    }
   }
   return IDB_OK;
 }

@@ -129,6 +129,37 @@ __global__ void gn_stats_kernel(const GnParams p) {
   if (threadIdx.x == 0) p.counters[b] = 0u;   // ready for the next GroupNorm call on this workspace
 }
 
+// Group statistics from the row-block channel sums that the producing GEMM epilogues wrote
+// (fixed summation order -> deterministic).  grid = (groups, batch), one warp per (image, group).
+__global__ void gn_finalize_kernel(const float2* __restrict__ s0, int c0, const float2* __restrict__ s1, int c1,
+                                   int rb_per_image, int cpg, int hw, float eps, float* __restrict__ stats) {
+  const int g = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+  const int groups = gridDim.x;
+  double s = 0.0, ss = 0.0;
+  const int cells = rb_per_image * cpg;
+  for (int i = lane; i < cells; i += 32) {
+    const int rb = i / cpg, c = g * cpg + (i - rb * cpg);
+    const long long row = static_cast<long long>(b) * rb_per_image + rb;
+    const float2 v = (c < c0) ? s0[row * c0 + c] : s1[row * c1 + (c - c0)];
+    s += v.x;
+    ss += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  }
+  if (lane == 0) {
+    const double n = static_cast<double>(hw) * cpg;
+    const double mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float* dst = stats + (static_cast<long long>(b) * groups + g) * 2;
+    dst[0] = static_cast<float>(mean);
+    dst[1] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+}
+
 __device__ __forceinline__ void gn_emit(const GnParams& p, int b, int pix, int c, const float4 v, const float* sc,
                                         const float* sh) {
   float y[4] = {v.x * sc[0] + sh[0], v.y * sc[1] + sh[1], v.z * sc[2] + sh[2], v.w * sc[3] + sh[3]};
@@ -531,9 +562,17 @@ extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
   threads = (threads + 31) / 32 * 32;
   if (threads < 64) threads = 64;  // the apply kernel's first `groups` threads publish mean / rstd
   dim3 grid(p.nchunks, a->batch);
-  const size_t stats_smem = static_cast<size_t>(2) * p.PY * C * sizeof(float);
-  gn_stats_kernel<<<grid, threads, stats_smem, stream>>>(p);
-  IDB_CHECK_LAUNCH("gn_stats");
+  const bool have_stats = a->x0_stats != nullptr && (a->x1 == nullptr || a->x1_stats != nullptr) && a->hw % 32 == 0;
+  if (have_stats) {   // statistics already produced by the GEMM epilogues of the sources
+    gn_finalize_kernel<<<dim3(a->groups, a->batch), 32, 0, stream>>>(
+        reinterpret_cast<const float2*>(a->x0_stats), p.c0, reinterpret_cast<const float2*>(a->x1_stats), p.c1,
+        a->hw / 32, p.cpg, a->hw, a->eps, p.stats);
+    IDB_CHECK_LAUNCH("gn_finalize");
+  } else {
+    const size_t stats_smem = static_cast<size_t>(2) * p.PY * C * sizeof(float);
+    gn_stats_kernel<<<grid, threads, stats_smem, stream>>>(p);
+    IDB_CHECK_LAUNCH("gn_stats");
+  }
   gn_apply_kernel<<<grid, threads, 0, stream>>>(p);
   IDB_CHECK_LAUNCH("gn_apply");
   return IDB_OK;

@@ -33,7 +33,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
               bias=None, rowvec=None, rowvec_ld: int = 0, residual=None, lora_down=None, lora_up=None, lora_seg_n: int = 0,
               geglu: bool = False, out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
               want_f32: bool = False, want_bf16: bool = False, k_splits: int = 1,
-              workspace: Optional[torch.Tensor] = None):
+              workspace: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, want_stats: bool = False):
     """a0: bf16 [B,H,W,C0] (or [M,K] for a Linear); w: bf16 [N, Ktot].  Returns (out_f32, out_bf16)."""
     _chk(a0, bf16, "a0"); _chk(w, bf16, "w")
     if a0.dim() == 2:
@@ -72,6 +72,9 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
     _chk(out_f32, f32, "out_f32", allow_none=True); _chk(out_bf16, bf16, "out_bf16", allow_none=True)
     if k_splits > 1 and workspace is None:
         workspace = torch.empty((k_splits, M, N), dtype=f32, device=a0.device)
+    if stats is None and want_stats:   # row-block channel statistics of the fp32 output (consumed by groupnorm)
+        stats = torch.empty(((M + 31) // 32, n_out, 2), dtype=f32, device=a0.device)
+    _chk(stats, f32, "stats", allow_none=True)
     args = _lib.GemmConvArgs(
         a0=a0.data_ptr(), a0_mode=mode, c0=C0, a1=_lib.ptr(a1), c1=c1, batch=B, height=H, width=W_,
         w=w.data_ptr(), n=N, bias=_lib.ptr(bias), rowvec=_lib.ptr(rowvec), rowvec_ld=rowvec_ld, residual=_lib.ptr(residual),
@@ -79,8 +82,10 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
         lora_rank_pad=0 if lora_up is None else lora_up.shape[1], lora_seg_n=lora_seg_n,
         flags=EPI_GEGLU if geglu else 0, out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
         k_splits=k_splits, workspace=_lib.ptr(workspace),
-        workspace_bytes=0 if workspace is None else workspace.numel() * 4)
+        workspace_bytes=0 if workspace is None else workspace.numel() * 4, stats_partials=_lib.ptr(stats))
     _lib.call("idb_gemm_conv", C.byref(args), _lib.stream_ptr())
+    if want_stats or stats is not None:
+        return out_f32, out_bf16, stats
     return out_f32, out_bf16
 
 
@@ -105,7 +110,7 @@ def groupnorm_workspace(batch: int, groups: int, device) -> torch.Tensor:
 
 
 def groupnorm(x0, gamma, beta, *, groups: int, eps: float, silu: bool, x1=None, out_norm=None, out_raw=None,
-              want_raw: bool = False, partials=None):
+              want_raw: bool = False, partials=None, x0_stats=None, x1_stats=None):
     """x0: fp32 [B, HW.., C0] NHWC (+ optional x1 [B, HW.., C1] concatenated on channels)."""
     _chk(x0, f32, "x0"); _chk(x1, f32, "x1", allow_none=True)
     _chk(gamma, f32, "gamma"); _chk(beta, f32, "beta")
@@ -122,7 +127,8 @@ def groupnorm(x0, gamma, beta, *, groups: int, eps: float, silu: bool, x1=None, 
         partials = groupnorm_workspace(B, groups, x0.device)
     args = _lib.GroupNormArgs(x0=x0.data_ptr(), c0=c0, x1=_lib.ptr(x1), c1=c1, batch=B, hw=hw, groups=groups, eps=eps,
                               gamma=gamma.data_ptr(), beta=beta.data_ptr(), silu=int(silu),
-                              out_norm=out_norm.data_ptr(), out_raw=_lib.ptr(out_raw), partials=partials.data_ptr())
+                              out_norm=out_norm.data_ptr(), out_raw=_lib.ptr(out_raw), partials=partials.data_ptr(),
+                              x0_stats=_lib.ptr(x0_stats), x1_stats=_lib.ptr(x1_stats))
     _lib.call("idb_groupnorm", C.byref(args), _lib.stream_ptr())
     return out_norm, out_raw
 

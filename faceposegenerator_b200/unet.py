@@ -192,28 +192,33 @@ class UNet2DConditionModel:
             return self._gemm(a0, w, **kw)
         return self._gemm(a0, w, lora_down=ld, lora_up=lu, lora_seg_n=seg_n, **kw)
 
-    def _resnet(self, r: _Resnet, h, skip, temb, gnws):
+    # A "stream" value is (fp32 NHWC tensor, row-block channel statistics or None): every GEMM that
+    # produces a residual-stream tensor also emits the sums GroupNorm needs, so the norm reads it once.
+    def _resnet(self, r: _Resnet, hs, skip, temb, gnws):
+        h, h_st = hs
+        sk, sk_st = skip if skip is not None else (None, None)
         B, H, W = h.shape[0], h.shape[1], h.shape[2]
-        n1, raw = ops.groupnorm(h, r.g1, r.b1, groups=self.groups, eps=self.eps, silu=True, x1=skip,
-                                want_raw=r.shortcut, partials=gnws)
-        t1, _ = self._gemm(n1, r.w1, mode=ops.A_3X3, bias=r.bias1, rowvec=temb[:, r.temb_off:],
-                           rowvec_ld=temb.shape[1], want_f32=True)
+        n1, raw = ops.groupnorm(h, r.g1, r.b1, groups=self.groups, eps=self.eps, silu=True, x1=sk,
+                                want_raw=r.shortcut, partials=gnws, x0_stats=h_st, x1_stats=sk_st)
+        t1, _, t1_st = self._gemm(n1, r.w1, mode=ops.A_3X3, bias=r.bias1, rowvec=temb[:, r.temb_off:],
+                                  rowvec_ld=temb.shape[1], want_f32=True, want_stats=True)
         t1 = t1.view(B, H, W, r.cout)
-        n2, _ = ops.groupnorm(t1, r.g2, r.b2, groups=self.groups, eps=self.eps, silu=True, partials=gnws)
+        n2, _ = ops.groupnorm(t1, r.g2, r.b2, groups=self.groups, eps=self.eps, silu=True, partials=gnws, x0_stats=t1_st)
         if r.shortcut:
-            o, _ = self._gemm(n2, r.w2, mode=ops.A_3X3, a1=raw, bias=r.bias2, want_f32=True)
+            o, _, o_st = self._gemm(n2, r.w2, mode=ops.A_3X3, a1=raw, bias=r.bias2, want_f32=True, want_stats=True)
         else:
-            o, _ = self._gemm(n2, r.w2, mode=ops.A_3X3, bias=r.bias2, residual=h, want_f32=True)
-        return o.view(B, H, W, r.cout)
+            o, _, o_st = self._gemm(n2, r.w2, mode=ops.A_3X3, bias=r.bias2, residual=h, want_f32=True, want_stats=True)
+        return o.view(B, H, W, r.cout), o_st
 
     def _context_kv(self, t: _Transformer, ctx_bf16):
         _, kv = self._lin_lora(ctx_bf16, t.w_kv2, t.lora["kv2"], t.c, want_bf16=True)
         return kv
 
-    def _transformer(self, t: _Transformer, h, kv, n_ctx, gnws):
+    def _transformer(self, t: _Transformer, hs, kv, n_ctx, gnws):
+        h, h_st = hs
         B, H, W, Cc = h.shape
         M, T = B * H * W, H * W
-        n, _ = ops.groupnorm(h, t.gn_g, t.gn_b, groups=self.groups, eps=1e-6, silu=False, partials=gnws)
+        n, _ = ops.groupnorm(h, t.gn_g, t.gn_b, groups=self.groups, eps=1e-6, silu=False, partials=gnws, x0_stats=h_st)
         x0, _ = self._gemm(n.view(M, Cc), t.w_in, bias=t.b_in, want_f32=True)
         # self-attention
         a = ops.layernorm(x0, *t.ln[0])
@@ -231,8 +236,8 @@ class UNet2DConditionModel:
         a = ops.layernorm(x2, *t.ln[2])
         _, g = self._gemm(a, t.w_ff1, bias=t.b_ff1, geglu=True, want_bf16=True)
         _, x3 = self._gemm(g, t.w_ff2, bias=t.b_ff2, residual=x2, want_bf16=True)
-        out, _ = self._gemm(x3, t.w_out, bias=t.b_out, residual=h.view(M, Cc), want_f32=True)
-        return out.view(B, H, W, Cc)
+        out, _, out_st = self._gemm(x3, t.w_out, bias=t.b_out, residual=h.view(M, Cc), want_f32=True, want_stats=True)
+        return out.view(B, H, W, Cc), out_st
 
     # ------------------------------------------------------------------ step-invariant context projections
     def encode_context(self, encoder_hidden_states: torch.Tensor):
@@ -269,9 +274,10 @@ class UNet2DConditionModel:
 
         def tap(name, v):
             if taps is not None:
-                taps[name] = v.permute(0, 3, 1, 2).float().clone()
+                taps[name] = v[0].permute(0, 3, 1, 2).float().clone()
 
-        h, _ = ops.conv3x3_small_cin(x, self.w_conv_in, self.b_conv_in, nchw=True)
+        h0, _ = ops.conv3x3_small_cin(x, self.w_conv_in, self.b_conv_in, nchw=True)
+        h = (h0, None)   # conv_in is a SIMT kernel: its GroupNorm consumer computes the statistics itself
         tap("conv_in", h)
         skips = [h]
         for i, blk in enumerate(self.down):
@@ -283,9 +289,10 @@ class UNet2DConditionModel:
                     tap(f"down_blocks.{i}.attentions.{j}", h)
                 skips.append(h)
             if blk.down is not None:
-                hb = ops.cast_bf16(h)
-                o, _ = self._gemm(hb, blk.down[0], mode=ops.A_3X3_S2, bias=blk.down[1], want_f32=True)
-                h = o.view(B, h.shape[1] // 2, h.shape[2] // 2, h.shape[3])
+                ht = h[0]
+                hb = ops.cast_bf16(ht)
+                o, _, o_st = self._gemm(hb, blk.down[0], mode=ops.A_3X3_S2, bias=blk.down[1], want_f32=True, want_stats=True)
+                h = (o.view(B, ht.shape[1] // 2, ht.shape[2] // 2, ht.shape[3]), o_st)
                 skips.append(h)
         h = self._resnet(self.mid.res0, h, None, temb, gnws)
         h = self._transformer(self.mid.attn, h, next(kvs), context.n_ctx, gnws)
@@ -298,10 +305,12 @@ class UNet2DConditionModel:
                     h = self._transformer(blk.attns[j], h, next(kvs), context.n_ctx, gnws)
                 tap(f"up_blocks.{i}.{j}", h)
             if blk.up is not None:
-                hu = ops.upsample2x(h)
-                o, _ = self._gemm(hu, blk.up[0], mode=ops.A_3X3, bias=blk.up[1], want_f32=True)
-                h = o.view(B, hu.shape[1], hu.shape[2], h.shape[3])
-        n, _ = ops.groupnorm(h, self.out_g, self.out_b, groups=self.groups, eps=self.eps, silu=True, partials=gnws)
+                ht = h[0]
+                hu = ops.upsample2x(ht)
+                o, _, o_st = self._gemm(hu, blk.up[0], mode=ops.A_3X3, bias=blk.up[1], want_f32=True, want_stats=True)
+                h = (o.view(B, hu.shape[1], hu.shape[2], ht.shape[3]), o_st)
+        n, _ = ops.groupnorm(h[0], self.out_g, self.out_b, groups=self.groups, eps=self.eps, silu=True, partials=gnws,
+                             x0_stats=h[1])
         eps = ops.conv3x3_small_cout(n, self.w_conv_out, self.b_conv_out)
         if in_dtype != f32:
             eps = eps.to(in_dtype)

@@ -112,24 +112,27 @@ class AutoencoderKL:
     def _gemm(self, a0, w, **kw):
         return ops.gemm_conv(a0, w, k_splits=0, workspace=self._ws(), **kw)
 
-    def _resnet(self, r, h, gnws):
+    # stream value = (fp32 NHWC tensor, row-block channel statistics or None), see unet.py
+    def _resnet(self, r, hs, gnws):
+        h, h_st = hs
         B, H, W = h.shape[:3]
         n1, raw = ops.groupnorm(h, r.g1, r.b1, groups=self.groups, eps=self.eps, silu=True, want_raw=r.shortcut,
-                                partials=gnws)
-        t1, _ = self._gemm(n1, r.w1, mode=ops.A_3X3, bias=r.bias1, want_f32=True)
+                                partials=gnws, x0_stats=h_st)
+        t1, _, t1_st = self._gemm(n1, r.w1, mode=ops.A_3X3, bias=r.bias1, want_f32=True, want_stats=True)
         n2, _ = ops.groupnorm(t1.view(B, H, W, r.cout), r.g2, r.b2, groups=self.groups, eps=self.eps, silu=True,
-                              partials=gnws)
+                              partials=gnws, x0_stats=t1_st)
         if r.shortcut:
-            o, _ = self._gemm(n2, r.w2, mode=ops.A_3X3, a1=raw, bias=r.bias2, want_f32=True)
+            o, _, o_st = self._gemm(n2, r.w2, mode=ops.A_3X3, a1=raw, bias=r.bias2, want_f32=True, want_stats=True)
         else:
-            o, _ = self._gemm(n2, r.w2, mode=ops.A_3X3, bias=r.bias2, residual=h, want_f32=True)
-        return o.view(B, H, W, r.cout)
+            o, _, o_st = self._gemm(n2, r.w2, mode=ops.A_3X3, bias=r.bias2, residual=h, want_f32=True, want_stats=True)
+        return o.view(B, H, W, r.cout), o_st
 
-    def _attention(self, h, gnws):
+    def _attention(self, hs, gnws):
+        h, h_st = hs
         at = self.attn
         B, H, W, Cc = h.shape
         T = H * W
-        n, _ = ops.groupnorm(h, at.g, at.b, groups=self.groups, eps=self.eps, silu=False, partials=gnws)
+        n, _ = ops.groupnorm(h, at.g, at.b, groups=self.groups, eps=self.eps, silu=False, partials=gnws, x0_stats=h_st)
         n2 = n.view(B * T, Cc)
         _, q = self._gemm(n2, at.wq, bias=at.bq, want_bf16=True)
         _, k = self._gemm(n2, at.wk, bias=at.bk, want_bf16=True)
@@ -143,8 +146,8 @@ class AutoencoderKL:
             self._gemm(q[sl], k[sl], out_f32=s)                # S = Q K^T      [T, T]
             ops.softmax_rows(s, Cc ** -0.5, out=p)
             self._gemm(p, vt, out_bf16=o[sl])                  # O = P V        [T, C]
-        out, _ = self._gemm(o, at.wo, bias=at.bo, residual=h.view(B * T, Cc), want_f32=True)
-        return out.view(B, H, W, Cc)
+        out, _, out_st = self._gemm(o, at.wo, bias=at.bo, residual=h.view(B * T, Cc), want_f32=True, want_stats=True)
+        return out.view(B, H, W, Cc), out_st
 
     def decode(self, z, return_dict: bool = True, generator=None, output_image: bool = False,
                taps: Optional[dict] = None):
@@ -156,22 +159,25 @@ class AutoencoderKL:
         B = z.shape[0]
         gnws = ops.groupnorm_workspace(B, self.groups, self.device)
         x = ops.vae_latent_prep(z, self.pq_w, self.pq_b, 1.0)
-        h, _ = ops.conv3x3_small_cin(x, self.w_in, self.b_in, nchw=False)
+        h0, _ = ops.conv3x3_small_cin(x, self.w_in, self.b_in, nchw=False)
+        h = (h0, None)
         h = self._resnet(self.mid0, h, gnws)
         h = self._attention(h, gnws)
         h = self._resnet(self.mid1, h, gnws)
         if taps is not None:
-            taps["mid"] = h.permute(0, 3, 1, 2).clone()
+            taps["mid"] = h[0].permute(0, 3, 1, 2).clone()
         for i, blk in enumerate(self.up):
             for r in blk.resnets:
                 h = self._resnet(r, h, gnws)
             if blk.up is not None:
-                hu = ops.upsample2x(h)
-                o, _ = self._gemm(hu, blk.up[0], mode=ops.A_3X3, bias=blk.up[1], want_f32=True)
-                h = o.view(B, hu.shape[1], hu.shape[2], h.shape[3])
+                ht = h[0]
+                hu = ops.upsample2x(ht)
+                o, _, o_st = self._gemm(hu, blk.up[0], mode=ops.A_3X3, bias=blk.up[1], want_f32=True, want_stats=True)
+                h = (o.view(B, hu.shape[1], hu.shape[2], ht.shape[3]), o_st)
             if taps is not None:
-                taps[f"up{i}"] = h.permute(0, 3, 1, 2).clone()
-        n, _ = ops.groupnorm(h, self.out_g, self.out_b, groups=self.groups, eps=self.eps, silu=True, partials=gnws)
+                taps[f"up{i}"] = h[0].permute(0, 3, 1, 2).clone()
+        n, _ = ops.groupnorm(h[0], self.out_g, self.out_b, groups=self.groups, eps=self.eps, silu=True, partials=gnws,
+                             x0_stats=h[1])
         img = ops.conv3x3_small_cout(n, self.w_out, self.b_out, postprocess=output_image)
         if not output_image and in_dtype != f32:
             img = img.to(in_dtype)

@@ -100,6 +100,10 @@ typedef struct {
   int32_t k_splits;
   float* workspace;
   size_t workspace_bytes;
+  /* optional: per-32-row-block channel statistics of the fp32 output, [ceil(M/32), N_out, 2] floats =
+   * (sum, sum of squares), written by the epilogue for free; idb_groupnorm consumes them instead of
+   * re-reading the tensor.  Needs out_f32, Wo a power of two (or a multiple of 128) and Ho*Wo % 32 == 0. */
+  float* stats_partials;
 } idb_gemm_conv_args;
 
 int idb_gemm_conv(const idb_gemm_conv_args* args, void* stream);
@@ -143,6 +147,10 @@ typedef struct {
   void* out_norm;                    /* bf16 */
   void* out_raw;                     /* bf16 or NULL */
   float* partials;
+  /* optional: row-block statistics produced by idb_gemm_conv(stats_partials) for x0 / x1
+   * ([hw/32 * batch, C, 2] each).  When given for every source the statistics pass over x is skipped. */
+  const float* x0_stats;
+  const float* x1_stats;
 } idb_groupnorm_args;
 int idb_groupnorm(const idb_groupnorm_args* args, void* stream);
 size_t idb_groupnorm_workspace_bytes(int32_t batch, int32_t groups);

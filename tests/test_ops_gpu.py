@@ -305,3 +305,32 @@ def test_cfg_ddpm_step_vs_oracle(ops, cuda_dev, use_cfg, vpred):
                                  use_cfg=use_cfg, v_prediction=vpred, x0_out=x0)
         assert rel(prev.cpu(), ref_prev) < 2e-6
         assert rel(x0.cpu(), ref_x0) < 2e-6
+
+
+@pytest.mark.parametrize("B,H,W,C0,C1,N", [(2, 64, 64, 320, 0, 320), (3, 8, 8, 1280, 1280, 1280), (2, 32, 32, 640, 320, 640),
+                                           (1, 256, 256, 128, 0, 128)])
+def test_groupnorm_from_epilogue_statistics(ops, cuda_dev, B, H, W, C0, C1, N):
+    """GroupNorm fed by the row-block channel sums that the producing conv GEMM wrote in its epilogue
+    (no statistics pass over the tensor) == GroupNorm that reads the tensor itself."""
+    g = torch.Generator(device="cuda").manual_seed(H + C0)
+    def produce(cin, cout):
+        x = rb(torch.randn(B, H, W, cin, device=cuda_dev, generator=g))
+        w = rb(torch.randn(cout, cin, 3, 3, device=cuda_dev, generator=g) / math.sqrt(9 * cin))
+        bias = torch.randn(cout, device=cuda_dev, generator=g)
+        o, _, st = ops.gemm_conv(x, pack_conv_w(w), mode=ops.A_3X3, bias=bias, want_f32=True, want_stats=True,
+                                 k_splits=0, workspace=torch.empty(16 << 20, dtype=torch.float32, device=cuda_dev))
+        return o.view(B, H * W, cout), st
+    x0, s0 = produce(64, C0)
+    x1, s1 = produce(64, C1) if C1 else (None, None)
+    # the partial sums themselves
+    ref_s = x0.view(B * H * W // 32, 32, C0).sum(1)
+    assert rel(s0[..., 0], ref_s) < 1e-5
+    C = C0 + C1
+    gamma = 1 + 0.1 * torch.randn(C, device=cuda_dev, generator=g)
+    beta = 0.1 * torch.randn(C, device=cuda_dev, generator=g)
+    y_fused, _ = ops.groupnorm(x0, gamma, beta, groups=32, eps=1e-5, silu=True, x1=x1, x0_stats=s0, x1_stats=s1)
+    y_plain, _ = ops.groupnorm(x0, gamma, beta, groups=32, eps=1e-5, silu=True, x1=x1)
+    xc = torch.cat([x0, x1], -1) if C1 else x0
+    ref = F.silu(F.group_norm(xc.permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
+    assert rel(y_fused.float(), ref) < 4e-3
+    assert (y_fused.float() - y_plain.float()).abs().max() < 0.07

@@ -20,5 +20,5 @@ a.record()
 for _ in range(20): fn()
 b.record(); torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 20
-print(json.dumps({"poly": os.environ.get("IDB_ATTN_POLY", "3"), "variant": os.environ.get("IDB_ATTN_VARIANT", "auto"), "rel_err": err, "ms_T4096_B8": round(ms, 4),
+print(json.dumps({"poly": os.environ.get("IDB_ATTN_POLY", "3"), "variant": os.environ.get("IDB_ATTN_VARIANT", "auto"), "packed": os.environ.get("IDB_ATTN_PACKED", "1"), "rel_err": err, "ms_T4096_B8": round(ms, 4),
                   "tflops": round(4.0 * B * h * T * T * 64 / ms / 1e9, 1)}))
