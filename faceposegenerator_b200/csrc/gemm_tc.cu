@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   static_assert(CG == 1 || !LORA, "fused LoRA runs on the 1-CTA kernel");
   static_assert(B_ROWS % 8 == 0, "B tile must be whole 8-row swizzle groups");
   constexpr int STG_OFFSET = STAGES * STAGE_BYTES + 1024;   // barriers live in the first 1 KiB after the ring (keeps 1024-B alignment)
+  constexpr int LORA_STG_OFFSET = STG_OFFSET + EPI_STAGING_BYTES;   // per-warp [16][32] fp32 LoRA up-weight tile (LORA only)
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
   static_assert(UMMA_N <= TMEM_BUF_STRIDE, "accumulator does not fit its TMEM buffer");
   static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment for SWIZZLE_128B");
@@ -335,17 +336,52 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
         }
         if (LORA) {
-          const float* up = p.lora_up + static_cast<long long>(col) * p.lora_rank_pad;
-          for (int r4 = 0; r4 < p.lora_rank_pad; r4 += 4) {
-            float t0, t1, t2, t3;  // lt[] index must be compile-time to stay in registers
-            if (r4 == 0) t0 = lt[0], t1 = lt[1], t2 = lt[2], t3 = lt[3];
-            else if (r4 == 4) t0 = lt[4], t1 = lt[5], t2 = lt[6], t3 = lt[7];
-            else if (r4 == 8) t0 = lt[8], t1 = lt[9], t2 = lt[10], t3 = lt[11];
-            else t0 = lt[12], t1 = lt[13], t2 = lt[14], t3 = lt[15];
+          // up-projection weights of this chunk's 32 columns: lane c fetches column col + c (coalesced),
+          // the warp transposes them through smem to [rank][32] so every lane can read them as
+          // broadcast float4s, and the rank-r update runs as packed fp32x2 FMAs.
+          float* lsm = reinterpret_cast<float*>(smem + LORA_STG_OFFSET) + warp * (16 * 32);
+          const float* up = p.lora_up + static_cast<long long>(col + lane) * p.lora_rank_pad;
+          __syncwarp();
+          if (p.lora_rank_pad == 4) {   // the common case (rank <= 4): fully unrolled, no dynamic indexing
+            const float4 u0 = __ldg(reinterpret_cast<const float4*>(up));
+            lsm[lane] = u0.x, lsm[32 + lane] = u0.y, lsm[64 + lane] = u0.z, lsm[96 + lane] = u0.w;
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float4 u = __ldg(reinterpret_cast<const float4*>(up + j * p.lora_rank_pad + r4));
-              acc[j] += t0 * u.x + t1 * u.y + t2 * u.z + t3 * u.w;
+            for (int rr = 0; rr < 4; ++rr) {
+              const float4* row = reinterpret_cast<const float4*>(lsm + rr * 32);
+              const float tr = lt[rr];
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                const float4 u = row[jj];
+                ffma2(acc[4 * jj], acc[4 * jj + 1], tr, tr, u.x, u.y, acc[4 * jj], acc[4 * jj + 1]);
+                ffma2(acc[4 * jj + 2], acc[4 * jj + 3], tr, tr, u.z, u.w, acc[4 * jj + 2], acc[4 * jj + 3]);
+              }
+            }
+          } else {
+            for (int r4 = 0; r4 < p.lora_rank_pad; r4 += 4) {
+              const float4 u = __ldg(reinterpret_cast<const float4*>(up + r4));
+              lsm[(r4 + 0) * 32 + lane] = u.x;
+              lsm[(r4 + 1) * 32 + lane] = u.y;
+              lsm[(r4 + 2) * 32 + lane] = u.z;
+              lsm[(r4 + 3) * 32 + lane] = u.w;
+            }
+            __syncwarp();
+            for (int r4 = 0; r4 < p.lora_rank_pad; r4 += 4) {
+              float tq[4];  // lt[] index must be compile-time to stay in registers
+              if (r4 == 0) tq[0] = lt[0], tq[1] = lt[1], tq[2] = lt[2], tq[3] = lt[3];
+              else if (r4 == 4) tq[0] = lt[4], tq[1] = lt[5], tq[2] = lt[6], tq[3] = lt[7];
+              else if (r4 == 8) tq[0] = lt[8], tq[1] = lt[9], tq[2] = lt[10], tq[3] = lt[11];
+              else tq[0] = lt[12], tq[1] = lt[13], tq[2] = lt[14], tq[3] = lt[15];
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr) {
+                const float4* row = reinterpret_cast<const float4*>(lsm + (r4 + rr) * 32);
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const float4 u = row[jj];
+                  ffma2(acc[4 * jj], acc[4 * jj + 1], tq[rr], tq[rr], u.x, u.y, acc[4 * jj], acc[4 * jj + 1]);
+                  ffma2(acc[4 * jj + 2], acc[4 * jj + 3], tq[rr], tq[rr], u.z, u.w, acc[4 * jj + 2], acc[4 * jj + 3]);
+                }
+              }
             }
           }
         }
@@ -507,7 +543,8 @@ static int pow2_divisor(int v, int cap) {
 template <int BLOCK_N, int STAGES, bool LORA, int CG>
 static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
   constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
-  constexpr int smem_bytes = STAGES * (A_TILE_BYTES + (UMMA_N / CG) * BLOCK_K * 2) + 1024 + 1024 + EPI_STAGING_BYTES;
+  constexpr int smem_bytes = STAGES * (A_TILE_BYTES + (UMMA_N / CG) * BLOCK_K * 2) + 1024 + 1024 + EPI_STAGING_BYTES +
+                             (LORA ? NUM_EPI_WARPS * 16 * 32 * 4 : 0);
   static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
   auto kern = gemm_tc_kernel<BLOCK_N, STAGES, LORA, CG>;
   static bool configured = false;  // per instantiation
