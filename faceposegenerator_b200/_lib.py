@@ -98,6 +98,7 @@ EXPORTS = {
 }
 
 _lib: Optional[C.CDLL] = None
+trace = None      # profiling only: set to a list to record (entry point, description) per call
 launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
 _LAUNCHES_PER_CALL = {"idb_groupnorm": 2, "idb_time_embed": 4}   # (a lower bound for split-K GEMMs)
 
@@ -138,8 +139,10 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def call(name: str, *args) -> None:
+def call(name: str, *args, desc=None) -> None:
     global launch_count
+    if trace is not None:
+        trace.append((name, desc))
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (code {rc}): {last_error()}")

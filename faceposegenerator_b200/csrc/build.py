@@ -46,6 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
         cmd = [_nvcc(), *ARCH_FLAGS, "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
                "--expt-relaxed-constexpr", "-c", os.path.join(HERE, src), "-o", obj]
+        cmd += os.environ.get("IDB_NVCC_EXTRA", "").split()   # e.g. -DIDB_EPI_PROF=1 for the epilogue clock() breakdown
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -25,21 +25,47 @@
 #include "idb_common.cuh"
 #include "idb_host.h"
 
+#ifndef IDB_EPI_PROF
+#define IDB_EPI_PROF 0
+#endif
+
 namespace idb {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = 512;
-constexpr int TMEM_BUF_STRIDE = 256;
-constexpr int EPI_STG_F32 = 32 * 32 * 4;                            // per-warp fp32 staging chunk (SWIZZLE_128B rows of 128 B)
-constexpr int EPI_STG_B16 = 32 * 32 * 2;                            // per-warp bf16 staging chunk (dense rows of 64 B)
-constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * (EPI_STG_F32 + EPI_STG_B16);  // 49,152 B
+constexpr int EPI_BUF_BYTES = 32 * 32 * 4;                          // per-warp staging buffer: a 32 x 32 fp32 chunk (SWIZZLE_128B rows) or a bf16 chunk
+constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_BUF_BYTES;    // 65,536 B
+constexpr int EPI_BIAS_BYTES = NUM_EPI_WARPS * 2 * 32 * 4;          // per-warp bias of its (<= 2) chunks of the tile
+constexpr int RES_BAR_OFFSET = 512;                                 // residual-load mbarriers [warp] inside the barrier KiB
+
+// Division of small non-negative integers by a launch-time constant: q = (x * ceil(2^40 / d)) >> 40, exact for
+// x, d < 2^20 (the host checks).  A runtime `/` costs ~25 dependent instructions; the tile loops of the three
+// warp roles decode a tile index with six of them, which dominated small-K tiles.
+struct FastDiv {
+  unsigned long long mul;
+  int d;
+  __host__ void set(int dd) {
+    d = dd;
+    mul = ((1ull << 40) + static_cast<unsigned long long>(dd) - 1) / static_cast<unsigned long long>(dd);
+  }
+  __device__ __forceinline__ int div(int x) const { return static_cast<int>((static_cast<unsigned long long>(x) * mul) >> 40); }
+  __device__ __forceinline__ void divmod(int x, int& q, int& r) const {
+    q = div(x);
+    r = x - q * d;
+  }
+};
+
+struct TileCoord {
+  int n_blk, ks, m_blk, tx, ty, tb;
+};
 
 struct GemmParams {
-  CUtensorMap tmA0, tmA1, tmW, tmL, tmOutF, tmOutB;   // tmOut*: 4-D [N_out, Wo, Ho, B] store maps (32-row boxes)
+  FastDiv fd_ntn, fd_ks, fd_tx, fd_ty, fd_seg;
+  CUtensorMap tmA0, tmA1, tmW, tmW1, tmL, tmOutF, tmOutB, tmRes;   // tmOut* / tmRes: 4-D [N_out, Wo, Ho, B] maps (32-row boxes); tmW1: W box of the pair's second CTA (LoRA)
   int mode0, cpb0, c0, nkb0, nkb1;
   int Ho, Wo, B;
   int BW, BH, BB;
@@ -54,12 +80,24 @@ struct GemmParams {
   const float* lora_up;
   int lora_rank_pad, lora_seg_n;
   int flags;
-  int debug;  // profiling only (IDB_GEMM_DEBUG): 1 = no MMA issue, 2 = no TMA loads
+  int debug;  // profiling only (IDB_GEMM_DEBUG): 1 = no MMA issue, 2 = no TMA loads, 4 = TMEM read only, 5 = no epilogue, 6 = no TMA stores
   float* out_f32;
   __nv_bfloat16* out_bf16;
   float* workspace;
   float2* stats;   // optional [ceil(M/32)][N] (sum, sum of squares) over each 32-row block of the fp32 output
 };
+
+template <int CG>
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, int rank) {
+  TileCoord c;
+  int t, mu, m2;
+  p.fd_ntn.divmod(tile, t, c.n_blk);
+  p.fd_ks.divmod(t, mu, c.ks);
+  c.m_blk = mu * CG + rank;
+  p.fd_tx.divmod(c.m_blk, m2, c.tx);
+  p.fd_ty.divmod(m2, c.tb, c.ty);
+  return c;
+}
 
 template <int BLOCK_N, int STAGES, bool LORA, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
@@ -68,12 +106,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
   constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M * CG, UMMA_N, 0, 0);
-  static_assert(CG == 1 || !LORA, "fused LoRA runs on the 1-CTA kernel");
   static_assert(B_ROWS % 8 == 0, "B tile must be whole 8-row swizzle groups");
   constexpr int STG_OFFSET = STAGES * STAGE_BYTES + 1024;   // barriers live in the first 1 KiB after the ring (keeps 1024-B alignment)
-  constexpr int LORA_STG_OFFSET = STG_OFFSET + EPI_STAGING_BYTES;   // per-warp [16][32] fp32 LoRA up-weight tile (LORA only)
+  constexpr int BIAS_STG_OFFSET = STG_OFFSET + EPI_STAGING_BYTES;
+  constexpr int LORA_STG_OFFSET = BIAS_STG_OFFSET + EPI_BIAS_BYTES;   // per-warp [16][32] fp32 LoRA up-weight tile (LORA only)
+  static_assert(BLOCK_N <= 256, "each epilogue warp stages at most two chunks per tile");
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
-  static_assert(UMMA_N <= TMEM_BUF_STRIDE, "accumulator does not fit its TMEM buffer");
+  // accumulator ring in TMEM: as many buffers as fit the 512 columns, so the MMA warp can run further ahead of the
+  // (latency-bound) epilogue of small-K tiles
+  constexpr int TMEM_BUF_STRIDE = (UMMA_N + 31) / 32 * 32;
+  constexpr int NBUF = (TMEM_COLS / TMEM_BUF_STRIDE) > 4 ? 4 : (TMEM_COLS / TMEM_BUF_STRIDE);
+  static_assert(NBUF >= 2, "need at least a double-buffered accumulator");
   static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment for SWIZZLE_128B");
 
   extern __shared__ uint8_t smem_raw[];
@@ -81,8 +124,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_empty = tmem_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -95,11 +138,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     tma_prefetch_desc(&p.tmW);
     if (p.nkb1 > 0) tma_prefetch_desc(&p.tmA1);
     if (LORA) tma_prefetch_desc(&p.tmL);
+    if (p.residual != nullptr) tma_prefetch_desc(&p.tmRes);
+    for (int w = 0; w < NUM_EPI_WARPS; ++w)
+      mbar_init(reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + RES_BAR_OFFSET) + w, 1);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], CG);     // one producer arrival per CTA of the pair (leader's barrier is the one used)
       mbar_init(&empty_bar[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < NBUF; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], NUM_EPI_WARPS * CG);
     }
@@ -128,20 +174,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       uint32_t phase = 0;
       const uint32_t smem_base = smem_u32(smem);
       for (int tile = unit; tile < total_tiles; tile += num_units) {
-        int t = tile;
-        const int n_blk = t % p.n_tiles_n;
-        t /= p.n_tiles_n;
-        const int ks = t % p.k_splits;
-        const int m_blk = (t / p.k_splits) * CG + rank;
-        const int tx = m_blk % p.tiles_x;
-        const int ty = (m_blk / p.tiles_x) % p.tiles_y;
-        const int tb = m_blk / (p.tiles_x * p.tiles_y);   // >= number of batch tiles for a padding block: TMA zero-fills
+        const TileCoord tc_ = decode_tile<CG>(p, tile, rank);
+        const int n_blk = tc_.n_blk, ks = tc_.ks;
+        const int tx = tc_.tx, ty = tc_.ty, tb = tc_.tb;   // tb >= number of batch tiles for a padding block: TMA zero-fills
         const int x0 = tx * p.BW, y0 = ty * p.BH, b0 = tb * p.BB;
         const int n0 = n_blk * BLOCK_N + rank * B_ROWS;
+        const int lora_row = LORA ? p.fd_seg.div(n_blk * BLOCK_N) * 16 : 0;   // this tile's adapter (16 padded down-projection rows)
         const int kb_begin = ks * p.kb_per_split;
         const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
         // running (tap, channel-block) counters instead of a division per k-block
-        int tap = (kb_begin < p.nkb0) ? kb_begin / p.cpb0 : 0;
+        int tap = (kb_begin > 0 && kb_begin < p.nkb0) ? kb_begin / p.cpb0 : 0;   // (only split-K tiles divide)
         int cbi = (kb_begin < p.nkb0) ? kb_begin - tap * p.cpb0 : 0;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -172,7 +214,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
           const CUtensorMap* tmA = seg1 ? &p.tmA1 : &p.tmA0;
           if (elect_one()) {
-            if (p.debug == 2 || p.debug == 3) {  // feed-rate experiment: signal the stage without moving data
+            if ((p.debug & 15) == 2 || (p.debug & 15) == 3) {  // feed-rate experiment: signal the stage without moving data
               if (CG == 1 || rank == 0) mbar_expect_tx_a(fb, 0);
               else mbar_arrive_remote_a(fb, 0);
             } else if (CG == 1) {
@@ -180,11 +222,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               if (five) tma_load_5d_a(sa, tmA, fb, c0, c1, c2, c3, c4);
               else tma_load_4d_a(sa, tmA, fb, c0, c1, c2, c3);
               tma_load_2d_a(sb, &p.tmW, fb, kb * BLOCK_K, n0);
-              if (LORA) tma_load_2d_a(sb + BLOCK_N * BLOCK_K * 2, &p.tmL, fb, kb * BLOCK_K, (n0 / p.lora_seg_n) * 16);
+              if (LORA) tma_load_2d_a(sb + BLOCK_N * BLOCK_K * 2, &p.tmL, fb, kb * BLOCK_K, lora_row);
             } else {
               if (five) tma2_load_5d_a(sa, tmA, fb, c0, c1, c2, c3, c4);
               else tma2_load_4d_a(sa, tmA, fb, c0, c1, c2, c3);
-              tma2_load_2d_a(sb, &p.tmW, fb, kb * BLOCK_K, n0);
+              if (!LORA) {
+                tma2_load_2d_a(sb, &p.tmW, fb, kb * BLOCK_K, n0);
+              } else if (rank == 0) {   // B rows [0, UMMA_N/2) of the pair's tile: all base-weight rows
+                tma2_load_2d_a(sb, &p.tmW, fb, kb * BLOCK_K, n0);
+              } else {                  // B rows [UMMA_N/2, UMMA_N): the remaining base rows, then the 16 LoRA-down rows
+                constexpr int W1_ROWS = BLOCK_N - B_ROWS;
+                tma2_load_2d_a(sb, &p.tmW1, fb, kb * BLOCK_K, n0);
+                tma2_load_2d_a(sb + W1_ROWS * BLOCK_K * 2, &p.tmL, fb, kb * BLOCK_K, lora_row);
+              }
               if (rank == 0) mbar_expect_tx_a(fb, 2 * STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
               else mbar_arrive_remote_a(fb, 0);
             }
@@ -202,20 +252,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
+      int it = 0, buf = 0;
+      uint32_t bphase = 0;
+      uint32_t mma_wait_empty = 0, mma_wait_full = 0;
+      const uint32_t mma_t0 = IDB_EPI_PROF ? clock() : 0u;
       const uint32_t smem_base = smem_u32(smem);
       const uint64_t desc_hi = umma_smem_desc_sw128(0);
       for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
-        const int ks = (tile / p.n_tiles_n) % p.k_splits;
+        const int ks = decode_tile<CG>(p, tile, 0).ks;
         const int kb_begin = ks * p.kb_per_split;
         const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
-        const int buf = it & 1;
-        mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
+        const uint32_t c0 = IDB_EPI_PROF ? clock() : 0u;
+        mbar_wait(&tmem_empty[buf], bphase ^ 1);
         tc_fence_after();
+        if (IDB_EPI_PROF) mma_wait_empty += clock() - c0;
         const uint32_t d_tmem = tmem_base + buf * TMEM_BUF_STRIDE;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
+          const uint32_t c2 = IDB_EPI_PROF ? clock() : 0u;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (IDB_EPI_PROF) mma_wait_full += clock() - c2;
           // descriptors are built convergently from warp-uniform values; one elected lane issues
           const uint32_t sa = smem_base + stage * STAGE_BYTES;
           const uint64_t adesc = desc_hi | static_cast<uint64_t>((sa >> 4) & 0x3FFF);
@@ -224,7 +280,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           const uint32_t tf = smem_base + STAGES * STAGE_BYTES + (2 * STAGES + buf) * 8;      // &tmem_full[buf]
           const uint32_t acc0 = (kb > kb_begin) ? 1u : 0u;
           if (elect_one()) {
-            if (p.debug != 1 && p.debug != 3) {
+            if ((p.debug & 15) != 1 && (p.debug & 15) != 3) {
               if (CG == 1) {
                 umma_bf16(d_tmem, adesc, bdesc, IDESC, acc0);
                 umma_bf16(d_tmem, adesc + 2, bdesc + 2, IDESC, 1u);   // +32 B per UMMA_K=16 step in the swizzle atom
@@ -251,15 +307,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             phase ^= 1;
           }
         }
+        if (++buf == NBUF) buf = 0, bphase ^= 1;
+      }
+      if (IDB_EPI_PROF && (p.debug & 0x400) && lane == 0 && p.workspace != nullptr) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(p.workspace) + static_cast<size_t>(gridDim.x) * NUM_EPI_WARPS * 8 + blockIdx.x * 4;
+        dst[0] = mma_wait_empty, dst[1] = mma_wait_full, dst[2] = clock() - mma_t0, dst[3] = it;
       }
     }
   } else {
     // ================================================================ epilogue warps
     // lane = accumulator row.  TMEM -> registers -> (bias, time-embedding row vector, LoRA up-projection,
-    // GEGLU, fp32 residual) -> per-warp smem staging chunk (32 rows x 32 columns) -> ONE TMA store per
+    // GEGLU, fp32 residual) -> per-warp smem staging buffer (32 rows x 32 columns) -> ONE TMA store per
     // chunk (4-D box over the NHWC output; rows outside the image are clipped by the TMA unit).
+    // 16 warps (4 per SM sub-partition): the per-chunk instruction stream is a long dependent chain, so
+    // the layers with K <= 1280 are bound by epilogue issue latency unless several warps interleave.
+    // Warp w owns TMEM lane quarter w & 3 and every 4th 32-column chunk (rotating with the tile index).
+    // The fp32 residual of a chunk is TMA-loaded INTO the staging buffer it is then added to and stored from.
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-    const int half = warp >> 2;    // which interleaved set of 32-column chunks
+    const int slot = warp >> 2;    // which interleaved set of 32-column chunks (rotates per tile)
     const int r = quarter * 32 + lane;
     const int rx = r % p.BW;
     const int ry = (r / p.BW) % p.BH;
@@ -268,27 +333,79 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const int bx0 = r0 % p.BW, by0 = (r0 / p.BW) % p.BH, bb0 = r0 / (p.BW * p.BH);
     const bool geglu = (p.flags & IDB_EPI_GEGLU) != 0;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t stg_f = smem_base + STG_OFFSET + warp * EPI_STG_F32;
-    const uint32_t stg_b = smem_base + STG_OFFSET + NUM_EPI_WARPS * EPI_STG_F32 + warp * EPI_STG_B16;
+    const uint32_t sbuf = smem_base + STG_OFFSET + warp * EPI_BUF_BYTES;
+    const uint32_t rbar = smem_base + STAGES * STAGE_BYTES + RES_BAR_OFFSET + warp * 8;
+    const bool both = p.out_f32 != nullptr && p.out_bf16 != nullptr;   // rare: staged and stored one after the other
+    const bool res_tma = p.residual != nullptr && !geglu && p.k_splits == 1 && (p.debug & 15) == 0;
     const int sw = lane & 7;       // SWIZZLE_128B phase of this lane's 128-byte fp32 staging row
+    constexpr int NCH = BLOCK_N / 32;
+    constexpr int MAXC = (NCH + 3) / 4;   // chunks per warp per tile
+    float* bsm = reinterpret_cast<float*>(smem + BIAS_STG_OFFSET) + warp * (MAXC * 32);
+    float* lsm = reinterpret_cast<float*>(smem + LORA_STG_OFFSET) + warp * (16 * 32);
+    uint32_t g = 0;                // residual chunks loaded so far (barrier parity = g & 1)
+    int buf = 0;                   // accumulator ring position of the current tile
+    uint32_t bphase = 0;
+    const bool prof = IDB_EPI_PROF && (p.debug & 0x400) != 0;   // per-warp clock() breakdown of the epilogue phases -> p.workspace (build with -DIDB_EPI_PROF=1)
+    uint32_t tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint32_t tc = 0;
+#define IDB_TICK(k)                       \
+  if (prof) {                             \
+    const uint32_t now = clock();         \
+    tp[k] += now - tc;                    \
+    tc = now;                             \
+  }
+    if (prof) tc = clock();
+
+    float pre_bias[MAXC];
+    float4 pre_up[MAXC];
+    auto prefetch_tables = [&](int tl, int itn) {   // lane c fetches column col + c of each chunk (coalesced)
+      const int n0_ = decode_tile<CG>(p, tl, 0).n_blk * BLOCK_N;
+#pragma unroll
+      for (int ci = 0; ci < MAXC; ++ci) {
+        const int col = n0_ + (((slot + itn) & 3) + 4 * ci) * 32 + lane;
+        const bool ok = (((slot + itn) & 3) + 4 * ci) < NCH && col < p.N;
+        pre_bias[ci] = (ok && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
+        if (LORA) pre_up[ci] = (ok && p.lora_rank_pad == 4) ? __ldg(reinterpret_cast<const float4*>(p.lora_up + static_cast<long long>(col) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (unit < total_tiles) prefetch_tables(unit, 0);
+
     int it = 0;
     for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
-      int t = tile;
-      const int n_blk = t % p.n_tiles_n;
-      t /= p.n_tiles_n;
-      const int ks = t % p.k_splits;
-      const int m_blk = (t / p.k_splits) * CG + rank;
-      const int tx = m_blk % p.tiles_x;
-      const int ty = (m_blk / p.tiles_x) % p.tiles_y;
-      const int tb = m_blk / (p.tiles_x * p.tiles_y);
+      const TileCoord tc_ = decode_tile<CG>(p, tile, rank);
+      const int n_blk = tc_.n_blk, ks = tc_.ks, m_blk = tc_.m_blk;
+      const int tx = tc_.tx, ty = tc_.ty, tb = tc_.tb;
       const int x = tx * p.BW + rx, y = ty * p.BH + ry, b = tb * p.BB + rb;
       const bool row_ok = (x < p.Wo) && (y < p.Ho) && (b < p.B);
       const long long orow = (static_cast<long long>(b) * p.Ho + y) * p.Wo + x;
       const int n0 = n_blk * BLOCK_N;
-      const int buf = it & 1;
+      const int chunk0 = (slot + it) & 3;
+      const int cx = tx * p.BW + bx0, cy = ty * p.BH + by0, cb = tb * p.BB + bb0;   // this warp's 32-row box
 
-      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      // ---- before the accumulator is ready: residual of the first chunk (TMA), bias and LoRA-up weights of
+      // all of this warp's chunks of the tile (lane c fetches column col + c, coalesced; kept in per-warp smem)
+      if (res_tma && chunk0 < NCH && n0 + chunk0 * 32 < p.N && lane == 0) {
+        tma_store_wait_read();                      // the previous store has finished reading the staging buffer
+        mbar_expect_tx_a(rbar, EPI_BUF_BYTES);
+        tma_load_4d_a(sbuf, &p.tmRes, rbar, n0 + chunk0 * 32, cx, cy, cb);
+      }
+      // bias / LoRA-up weights of this warp's chunks were fetched into registers one tile ago: publish them to
+      // the per-warp smem tables, then request the next tile's (their latency hides behind this tile's work)
+      __syncwarp();   // the previous tile's reads of bsm / lsm are complete
+#pragma unroll
+      for (int ci = 0; ci < MAXC; ++ci) {
+        if (p.bias != nullptr) bsm[ci * 32 + lane] = pre_bias[ci];
+        if (LORA && p.lora_rank_pad == 4) {
+          float* d = lsm + ci * 128 + lane;
+          d[0] = pre_up[ci].x, d[32] = pre_up[ci].y, d[64] = pre_up[ci].z, d[96] = pre_up[ci].w;
+        }
+      }
+      __syncwarp();
+      if (tile + num_units < total_tiles) prefetch_tables(tile + num_units, it + 1);
+      IDB_TICK(0);   // tile prologue (bias / LoRA prefetch, residual request)
+      mbar_wait(&tmem_full[buf], bphase);
       tc_fence_after();
+      IDB_TICK(1);   // waiting for the accumulator
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * TMEM_BUF_STRIDE;
 
       float lt[16];
@@ -300,13 +417,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         for (int j = 0; j < 16; ++j) lt[j] = __uint_as_float(lv[j]);
       }
 
-      for (int chunk = half; chunk < BLOCK_N / 32; chunk += 2) {
+      int ci = 0;
+      for (int chunk = chunk0; chunk < NCH; chunk += 4, ++ci) {
         const int col = n0 + chunk * 32;
         uint32_t v[32];
-        if (p.debug == 5) continue;   // profiling: no TMEM read, no stores
+        if ((p.debug & 15) == 5) continue;   // profiling: no TMEM read, no stores
+        if (res_tma && ci > 0 && col < p.N && lane == 0) {   // (the first chunk's residual was requested above)
+          tma_store_wait_read();
+          mbar_expect_tx_a(rbar, EPI_BUF_BYTES);
+          tma_load_4d_a(sbuf, &p.tmRes, rbar, col, cx, cy, cb);
+        }
         IDB_TMEM_LD_X32(t_row + chunk * 32, v);
         tmem_ld_wait();
-        if (col >= p.N || p.debug == 4) continue;   // warp-uniform (debug 4: TMEM read only)
+        IDB_TICK(2);   // TMEM load
+        if (col >= p.N || (p.debug & 15) == 4) continue;   // warp-uniform (debug 4: TMEM read only)
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
@@ -319,12 +443,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
           continue;
         }
-        if (p.bias != nullptr) {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + col);
+        if (p.bias != nullptr && !(p.debug & 0x20)) {
+          const float4* bp = reinterpret_cast<const float4*>(bsm + ci * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 bv = __ldg(bp + j);
-            acc[4 * j] += bv.x, acc[4 * j + 1] += bv.y, acc[4 * j + 2] += bv.z, acc[4 * j + 3] += bv.w;
+            const float4 bv = bp[j];
+            fadd2(acc[4 * j], acc[4 * j + 1], acc[4 * j], acc[4 * j + 1], bv.x, bv.y);
+            fadd2(acc[4 * j + 2], acc[4 * j + 3], acc[4 * j + 2], acc[4 * j + 3], bv.z, bv.w);
           }
         }
         if (p.rowvec != nullptr && row_ok) {
@@ -332,23 +457,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 rv = __ldg(rp + j);
-            acc[4 * j] += rv.x, acc[4 * j + 1] += rv.y, acc[4 * j + 2] += rv.z, acc[4 * j + 3] += rv.w;
+            fadd2(acc[4 * j], acc[4 * j + 1], acc[4 * j], acc[4 * j + 1], rv.x, rv.y);
+            fadd2(acc[4 * j + 2], acc[4 * j + 3], acc[4 * j + 2], acc[4 * j + 3], rv.z, rv.w);
           }
         }
         if (LORA) {
-          // up-projection weights of this chunk's 32 columns: lane c fetches column col + c (coalesced),
-          // the warp transposes them through smem to [rank][32] so every lane can read them as
-          // broadcast float4s, and the rank-r update runs as packed fp32x2 FMAs.
-          float* lsm = reinterpret_cast<float*>(smem + LORA_STG_OFFSET) + warp * (16 * 32);
-          const float* up = p.lora_up + static_cast<long long>(col + lane) * p.lora_rank_pad;
-          __syncwarp();
-          if (p.lora_rank_pad == 4) {   // the common case (rank <= 4): fully unrolled, no dynamic indexing
-            const float4 u0 = __ldg(reinterpret_cast<const float4*>(up));
-            lsm[lane] = u0.x, lsm[32 + lane] = u0.y, lsm[64 + lane] = u0.z, lsm[96 + lane] = u0.w;
-            __syncwarp();
+          if (p.lora_rank_pad == 4) {   // the common case (rank <= 4): weights already staged, fully unrolled
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
-              const float4* row = reinterpret_cast<const float4*>(lsm + rr * 32);
+              const float4* row = reinterpret_cast<const float4*>(lsm + ci * 128 + rr * 32);
               const float tr = lt[rr];
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
@@ -358,6 +475,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               }
             }
           } else {
+            // general rank: lane c fetches column col + c, the warp transposes through smem to [rank][32]
+            const float* up = p.lora_up + static_cast<long long>(col + lane) * p.lora_rank_pad;
+            __syncwarp();
             for (int r4 = 0; r4 < p.lora_rank_pad; r4 += 4) {
               const float4 u = __ldg(reinterpret_cast<const float4*>(up + r4));
               lsm[(r4 + 0) * 32 + lane] = u.x;
@@ -388,34 +508,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         int nc = 32, ocol = col;
         if (geglu) {  // chunk = [a(16) | g(16)] -> 16 outputs at column col/2
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = acc[j] * gelu_erf_f(acc[16 + j]);
+          for (int j = 0; j < 16; j += 2) geglu2(acc[j], acc[j + 1], acc[j], acc[j + 1], acc[16 + j], acc[17 + j]);
           nc = 16, ocol = col >> 1;
         }
-        if (p.residual != nullptr && row_ok) {
-          const float4* rp = reinterpret_cast<const float4*>(p.residual + orow * p.N_out + ocol);
-          if (geglu) {
+        IDB_TICK(3);   // bias / rowvec / LoRA / GEGLU math
+        if (res_tma) {
+          // this chunk's residual has landed in the staging buffer: add it in place (each lane touches only its row)
+          mbar_wait(reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + RES_BAR_OFFSET) + warp, g & 1);
+          ++g;
+          const uint32_t row = sbuf + lane * 128;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 rv = __ldg(rp + j);
-              acc[4 * j] += rv.x, acc[4 * j + 1] += rv.y, acc[4 * j + 2] += rv.z, acc[4 * j + 3] += rv.w;
-            }
-          } else {
+          for (int j = 0; j < 8; ++j) {
+            float4 rv;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(rv.x), "=f"(rv.y), "=f"(rv.z), "=f"(rv.w)
+                         : "r"(row + ((j ^ sw) << 4)));
+            fadd2(acc[4 * j], acc[4 * j + 1], acc[4 * j], acc[4 * j + 1], rv.x, rv.y);
+            fadd2(acc[4 * j + 2], acc[4 * j + 3], acc[4 * j + 2], acc[4 * j + 3], rv.z, rv.w);
+          }
+        } else {
+          if (p.residual != nullptr && row_ok) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + orow * p.N_out + ocol);
+            if (geglu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 rv = __ldg(rp + j);
-              acc[4 * j] += rv.x, acc[4 * j + 1] += rv.y, acc[4 * j + 2] += rv.z, acc[4 * j + 3] += rv.w;
+              for (int j = 0; j < 4; ++j) {
+                const float4 rv = __ldg(rp + j);
+                acc[4 * j] += rv.x, acc[4 * j + 1] += rv.y, acc[4 * j + 2] += rv.z, acc[4 * j + 3] += rv.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 rv = __ldg(rp + j);
+                acc[4 * j] += rv.x, acc[4 * j + 1] += rv.y, acc[4 * j + 2] += rv.z, acc[4 * j + 3] += rv.w;
+              }
             }
           }
+          if (lane == 0) tma_store_wait_read();   // the previous store has finished reading the staging buffer
+          __syncwarp();
         }
-        // ---- stage (previous TMA stores of this warp must have finished READING the staging chunk)
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
+        IDB_TICK(4);   // residual wait + add, or wait for the previous store's smem read
         if (p.stats != nullptr && !row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] = 0.f;
         }
-        if (p.out_f32 != nullptr) {   // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row `lane` lands at j ^ (lane & 7)
-          const uint32_t row = stg_f + lane * 128;
+        if (p.out_f32 != nullptr && !(p.debug & 0x40)) {   // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row `lane` lands at j ^ (lane & 7)
+          const uint32_t row = sbuf + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             if (j * 4 < nc)
@@ -423,9 +560,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                            "f"(acc[4 * j + 1]), "f"(acc[4 * j + 2]), "f"(acc[4 * j + 3])
                            : "memory");
           }
+          if (p.stats != nullptr) {
+            // GroupNorm statistics of the tensor being written, for free: lane c reduces column c of the
+            // staged 32 x 32 fp32 chunk (rows outside the image were staged as zeros)
+            __syncwarp();
+            float cs = 0.f, cs2 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 32; ++rr) {
+              float v;
+              asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sbuf + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + ((lane & 3) << 2)));
+              cs += v;
+              cs2 = fmaf(v, v, cs2);
+            }
+            const long long rowblock = static_cast<long long>(m_blk) * 4 + quarter;
+            if (ocol + lane < p.N_out) p.stats[rowblock * p.N_out + ocol + lane] = make_float2(cs, cs2);
+          }
+          IDB_TICK(5);   // staging (+ statistics)
+          if (!(p.debug & 0x10)) fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          IDB_TICK(6);   // proxy fence
+          if (lane == 0) {
+            if (!(p.debug & 0x80)) tma_store_4d(&p.tmOutF, sbuf, ocol, cx, cy, cb);
+            tma_store_commit();
+            if (both) tma_store_wait_read();   // the bf16 copy is staged in the same buffer next
+          }
+          if (both) __syncwarp();
         }
-        if (p.out_bf16 != nullptr) {  // dense rows of nc * 2 bytes
-          const uint32_t row = stg_b + lane * (nc * 2);
+        if (p.out_bf16 != nullptr && !(p.debug & 0x40)) {  // dense rows of nc * 2 bytes
+          const uint32_t row = sbuf + lane * (nc * 2);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             if (j * 8 < nc)
@@ -434,30 +596,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                            "r"(pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5])), "r"(pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]))
                            : "memory");
           }
-        }
-        if (p.stats != nullptr) {
-          // GroupNorm statistics of the tensor being written, for free: lane c reduces column c of the
-          // staged 32 x 32 fp32 chunk (rows outside the image were staged as zeros)
+          IDB_TICK(5);   // staging
+          if (!(p.debug & 0x10)) fence_proxy_async_smem();
           __syncwarp();
-          float cs = 0.f, cs2 = 0.f;
-#pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
-            float v;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(stg_f + rr * 128 + ((((lane >> 2) ^ (rr & 7))) << 4) + ((lane & 3) << 2)));
-            cs += v;
-            cs2 = fmaf(v, v, cs2);
+          IDB_TICK(6);   // proxy fence
+          if (lane == 0) {
+            if (!(p.debug & 0x80)) tma_store_4d(&p.tmOutB, sbuf, ocol, cx, cy, cb);
+            tma_store_commit();
           }
-          const long long rowblock = static_cast<long long>(m_blk) * 4 + quarter;
-          if (ocol + lane < p.N_out) p.stats[rowblock * p.N_out + ocol + lane] = make_float2(cs, cs2);
         }
-        fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
-        __syncwarp();
-        if (lane == 0) {
-          const int cx = tx * p.BW + bx0, cy = ty * p.BH + by0, cb = tb * p.BB + bb0;
-          if (p.out_f32 != nullptr) tma_store_4d(&p.tmOutF, stg_f, ocol, cx, cy, cb);
-          if (p.out_bf16 != nullptr) tma_store_4d(&p.tmOutB, stg_b, ocol, cx, cy, cb);
-          tma_store_commit();
-        }
+        IDB_TICK(7);   // store issue
       }
       // this warp is done reading the accumulator buffer
       tc_fence_before();
@@ -466,7 +614,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         if (CG == 2 && rank != 0) mbar_arrive_remote(&tmem_empty[buf], 0);   // the leader's MMA warp waits on ITS barrier
         else mbar_arrive(&tmem_empty[buf]);
       }
+      if (++buf == NBUF) buf = 0, bphase ^= 1;
     }
+    if (prof && lane == 0 && p.workspace != nullptr) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(p.workspace) + (static_cast<size_t>(blockIdx.x) * NUM_EPI_WARPS + warp) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dst[k] = tp[k];
+    }
+#undef IDB_TICK
     if (lane == 0) tma_store_wait_all();   // every output byte is written before the CTA retires
   }
 
@@ -544,7 +699,7 @@ template <int BLOCK_N, int STAGES, bool LORA, int CG>
 static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
   constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
   constexpr int smem_bytes = STAGES * (A_TILE_BYTES + (UMMA_N / CG) * BLOCK_K * 2) + 1024 + 1024 + EPI_STAGING_BYTES +
-                             (LORA ? NUM_EPI_WARPS * 16 * 32 * 4 : 0);
+                             EPI_BIAS_BYTES + (LORA ? NUM_EPI_WARPS * 16 * 32 * 4 : 0);   // ring + slack + barriers + staging + bias (+ LoRA)
   static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
   auto kern = gemm_tc_kernel<BLOCK_N, STAGES, LORA, CG>;
   static bool configured = false;  // per instantiation
@@ -639,10 +794,10 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
       return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: stats_partials needs power-of-two Wo (or Wo % 128 == 0) and Ho*Wo % 32 == 0");
   }
 
-  // CTA pairs (cta_group::2) whenever there are at least two M blocks and no fused LoRA
+  // CTA pairs (cta_group::2) whenever there are at least two M blocks
   static const int force_cg = env_int("IDB_GEMM_CG", 0);
-  int cg = (!lora && p.n_tiles_m >= 2) ? 2 : 1;
-  if (force_cg == 1 || force_cg == 2) cg = (lora ? 1 : force_cg);
+  int cg = (p.n_tiles_m >= 2) ? 2 : 1;
+  if (force_cg == 1 || force_cg == 2) cg = force_cg;
   // N tile: minimise  waves x per-tile MMA time / L2-feed efficiency.  The operand feed from L2 caps
   // the tensor pipe at about 8 KB/clk chip-wide: eff = min(1, 8000 / (148 * bytes per clk per SM)).
   const int sms = num_sms();
@@ -666,7 +821,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     }
     if (block_n == 0) block_n = (a->n > 160) ? 256 : (a->n > 128 ? 160 : 128);
     static const int force_bn = env_int("IDB_GEMM_BN", 0);   // profiling only
-    if (force_bn > 0 && a->n % force_bn == 0) block_n = force_bn;
+    if ((force_bn == 128 || force_bn == 160 || force_bn == 256) && a->n % force_bn == 0) block_n = force_bn;
   }
   p.n_tiles_n = (a->n + block_n - 1) / block_n;
 
@@ -691,6 +846,14 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   if (p.k_splits > 1 && (!a->workspace || (a->k_splits > 1 && a->workspace_bytes != 0 &&
                                            idb_gemm_conv_workspace_bytes(p.M, a->n, p.k_splits) > a->workspace_bytes)))
     return fail(IDB_E_BADARG, "idb_gemm_conv: split-K needs a (large enough) workspace");
+
+  p.fd_ntn.set(p.n_tiles_n);
+  p.fd_ks.set(p.k_splits);
+  p.fd_tx.set(p.tiles_x);
+  p.fd_ty.set(p.tiles_y);
+  p.fd_seg.set(lora ? a->lora_seg_n : 1);
+  if (static_cast<long long>(m_units) * p.n_tiles_n * p.k_splits >= (1ll << 20) || p.n_tiles_m >= (1 << 20))
+    return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: more than 2^20 tiles");
 
   p.bias = a->bias;
   p.rowvec = a->rowvec;
@@ -742,6 +905,12 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     uint64_t dims[2] = {uint64_t(k_tot), uint64_t(a->n)};
     uint64_t strides[1] = {uint64_t(k_tot) * 2};
     uint32_t box[2] = {64, uint32_t(block_n / cg)};
+    if (lora && cg == 2) {
+      // the pair's B tile is [160 base rows | 16 LoRA-down rows]: CTA 0 stages base rows 0-87, CTA 1 rows 88-159 + LoRA
+      box[1] = (block_n + 16) / 2;
+      uint32_t box1[2] = {64, uint32_t(block_n - (block_n + 16) / 2)};
+      if (int rc = make_tmap_bf16(&p.tmW1, a->w, 2, dims, strides, box1)) return rc;
+    }
     if (int rc = make_tmap_bf16(&p.tmW, a->w, 2, dims, strides, box)) return rc;
   }
   // output store maps: 4-D [N_out, Wo, Ho, B], one box = the 32 tile rows a warp owns x 32 (16 for GEGLU) columns
@@ -761,23 +930,24 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
       uint64_t strides[3] = {No * 2, uint64_t(p.Wo) * No * 2, uint64_t(p.Ho) * p.Wo * No * 2};
       if (int rc = make_tmap(&p.tmOutB, a->out_bf16, 2, 0, 4, dims, strides, box)) return rc;
     }
+    if (a->residual && !geglu) {   // fp32 [M, N_out] like out_f32: prefetched by TMA into the staging buffers
+      uint64_t strides[3] = {No * 4, uint64_t(p.Wo) * No * 4, uint64_t(p.Ho) * p.Wo * No * 4};
+      if (int rc = make_tmap(&p.tmRes, a->residual, 4, 128, 4, dims, strides, box)) return rc;
+    }
   }
   GemmParams pk = p;
   if (p.k_splits > 1) pk.stats = nullptr;   // statistics come from rowblock_stats_kernel after the finalize
   const int total_tiles = m_units * p.n_tiles_n * p.k_splits;
   const int grid = cg * (total_tiles < units ? total_tiles : units);
   int rc;
-  if (lora) rc = launch_gemm<160, 4, true, 1>(pk, grid, stream);
+  if (lora && cg == 2) rc = launch_gemm<160, 4, true, 2>(pk, grid, stream);
+  else if (lora) rc = launch_gemm<160, 3, true, 1>(pk, grid, stream);
   else if (cg == 1 && block_n == 256) rc = launch_gemm<256, 3, false, 1>(pk, grid, stream);
   else if (cg == 1 && block_n == 160) rc = launch_gemm<160, 4, false, 1>(pk, grid, stream);
-  else if (cg == 1 && block_n == 64) rc = launch_gemm<64, 7, false, 1>(pk, grid, stream);
-  else if (cg == 1 && block_n == 96) rc = launch_gemm<96, 6, false, 1>(pk, grid, stream);
-  else if (cg == 1 && block_n == 192) rc = launch_gemm<192, 4, false, 1>(pk, grid, stream);
-  else if (cg == 1 && block_n == 224) rc = launch_gemm<224, 3, false, 1>(pk, grid, stream);
-  else if (cg == 1) rc = launch_gemm<128, 5, false, 1>(pk, grid, stream);
-  else if (block_n == 256) rc = launch_gemm<256, 5, false, 2>(pk, grid, stream);
+  else if (cg == 1) rc = launch_gemm<128, 4, false, 1>(pk, grid, stream);
+  else if (block_n == 256) rc = launch_gemm<256, 4, false, 2>(pk, grid, stream);
   else if (block_n == 160) rc = launch_gemm<160, 6, false, 2>(pk, grid, stream);
-  else rc = launch_gemm<128, 7, false, 2>(pk, grid, stream);
+  else rc = launch_gemm<128, 6, false, 2>(pk, grid, stream);
   if (rc) return rc;
 
   if (p.k_splits > 1) {

@@ -355,10 +355,43 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, 
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}\n"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 // ----------------------------------------------------------------------------- math
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 // exact-erf GELU (diffusers GEGLU uses F.gelu default = erf form)
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// GEGLU on two (a, g) pairs with packed fp32x2 math and no MUFU / erff call (the FF1 epilogue is issue-bound):
+//   a * g * Phi(g),  Phi(g) = 0.5 * (1 + erf(g / sqrt 2)) ~ 0.5 + t * Q(t^2),  t = clamp(g, +-4.25) / 4.25
+// Q: degree-8 near-minimax fit (tools/fit_gelu.py); |Phi error| < 1.5e-5 everywhere, i.e. far below the
+// bf16 rounding (2^-9 relative) applied to the result right after.
+__device__ __forceinline__ void geglu2(float& o0, float& o1, float a0, float a1, float g0, float g1) {
+  const float c0 = fminf(fmaxf(g0, -4.25f), 4.25f), c1 = fminf(fmaxf(g1, -4.25f), 4.25f);
+  float t0, t1, s0, s1, q0, q1;
+  fmul2(t0, t1, c0, c1, 0.23529411764705882f, 0.23529411764705882f);
+  fmul2(s0, s1, t0, t1, t0, t1);
+  ffma2(q0, q1, s0, s1, 6.304464204e-01f, 6.304464204e-01f, -3.341707352e+00f, -3.341707352e+00f);
+  ffma2(q0, q1, q0, q1, s0, s1, 7.832165652e+00f, 7.832165652e+00f);
+  ffma2(q0, q1, q0, q1, s0, s1, -1.081716508e+01f, -1.081716508e+01f);
+  ffma2(q0, q1, q0, q1, s0, s1, 9.943536263e+00f, 9.943536263e+00f);
+  ffma2(q0, q1, q0, q1, s0, s1, -6.532679704e+00f, -6.532679704e+00f);
+  ffma2(q0, q1, q0, q1, s0, s1, 3.202495144e+00f, 3.202495144e+00f);
+  ffma2(q0, q1, q0, q1, s0, s1, -1.198347137e+00f, -1.198347137e+00f);
+  ffma2(q0, q1, q0, q1, s0, s1, 3.989023346e-01f, 3.989023346e-01f);
+  float ph0, ph1;   // Q was fitted against (Phi(g) - 0.5) / g, so Phi = 0.5 + clamp(g) * Q
+  ffma2(ph0, ph1, c0, c1, q0, q1, 0.5f, 0.5f);
+  float ag0, ag1;
+  fmul2(ag0, ag1, a0, a1, g0, g1);
+  fmul2(o0, o1, ag0, ag1, ph0, ph1);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

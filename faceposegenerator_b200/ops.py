@@ -83,7 +83,10 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
         flags=EPI_GEGLU if geglu else 0, out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
         k_splits=k_splits, workspace=_lib.ptr(workspace),
         workspace_bytes=0 if workspace is None else workspace.numel() * 4, stats_partials=_lib.ptr(stats))
-    _lib.call("idb_gemm_conv", C.byref(args), _lib.stream_ptr())
+    _lib.call("idb_gemm_conv", C.byref(args), _lib.stream_ptr(),
+              desc=None if _lib.trace is None else dict(M=M, N=N, K=taps * C0 + c1, mode=mode, lora=lora_down is not None,
+                                                        geglu=geglu, f32=out_f32 is not None, b16=out_bf16 is not None,
+                                                        res=residual is not None, stats=stats is not None))
     if want_stats or stats is not None:
         return out_f32, out_bf16, stats
     return out_f32, out_bf16
@@ -100,7 +103,8 @@ def attention(q, k, v, out=None, *, batch: int, heads: int, t_q: int, t_kv: int,
     args = _lib.AttentionArgs(q=q.data_ptr(), ld_q=q.shape[-1], col0_q=col0_q, k=k.data_ptr(), ld_k=k.shape[-1],
                               col0_k=col0_k, v=v.data_ptr(), ld_v=v.shape[-1], col0_v=col0_v, out=out.data_ptr(),
                               ld_out=out.shape[-1], batch=batch, heads=heads, t_q=t_q, t_kv=t_kv, scale=scale)
-    _lib.call("idb_attention", C.byref(args), _lib.stream_ptr())
+    _lib.call("idb_attention", C.byref(args), _lib.stream_ptr(),
+              desc=None if _lib.trace is None else dict(B=batch, heads=heads, Tq=t_q, Tkv=t_kv))
     return out
 
 

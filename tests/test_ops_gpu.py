@@ -56,6 +56,26 @@ def test_linear_bias_residual_rowvec(ops, cuda_dev):
     assert rel(o16.float(), ref) < 4e-3
 
 
+@pytest.mark.parametrize("M,K,N", [(4096, 320, 320), (154, 1024, 640), (8192, 1280, 1280), (32768, 320, 320),
+                                   (2048, 640, 2560), (300, 64, 32), (100, 320, 320)])
+@pytest.mark.parametrize("out", ["f32", "bf16"])
+def test_linear_residual_single_output(ops, cuda_dev, M, K, N, out):
+    """One output + fp32 residual: the epilogue prefetches the residual by TMA into its staging buffers
+    (the path every residual-stream GEMM of the UNet takes)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = rb(torch.randn(M, K, device=cuda_dev, generator=g))
+    w = rb(torch.randn(N, K, device=cuda_dev, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=cuda_dev, generator=g)
+    res = torch.randn(M, N, device=cuda_dev, generator=g)
+    ref = x.float() @ w.float().t() + bias + res
+    for _ in range(2):   # twice: staging-buffer / barrier phases must be clean across launches
+        o32, o16 = ops.gemm_conv(x, w, bias=bias, residual=res, want_f32=out == "f32", want_bf16=out == "bf16")
+        if out == "f32":
+            assert o16 is None and rel(o32, ref) < 2e-5, rel(o32, ref)
+        else:
+            assert o32 is None and rel(o16.float(), ref) < 4e-3
+
+
 def test_linear_geglu(ops, cuda_dev):
     M, K, C4 = 1024, 320, 1280
     g = torch.Generator(device="cuda").manual_seed(2)
@@ -96,6 +116,14 @@ def test_linear_fused_lora(ops, cuda_dev, C, Kin, nseg):
     assert rel(o32, ref) < 3e-5, rel(o32, ref)
     # the adapter really contributes
     assert rel(o32, torch.cat([x.float() @ wsi.float().t() for wsi in ws], 1) + bias) > 1e-3
+    # bf16 output + residual (attention out-projection path), and a single-M-tile problem (1-CTA kernel)
+    res = torch.randn(M, nseg * C, device=cuda_dev, generator=g)
+    o32r, _ = ops.gemm_conv(x, w, bias=bias, residual=res, lora_down=ld, lora_up=lu, lora_seg_n=C, want_f32=True)
+    assert rel(o32r, ref + res) < 3e-5
+    _, o16 = ops.gemm_conv(x, w, bias=bias, lora_down=ld, lora_up=lu, lora_seg_n=C, want_bf16=True)
+    assert rel(o16.float(), ref) < 4e-3
+    o32s, _ = ops.gemm_conv(x[:100].contiguous(), w, bias=bias, lora_down=ld, lora_up=lu, lora_seg_n=C, want_f32=True)
+    assert rel(o32s, ref[:100]) < 3e-5
 
 
 @pytest.mark.parametrize("M,K,N,splits", [(512, 11520, 1280, 4), (128, 23040, 1280, 8), (2048, 640, 640, 3)])

@@ -25,3 +25,11 @@ for i in range(3):
     if i == 0:
         print(f"launches per forward: {_lib.launch_count - n0}; before profiled forward: {n0 + 2 * (_lib.launch_count - n0)}",
               file=sys.stderr)
+# shape trace of one more forward (not profiled by `-c`), joined with the ncu launch list by tools/join_trace.py
+import json  # noqa: E402
+_lib.trace = []
+unet.forward(x, t, context=context)
+torch.cuda.synchronize()
+os.makedirs("gpurun_out", exist_ok=True)
+with open(os.environ.get("IDB_TRACE_OUT", "gpurun_out/step_trace.json"), "w") as f:
+    json.dump(_lib.trace, f)
