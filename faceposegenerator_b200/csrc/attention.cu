@@ -545,6 +545,306 @@ __global__ void __launch_bounds__(AT2_THREADS, 1) attention256_kernel(const __gr
   }
 }
 
+
+// ---------------------------------------------------------------------------------------- row-split 256-query variant
+// Same tiling as attention256_kernel (two 128-row query tiles x / "lanes" share every K_j / V_j tile), but each
+// query row's 128 scores are split between TWO threads (64 keys each, warps w and w + 4 of the same TMEM lane
+// quarter), i.e. 16 softmax warps = 4 per SM sub-partition.  With one row per thread the SM sub-partitions saw
+// ~1 runnable warp (the other lane waits for its MMAs) and the 128 live scores spilled; here every thread keeps
+// 64 scores in registers, the pair exchanges its partial row maxima through smem (one 64-thread named barrier
+// per tile), row sums stay partial until the end, and each thread rescales / writes 32 of the 64 O columns.
+constexpr int AT3_THREADS = 576;   // warps 0-7: softmax lane a, 8-15: lane b, 16: TMA, 17: MMA
+constexpr int AT3_XCHG = 2 * 2 * 128 * 2 * 4;   // [parity][lane x][row][half] partial maxima
+constexpr int AT3_SMEM = 2 * ATT_TILE /*Q*/ + AT2_RING * ATT_TILE + 4 * ATT_TILE /*P a,b*/ + 1024 + 256 + 2 * AT3_XCHG;
+
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// two exp2 by the FMA/ALU pipes (Cody-Waite + cubic, packed fp32x2 where the ISA allows)
+__device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float x1) {
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  const float magic = 12582912.0f;
+  float xf0, xf1, n0, n1, f0, f1, p0, p1;
+  fadd2(xf0, xf1, x0, x1, magic, magic);
+  fadd2(n0, n1, xf0, xf1, -magic, -magic);
+  fadd2(f0, f1, x0, x1, -n0, -n1);
+  ffma2(p0, p1, f0, f1, 0.05550410866f, 0.05550410866f, 0.24022650696f, 0.24022650696f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.69314718056f, 0.69314718056f);
+  ffma2(p0, p1, p0, p1, f0, f1, 1.0f, 1.0f);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(xf0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(xf1) << 23));
+}
+
+template <int POLY_MASK>   // pairs (i, i+1) with ((i >> 1) & POLY_MASK) == POLY_MASK take the polynomial exp2: 1 -> 1/2, 3 -> 1/4, 7 -> 1/8, 32 -> none
+__global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2][128 x 64]
+  uint8_t* sRing = sQ + 2 * ATT_TILE;
+  uint8_t* sP = sRing + AT2_RING * ATT_TILE;            // [2][2 k-atoms][128 x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATT_TILE);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + AT2_RING;
+  uint64_t* s_full = kv_empty + AT2_RING;   // [2]
+  uint64_t* p_full = s_full + 2;            // [2]
+  uint64_t* o_done = p_full + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  float* xch_m = reinterpret_cast<float*>(sP + 4 * ATT_TILE + 1024 + 256);   // [parity][x][row][half]
+  float* xch_l = xch_m + AT3_XCHG / 4;                                         // [x][row][half] (final row sums)
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * ATT_BM;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_tiles = p.n_kv_tiles;
+
+  if (warp == 16 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < AT2_RING; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int x = 0; x < 2; ++x) {
+      mbar_init(&s_full[x], 1);
+      mbar_init(&p_full[x], 8);
+      mbar_init(&o_done[x], 1);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 17) tmem_alloc<AT2_TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t smem_base = smem_u32(smem);
+
+  if (warp == 16) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * ATT_TILE);
+      tma_load_3d(sQ, &p.tmQ, q_full, p.col0_q + head * ATT_D, q0, b);
+      tma_load_3d(sQ + ATT_TILE, &p.tmQ, q_full, p.col0_q + head * ATT_D, q0 + ATT_BM, b);
+      for (int i = 0; i < 2 * n_tiles; ++i) {
+        const int slot = i % AT2_RING;
+        const uint32_t ph = (i / AT2_RING) & 1;
+        mbar_wait(&kv_empty[slot], ph ^ 1);
+        mbar_expect_tx(&kv_full[slot], ATT_TILE);
+        const int j = i >> 1;
+        if ((i & 1) == 0)
+          tma_load_3d(sRing + slot * ATT_TILE, &p.tmK, &kv_full[slot], p.col0_k + head * ATT_D, j * ATT_BN, b);
+        else
+          tma_load_3d(sRing + slot * ATT_TILE, &p.tmV, &kv_full[slot], p.col0_v + head * ATT_D, j * ATT_BN, b);
+      }
+    }
+  } else if (warp == 17) {
+    // ================================================================ MMA issuer (convergent loop, elected issue)
+    constexpr uint32_t IDESC_S = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
+    constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // B (= V) is MN-major
+    const uint64_t desc_hi = umma_smem_desc_sw128(0);
+    const uint32_t bar0 = smem_base + 2 * ATT_TILE + AT2_RING * ATT_TILE + 4 * ATT_TILE;   // &bars[0]
+    auto bar_addr = [&](int idx) { return bar0 + idx * 8; };
+    const int I_KVE = 1 + AT2_RING, I_SF = 1 + 2 * AT2_RING, I_OD = I_SF + 4;
+    auto mk = [&](uint32_t addr) { return desc_hi | static_cast<uint64_t>((addr >> 4) & 0x3FFF); };
+
+    auto issue_qk = [&](int x, int j) {   // S_x = Q_x K_j^T
+      const int i = 2 * j, slot = i % AT2_RING;
+      if (x == 0) {
+        mbar_wait(&kv_full[slot], (i / AT2_RING) & 1);
+        tc_fence_after();
+      }
+      const uint64_t qd = mk(smem_base + x * ATT_TILE);
+      const uint64_t kd = mk(smem_base + 2 * ATT_TILE + slot * ATT_TILE);
+      const uint32_t tS = tmem_base + x * 128;
+      if (elect_one()) {
+        umma_bf16(tS, qd, kd, IDESC_S, 0u);
+        umma_bf16(tS, qd + 2, kd + 2, IDESC_S, 1u);
+        umma_bf16(tS, qd + 4, kd + 4, IDESC_S, 1u);
+        umma_bf16(tS, qd + 6, kd + 6, IDESC_S, 1u);
+        umma_commit_a(bar_addr(I_SF + x));
+        if (x == 1) umma_commit_a(bar_addr(I_KVE + slot));   // covers lane a's MMAs on this K tile too
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int x, int j) {   // O_x += P_x V_j
+      const int i = 2 * j + 1, slot = i % AT2_RING;
+      if (x == 0) {
+        mbar_wait(&kv_full[slot], (i / AT2_RING) & 1);
+        tc_fence_after();
+      }
+      const uint32_t pbase = smem_base + 2 * ATT_TILE + AT2_RING * ATT_TILE + x * 2 * ATT_TILE;
+      const uint32_t vbase = smem_base + 2 * ATT_TILE + slot * ATT_TILE;
+      const uint32_t tO = tmem_base + 256 + x * 64;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < ATT_BN / 16; ++kk) {
+          const uint64_t ad = mk(pbase + (kk >> 2) * ATT_TILE + (kk & 3) * 32);
+          const uint64_t bd = mk(vbase + kk * 2048);
+          umma_bf16(tO, ad, bd, IDESC_O, (j > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit_a(bar_addr(I_OD + x));
+        if (x == 1) umma_commit_a(bar_addr(I_KVE + slot));
+      }
+      __syncwarp();
+    };
+
+    mbar_wait(q_full, 0);
+    tc_fence_after();
+    issue_qk(0, 0);
+    issue_qk(1, 0);
+    for (int j = 0; j < n_tiles; ++j) {
+      for (int x = 0; x < 2; ++x) {
+        mbar_wait(&p_full[x], j & 1);  // P_x(j) staged, S_x consumed, O_x rescaled
+        tc_fence_after();
+        if (j + 1 < n_tiles) issue_qk(x, j + 1);
+        issue_pv(x, j);
+      }
+    }
+  } else {
+    // ================================================================ softmax warps (two threads per query row)
+    const int x = warp >> 3;            // query tile ("lane") of the CTA
+    const int wq = warp & 3;            // TMEM lane quarter (= warp % 4)
+    const int hs = (warp >> 2) & 1;     // which 64 keys of the tile / which 32 columns of O
+    const int r = wq * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + x * 128 + hs * 64;
+    const uint32_t tO = tmem_base + lane_off + 256 + x * 64 + hs * 32;
+    const float c = p.scale_log2;
+    const int pair_id = 1 + x * 4 + wq;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint8_t* prow = sP + x * 2 * ATT_TILE + hs * ATT_TILE + r * 128;   // this thread's 64 keys = k-atom hs of row r
+    const int sw = r & 7;
+
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[x], j & 1);
+      tc_fence_after();
+      const int kv_valid = min(ATT_BN, p.Tkv - j * ATT_BN) - hs * 64;   // my keys < kv_valid are real
+      // pass 1: row maximum of my 64 scores (they are re-read from TMEM for pass 2: keeping them would spill)
+      float m0 = -INFINITY, m1 = -INFINITY;
+      {
+        uint32_t s0[32], s1[32];
+        IDB_TMEM_LD_X32(tS, s0);
+        IDB_TMEM_LD_X32(tS + 32, s1);
+        tmem_ld_wait();
+        if (kv_valid < 64) {   // ragged last tile (warp-uniform branch)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i >= kv_valid) s0[i] = 0xff800000u;
+            if (32 + i >= kv_valid) s1[i] = 0xff800000u;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          m0 = fmaxf(m0, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s0[i + 1])));
+          m1 = fmaxf(m1, fmaxf(__uint_as_float(s1[i]), __uint_as_float(s1[i + 1])));
+        }
+      }
+      // exchange the partial row maxima with the thread that owns the row's other 64 keys
+      float* xm = xch_m + (((j & 1) * 2 + x) * 128 + r) * 2;
+      const float m_loc = fmaxf(m0, m1);
+      xm[hs] = m_loc;
+      pair_barrier(pair_id);
+      const float m_tile = fmaxf(m_loc, xm[hs ^ 1]) * c;
+      // lazy rescale: the exponent reference m_run only moves when some row of this warp would otherwise
+      // produce P > 2^8 (both warps of the pair see the same maxima, so they take the same decision)
+      const bool bump = __any_sync(0xffffffffu, m_tile > m_run + AT2_RESCALE_THRESHOLD);
+      float alpha = 1.0f;
+      if (bump) {
+        const float m_upd = fmaxf(m_run, m_tile);
+        alpha = ex2(m_run - m_upd);   // 0 on the first tile (m_run = -inf)
+        m_run = m_upd;
+        l_run *= alpha;
+      }
+      const float neg_m = -m_run;
+      if (j > 0) {
+        mbar_wait(&o_done[x], (j - 1) & 1);   // PV_x(j-1) retired: O readable, P buffer free
+        tc_fence_after();
+        if (bump) {   // my 32 of the row's 64 O columns
+          uint32_t v[32];
+          IDB_TMEM_LD_X32(tO, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          IDB_TMEM_ST_X32(tO, v);
+          tmem_st_wait();
+        }
+      }
+      float l0 = 0.f, l1 = 0.f;
+      auto emit = [&](int half) {   // pass 2 over 32 of my keys: P = exp2(S c - m), row sum, bf16, swizzled K-major smem
+        uint32_t sv[32];
+        IDB_TMEM_LD_X32(tS + half * 32, sv);
+        tmem_ld_wait();
+        if (kv_valid < 64) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (half * 32 + i >= kv_valid) sv[i] = 0xff800000u;
+        }
+        float pv[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {   // masked keys: exp2(-inf) = 0 (MUFU) / 2^-126 (polynomial)
+          float x0, x1;
+          ffma2(x0, x1, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]), c, c, neg_m, neg_m);
+          if (((i >> 1) & POLY_MASK) == POLY_MASK) {
+            exp2_poly2(pv[i], pv[i + 1], x0, x1);
+          } else {
+            pv[i] = ex2(x0);
+            pv[i + 1] = ex2(x1);
+          }
+          fadd2(l0, l1, l0, l1, pv[i], pv[i + 1]);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = half * 4 + q;
+          uint4 w = make_uint4(pack_bf16x2(pv[8 * q], pv[8 * q + 1]), pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]),
+                               pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]), pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]));
+          *reinterpret_cast<uint4*>(prow + ((chunk ^ sw) << 4)) = w;
+        }
+      };
+      emit(0);
+      emit(1);
+      l_run += l0 + l1;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[x]);
+    }
+    // ---- epilogue: combine the two partial row sums, O / l (my 32 columns)
+    float* xl = xch_l + (x * 128 + r) * 2;
+    xl[hs] = l_run;
+    pair_barrier(pair_id);
+    const float inv_l = 1.0f / (l_run + xl[hs ^ 1]);
+    mbar_wait(&o_done[x], (n_tiles - 1) & 1);
+    tc_fence_after();
+    const int row = q0 + x * ATT_BM + r;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Tq + row) * p.ld_out + head * ATT_D + hs * 32;
+    {
+      uint32_t v[32];
+      IDB_TMEM_LD_X32(tO, v);
+      tmem_ld_wait();
+      if (row < p.Tq) {
+        uint4* dst = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * q]) * inv_l, __uint_as_float(v[8 * q + 1]) * inv_l),
+                              pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv_l, __uint_as_float(v[8 * q + 3]) * inv_l),
+                              pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv_l, __uint_as_float(v[8 * q + 5]) * inv_l),
+                              pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv_l, __uint_as_float(v[8 * q + 7]) * inv_l));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 17) {
+    tc_fence_after();
+    tmem_dealloc<AT2_TMEM_COLS>(tmem_base);
+  }
+}
+
 }  // namespace idb
 
 using namespace idb;
@@ -597,6 +897,27 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
   }
   static const int force_variant = getenv("IDB_ATTN_VARIANT") ? atoi(getenv("IDB_ATTN_VARIANT")) : 0;
   const bool use256 = force_variant ? (force_variant == 256) : (a->t_q >= 1024 && a->t_kv >= 512);
+  static const int rs_poly = getenv("IDB_ATTN_RSPOLY") ? atoi(getenv("IDB_ATTN_RSPOLY")) : 3;
+  if (use256 && force_variant != 256) {   // row-split 256-query kernel (16 softmax warps)
+    void (*kern)(AttnParams) = attention_rs_kernel<3>;
+    if (rs_poly == 1) kern = attention_rs_kernel<1>;
+    else if (rs_poly == 7) kern = attention_rs_kernel<7>;
+    else if (rs_poly == 32) kern = attention_rs_kernel<32>;
+    static bool configured3 = false;
+    if (!configured3) {
+      void (*all[4])(AttnParams) = {attention_rs_kernel<1>, attention_rs_kernel<3>, attention_rs_kernel<7>, attention_rs_kernel<32>};
+      for (int i = 0; i < 4; ++i) {
+        cudaError_t e3 = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM);
+        if (e3 != cudaSuccess) return fail(IDB_E_CUDA, std::string("cudaFuncSetAttribute(attention_rs): ") + cudaGetErrorString(e3));
+      }
+      configured3 = true;
+    }
+    dim3 grid3((a->t_q + 2 * ATT_BM - 1) / (2 * ATT_BM), a->heads, a->batch);
+    kern<<<grid3, AT3_THREADS, AT3_SMEM, stream>>>(p);
+    cudaError_t e3 = cudaGetLastError();
+    if (e3 != cudaSuccess) return fail(IDB_E_CUDA, std::string("attention_rs launch: ") + cudaGetErrorString(e3));
+    return IDB_OK;
+  }
   if (use256) {   // two query tiles per CTA share the K/V stream (long sequences)
     static const int poly = getenv("IDB_ATTN_POLY") ? atoi(getenv("IDB_ATTN_POLY")) : 7;
     static const int packed = getenv("IDB_ATTN_PACKED") ? atoi(getenv("IDB_ATTN_PACKED")) : 1;

@@ -673,19 +673,20 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int k_split
 // row-block numbering matches the tile order of the fused epilogue only for raster-ordered tiles,
 // which is what the host guarantees before using this path (BW * BH multiple of 32 rows per image).
 __global__ void rowblock_stats_kernel(const float* __restrict__ x, long long M, int N, float2* __restrict__ stats) {
-  const long long rowblock = blockIdx.x;
-  for (int c = threadIdx.x; c < N; c += blockDim.x) {
-    float s = 0.f, s2 = 0.f;
-    for (int rr = 0; rr < 32; ++rr) {
-      const long long row = rowblock * 32 + rr;
-      if (row < M) {
-        const float v = x[row * N + c];
-        s += v;
-        s2 = fmaf(v, v, s2);
-      }
-    }
-    stats[rowblock * N + c] = make_float2(s, s2);
+  const long long rowblock = blockIdx.x;   // grid = (row blocks, ceil(N / 128)), one thread per column
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const long long row0 = rowblock * 32;
+  float v[32];
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) v[rr] = (row0 + rr < M) ? x[(row0 + rr) * N + c] : 0.f;   // 32 independent loads in flight
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int rr = 0; rr < 32; ++rr) {   // same summation order as the fused epilogue
+    s += v[rr];
+    s2 = fmaf(v[rr], v[rr], s2);
   }
+  stats[rowblock * N + c] = make_float2(s, s2);
 }
 
 // ---------------------------------------------------------------------------------------- host side
@@ -960,7 +961,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("splitk_finalize launch: ") + cudaGetErrorString(e));
     if (p.stats != nullptr) {
       const unsigned nrb = static_cast<unsigned>((p.M + 31) / 32);
-      rowblock_stats_kernel<<<nrb, 256, 0, stream>>>(p.out_f32, p.M, p.N, p.stats);
+      rowblock_stats_kernel<<<dim3(nrb, (p.N + 127) / 128), 128, 0, stream>>>(p.out_f32, p.M, p.N, p.stats);
       e = cudaGetLastError();
       if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("rowblock_stats launch: ") + cudaGetErrorString(e));
     }

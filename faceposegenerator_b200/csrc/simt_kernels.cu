@@ -130,29 +130,38 @@ __global__ void gn_stats_kernel(const GnParams p) {
 }
 
 // Group statistics from the row-block channel sums that the producing GEMM epilogues wrote
-// (fixed summation order -> deterministic).  grid = (groups, batch), one warp per (image, group).
+// (fixed summation order -> deterministic).  grid = (groups, batch), 256 threads per (image, group).
 __global__ void gn_finalize_kernel(const float2* __restrict__ s0, int c0, const float2* __restrict__ s1, int c1,
                                    int rb_per_image, int cpg, int hw, float eps, float* __restrict__ stats) {
-  const int g = blockIdx.x, b = blockIdx.y, lane = threadIdx.x;
+  const int g = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = gridDim.x;
+  __shared__ double sh_s[8], sh_ss[8];
   double s = 0.0, ss = 0.0;
-  const int cells = rb_per_image * cpg;
-  for (int i = lane; i < cells; i += 32) {
-    const int rb = i / cpg, c = g * cpg + (i - rb * cpg);
-    const long long row = static_cast<long long>(b) * rb_per_image + rb;
-    const float2 v = (c < c0) ? s0[row * c0 + c] : s1[row * c1 + (c - c0)];
-    s += v.x;
-    ss += v.y;
+  // the group's cpg channels are contiguous in every row block (a group may straddle the two concatenated sources)
+  const int cbase = g * cpg;
+  const long long row0 = static_cast<long long>(b) * rb_per_image;
+  for (int rb = warp; rb < rb_per_image; rb += 8) {
+    const long long row = row0 + rb;
+    for (int c = cbase + lane; c < cbase + cpg; c += 32) {
+      const float2 v = (c < c0) ? s0[row * c0 + c] : s1[row * c1 + (c - c0)];
+      s += v.x;
+      ss += v.y;
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     s += __shfl_xor_sync(0xffffffffu, s, o);
     ss += __shfl_xor_sync(0xffffffffu, ss, o);
   }
-  if (lane == 0) {
+  if (lane == 0) sh_s[warp] = s, sh_ss[warp] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tss = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) ts += sh_s[w], tss += sh_ss[w];
     const double n = static_cast<double>(hw) * cpg;
-    const double mean = s / n;
-    double var = ss / n - mean * mean;
+    const double mean = ts / n;
+    double var = tss / n - mean * mean;
     if (var < 0.0) var = 0.0;
     float* dst = stats + (static_cast<long long>(b) * groups + g) * 2;
     dst[0] = static_cast<float>(mean);
@@ -564,7 +573,7 @@ extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
   dim3 grid(p.nchunks, a->batch);
   const bool have_stats = a->x0_stats != nullptr && (a->x1 == nullptr || a->x1_stats != nullptr) && a->hw % 32 == 0;
   if (have_stats) {   // statistics already produced by the GEMM epilogues of the sources
-    gn_finalize_kernel<<<dim3(a->groups, a->batch), 32, 0, stream>>>(
+    gn_finalize_kernel<<<dim3(a->groups, a->batch), 256, 0, stream>>>(
         reinterpret_cast<const float2*>(a->x0_stats), p.c0, reinterpret_cast<const float2*>(a->x1_stats), p.c1,
         a->hw / 32, p.cpg, a->hw, a->eps, p.stats);
     IDB_CHECK_LAUNCH("gn_finalize");
