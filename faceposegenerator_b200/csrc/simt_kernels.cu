@@ -137,16 +137,21 @@ __global__ void gn_finalize_kernel(const float2* __restrict__ s0, int c0, const 
   const int groups = gridDim.x;
   __shared__ double sh_s[8], sh_ss[8];
   double s = 0.0, ss = 0.0;
-  // the group's cpg channels are contiguous in every row block (a group may straddle the two concatenated sources)
+  // cells (row block, channel of the group) are spread over the 256 threads, four independent loads in flight per
+  // thread (a group may straddle the two concatenated sources, so the source is chosen per channel)
   const int cbase = g * cpg;
   const long long row0 = static_cast<long long>(b) * rb_per_image;
-  for (int rb = warp; rb < rb_per_image; rb += 8) {
+  const int cells = rb_per_image * cpg;
+  auto cell = [&](int i) -> float2 {
+    if (i >= cells) return make_float2(0.f, 0.f);
+    const int rb = i / cpg, c = cbase + (i - rb * cpg);
     const long long row = row0 + rb;
-    for (int c = cbase + lane; c < cbase + cpg; c += 32) {
-      const float2 v = (c < c0) ? s0[row * c0 + c] : s1[row * c1 + (c - c0)];
-      s += v.x;
-      ss += v.y;
-    }
+    return (c < c0) ? s0[row * c0 + c] : s1[row * c1 + (c - c0)];
+  };
+  for (int i = threadIdx.x; i < cells; i += 4 * 256) {
+    const float2 v0 = cell(i), v1 = cell(i + 256), v2 = cell(i + 512), v3 = cell(i + 768);
+    s += (static_cast<double>(v0.x) + v1.x) + (static_cast<double>(v2.x) + v3.x);
+    ss += (static_cast<double>(v0.y) + v1.y) + (static_cast<double>(v2.y) + v3.y);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -394,52 +399,59 @@ __global__ void conv_small_cin_kernel(const float* __restrict__ x, int x_nchw, c
   }
 }
 
-// conv3x3 pad 1, tiny Cout: one warp per output pixel, lanes stride the channel axis (8 B loads).
+// conv3x3 pad 1, tiny Cout: a warp walks CSC_PPW consecutive output pixels (lanes stride the channel axis, 8 B
+// loads), so the CTA's smem copy of the weights is amortised over 8 x CSC_PPW pixels and the 3x3 windows of
+// neighbouring pixels hit in L1.
+constexpr int CSC_PPW = 8;
 template <int COUT>
 __global__ void conv_small_cout_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                        const float* __restrict__ bias, float* __restrict__ out, int postprocess, int B,
                                        int H, int W, int Cin) {
   extern __shared__ float sw[];  // [COUT][9][Cin]
-  for (int i = threadIdx.x; i < COUT * 9 * Cin; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x * 4; i < COUT * 9 * Cin; i += blockDim.x * 4)
+    *reinterpret_cast<float4*>(sw + i) = *reinterpret_cast<const float4*>(w + i);
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const long long pix = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long pix0 = (blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5)) * CSC_PPW;
   const long long npix = static_cast<long long>(B) * H * W;
-  if (pix >= npix) return;
-  const int xw = static_cast<int>(pix % W);
-  const int yh = static_cast<int>((pix / W) % H);
-  const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
-  float acc[COUT];
+  for (int pi = 0; pi < CSC_PPW; ++pi) {
+    const long long pix = pix0 + pi;
+    if (pix >= npix) return;
+    const int xw = static_cast<int>(pix % W);
+    const int yh = static_cast<int>((pix / W) % H);
+    const int b = static_cast<int>(pix / (static_cast<long long>(W) * H));
+    float acc[COUT];
 #pragma unroll
-  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
-  for (int tap = 0; tap < 9; ++tap) {
-    const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
-    if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
-    const __nv_bfloat16* xr = x + ((static_cast<long long>(b) * H + yy) * W + xx) * Cin;
-    for (int c = lane * 4; c < Cin; c += 128) {
-      const uint2 raw = *reinterpret_cast<const uint2*>(xr + c);
-      const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
-      const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
-      const float v0 = __low2float(p0), v1 = __high2float(p0), v2 = __low2float(p1), v3 = __high2float(p1);
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = yh + tap / 3 - 1, xx = xw + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const __nv_bfloat16* xr = x + ((static_cast<long long>(b) * H + yy) * W + xx) * Cin;
+      for (int c = lane * 4; c < Cin; c += 128) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(xr + c);
+        const __nv_bfloat162 p0 = *reinterpret_cast<const __nv_bfloat162*>(&raw.x);
+        const __nv_bfloat162 p1 = *reinterpret_cast<const __nv_bfloat162*>(&raw.y);
+        const float v0 = __low2float(p0), v1 = __high2float(p0), v2 = __low2float(p1), v3 = __high2float(p1);
 #pragma unroll
-      for (int o = 0; o < COUT; ++o) {
-        const float4 wv = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * Cin + c);
-        acc[o] += (v0 * wv.x + v1 * wv.y) + (v2 * wv.z + v3 * wv.w);
+        for (int o = 0; o < COUT; ++o) {
+          const float4 wv = *reinterpret_cast<const float4*>(sw + (o * 9 + tap) * Cin + c);
+          acc[o] += (v0 * wv.x + v1 * wv.y) + (v2 * wv.z + v3 * wv.w);
+        }
       }
     }
-  }
 #pragma unroll
-  for (int o = 0; o < COUT; ++o)
-    for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
-  if (lane == 0) {
+    for (int o = 0; o < COUT; ++o)
+      for (int s = 16; s > 0; s >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], s);
+    if (lane == 0) {
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) {
-      float v = acc[o] + (bias ? bias[o] : 0.f);
-      if (postprocess) {
-        v = fminf(fmaxf(v * 0.5f + 0.5f, 0.f), 1.f);
-        out[pix * COUT + o] = v;  // NHWC image
-      } else {
-        out[((static_cast<long long>(b) * COUT + o) * H + yh) * W + xw] = v;  // NCHW
+      for (int o = 0; o < COUT; ++o) {
+        float v = acc[o] + (bias ? bias[o] : 0.f);
+        if (postprocess) {
+          v = fminf(fmaxf(v * 0.5f + 0.5f, 0.f), 1.f);
+          out[pix * COUT + o] = v;  // NHWC image
+        } else {
+          out[((static_cast<long long>(b) * COUT + o) * H + yh) * W + xw] = v;  // NCHW
+        }
       }
     }
   }
@@ -664,7 +676,7 @@ extern "C" int idb_conv3x3_small_cout(const void* x_bf16, const float* w, const 
   if (smem > 48 * 1024) return fail(IDB_E_UNSUPPORTED, "idb_conv3x3_small_cout: weights exceed 48 KiB of shared memory");
   const long long npix = static_cast<long long>(batch) * h * wd;
   const int wpb = 8;
-  const unsigned grid = static_cast<unsigned>((npix + wpb - 1) / wpb);
+  const unsigned grid = static_cast<unsigned>((npix + wpb * CSC_PPW - 1) / (wpb * CSC_PPW));
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x_bf16);
   if (cout == 4)
     conv_small_cout_kernel<4><<<grid, wpb * 32, smem, stream>>>(xb, w, bias, out, postprocess, batch, h, wd, cin);

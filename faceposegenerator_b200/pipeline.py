@@ -164,7 +164,7 @@ class StableDiffusionPipeline:
             st.x2[n:].copy_(st.latents)
         else:
             st.x2.copy_(st.latents)
-        eps2 = self.unet.forward(st.x2, st.t_dev, context=st.context, return_dict=False)[0]
+        eps2 = self.unet.forward(st.x2, st.t_dev, context=st.context, temb=st.temb, return_dict=False)[0]
         ops.cfg_ddpm_step(eps2, st.latents, st.noise, st.coef, guidance_scale=st.guidance_scale,
                           use_cfg=st.do_cfg, v_prediction=st.vpred, x_prev=st.lat_next)
         st.latents.copy_(st.lat_next)
@@ -180,6 +180,7 @@ class StableDiffusionPipeline:
             noise=torch.zeros((n, 4, h, w), dtype=f32, device=dev),
             x2=torch.zeros((rows, 4, h, w), dtype=f32, device=dev),
             t_dev=torch.zeros((rows,), dtype=f32, device=dev),
+            temb=torch.zeros((rows, self.unet.t_w_all.shape[0]), dtype=f32, device=dev),
             coef=torch.zeros((5,), dtype=f32, device=dev), graph=None, launches_per_step=0)
 
     # ------------------------------------------------------------------ __call__
@@ -232,10 +233,14 @@ class StableDiffusionPipeline:
                     dst.copy_(src)
             st.latents.copy_(latents)
             t_table = torch.tensor(timesteps, dtype=f32, device=dev)
+            # the time embedding + all 22 time_emb_proj layers depend on the timestep only: one batched call for
+            # every step of this image batch instead of one per step
+            temb_table = self.unet.time_embedding(t_table)
 
             for i in self.progress_bar(range(len(timesteps))):
                 t = timesteps[i]
                 st.t_dev.copy_(t_table[i].expand_as(st.t_dev))
+                st.temb.copy_(temb_table[i].expand_as(st.temb))
                 st.coef.copy_(self.scheduler.coef_row(i, t, dev))
                 if teacher is not None:
                     st.latents.copy_(teacher[i])

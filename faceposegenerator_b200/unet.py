@@ -248,9 +248,18 @@ class UNet2DConditionModel:
         return SimpleNamespace(kv=[self._context_kv(t, ctx) for t in self.transformers], n_ctx=S, batch=B,
                                lora_version=self._lora_version)
 
+    # ------------------------------------------------------------------ timestep-only part of the forward
+    def time_embedding(self, timesteps: torch.Tensor) -> torch.Tensor:
+        """Timesteps fp32 [S] -> [S, sum of ResnetBlock2D widths]: sinusoid -> TimestepEmbedding MLP -> SiLU ->
+        all 22 `time_emb_proj` layers in one batched call.  It depends on the timestep only (not on the
+        sample, the prompt or LoRA), so the pipeline evaluates it once for all scheduler timesteps of a call
+        and hands each step its row (`forward(..., temb=...)`)."""
+        t = timesteps.to(device=self.device, dtype=f32).reshape(-1).contiguous()
+        return ops.time_embed(t, self.t_w1, self.t_b1, self.t_w2, self.t_b2, self.t_w_all, self.t_b_all)
+
     # ------------------------------------------------------------------ forward
     def forward(self, sample, timestep, encoder_hidden_states=None, class_labels=None, return_dict: bool = True,
-                context=None, taps: Optional[dict] = None):
+                context=None, taps: Optional[dict] = None, temb: Optional[torch.Tensor] = None):
         if class_labels is not None:
             raise NotImplementedError("SD2.1-base has no class embedding")
         in_dtype = sample.dtype
@@ -270,7 +279,10 @@ class UNet2DConditionModel:
             raise RuntimeError("stale / mismatched encode_context() result")
         kvs = iter(context.kv)
         gnws = ops.groupnorm_workspace(B, self.groups, self.device)
-        temb = ops.time_embed(t, self.t_w1, self.t_b1, self.t_w2, self.t_b2, self.t_w_all, self.t_b_all)
+        if temb is None:
+            temb = ops.time_embed(t, self.t_w1, self.t_b1, self.t_w2, self.t_b2, self.t_w_all, self.t_b_all)
+        elif temb.shape != (B, self.t_w_all.shape[0]) or temb.dtype != f32 or not temb.is_contiguous():
+            raise ValueError("temb must be a contiguous fp32 [batch, n_time_proj] tensor from time_embedding()")
 
         def tap(name, v):
             if taps is not None:
