@@ -65,7 +65,8 @@ struct TileCoord {
 
 struct GemmParams {
   FastDiv fd_ntn, fd_ks, fd_tx, fd_ty, fd_seg;
-  CUtensorMap tmA0, tmA1, tmW, tmW1, tmL, tmOutF, tmOutB, tmRes;   // tmOut* / tmRes: 4-D [N_out, Wo, Ho, B] maps (32-row boxes); tmW1: W box of the pair's second CTA (LoRA)
+  CUtensorMap tmA0, tmA1, tmW, tmW1, tmL, tmU, tmOutF, tmOutB, tmRes;   // tmU: LoRA up-projection weights [N, 64] bf16
+  CUtensorMap _pad_unused;   // tmOut* / tmRes: 4-D [N_out, Wo, Ho, B] maps (32-row boxes); tmW1: W box of the pair's second CTA (LoRA)
   int mode0, cpb0, c0, nkb0, nkb1;
   int Ho, Wo, B;
   int BW, BH, BB;
@@ -77,8 +78,7 @@ struct GemmParams {
   const float* rowvec;
   long long rowvec_ld;
   const float* residual;
-  const float* lora_up;
-  int lora_rank_pad, lora_seg_n;
+  int lora_seg_n;
   int flags;
   int debug;  // profiling only (IDB_GEMM_DEBUG): 1 = no MMA issue, 2 = no TMA loads, 4 = TMEM read only, 5 = no epilogue, 6 = no TMA stores
   float* out_f32;
@@ -109,7 +109,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   static_assert(B_ROWS % 8 == 0, "B tile must be whole 8-row swizzle groups");
   constexpr int STG_OFFSET = STAGES * STAGE_BYTES + 1024;   // barriers live in the first 1 KiB after the ring (keeps 1024-B alignment)
   constexpr int BIAS_STG_OFFSET = STG_OFFSET + EPI_STAGING_BYTES;
-  constexpr int LORA_STG_OFFSET = BIAS_STG_OFFSET + EPI_BIAS_BYTES;   // per-warp [16][32] fp32 LoRA up-weight tile (LORA only)
+  // LoRA only: the x A^T tile (bf16, 128 rows x 128 B, K-major SWIZZLE_128B, first 32 B of a row used) and two buffers
+  // for the up-projection weight tile of the current N block (same layout, BLOCK_N / CG rows)
+  constexpr int LORA_T_OFFSET = (BIAS_STG_OFFSET + EPI_BIAS_BYTES + 1023) / 1024 * 1024;
+  constexpr int LORA_U_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;
+  constexpr int LORA_U_OFFSET = LORA_T_OFFSET + A_TILE_BYTES;
+  constexpr int LORA_BAR_OFFSET = 704;   // t_ready[4], d_full[4], up_full[2], up_empty[2] inside the barrier KiB
+  static_assert(!LORA || LORA_U_BYTES % 1024 == 0, "up-projection tile must keep 1024B alignment");
   static_assert(BLOCK_N <= 256, "each epilogue warp stages at most two chunks per tile");
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
   // accumulator ring in TMEM: as many buffers as fit the 512 columns, so the MMA warp can run further ahead of the
@@ -137,7 +143,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     tma_prefetch_desc(&p.tmA0);
     tma_prefetch_desc(&p.tmW);
     if (p.nkb1 > 0) tma_prefetch_desc(&p.tmA1);
-    if (LORA) tma_prefetch_desc(&p.tmL);
+    if (LORA) {
+      tma_prefetch_desc(&p.tmL);
+      tma_prefetch_desc(&p.tmU);
+      uint64_t* lb = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + LORA_BAR_OFFSET);
+      for (int b = 0; b < 4; ++b) {
+        mbar_init(&lb[b], 4 * CG);   // t_ready: the four T-extraction warps of each CTA of the pair
+        mbar_init(&lb[4 + b], 1);    // d_full: up-projection MMA retired
+      }
+      for (int u = 0; u < 2; ++u) {
+        mbar_init(&lb[8 + u], CG);   // up_full
+        mbar_init(&lb[10 + u], 1);   // up_empty
+      }
+      for (int q = 0; q < 4; ++q) reinterpret_cast<int*>(&lb[12])[q] = 0;   // T-staging claim counters per lane quarter
+    }
     if (p.residual != nullptr) tma_prefetch_desc(&p.tmRes);
     for (int w = 0; w < NUM_EPI_WARPS; ++w)
       mbar_init(reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + RES_BAR_OFFSET) + w, 1);
@@ -170,7 +189,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     // The whole warp runs the loop convergently on warp-uniform values (so addresses / coordinates
     // live in uniform registers); one elected lane issues the TMA and barrier operations.
     {
-      int stage = 0;
+      int stage = 0, pit = 0;
       uint32_t phase = 0;
       const uint32_t smem_base = smem_u32(smem);
       for (int tile = unit; tile < total_tiles; tile += num_units) {
@@ -245,6 +264,28 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             phase ^= 1;
           }
         }
+        if (LORA) {
+          // up-projection weights of this N block (rows of this CTA's half of the tile), double-buffered; issued AFTER
+          // the tile's k-blocks: the MMA warp frees buffer u while it works on those (see the MMA loop)
+          const int u = pit & 1;
+          uint64_t* lb = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + LORA_BAR_OFFSET);
+          mbar_wait(&lb[10 + u], ((pit >> 1) & 1) ^ 1);   // up_empty
+          const uint32_t ub = smem_base + STAGES * STAGE_BYTES + LORA_BAR_OFFSET + (8 + u) * 8;   // &up_full[u]
+          const uint32_t us = smem_base + LORA_U_OFFSET + u * LORA_U_BYTES;
+          const int urow = n_blk * BLOCK_N + rank * (BLOCK_N / CG);
+          if (elect_one()) {
+            if (CG == 1) {
+              mbar_expect_tx_a(ub, LORA_U_BYTES);
+              tma_load_2d_a(us, &p.tmU, ub, 0, urow);
+            } else {
+              tma2_load_2d_a(us, &p.tmU, ub, 0, urow);
+              if (rank == 0) mbar_expect_tx_a(ub, 2 * LORA_U_BYTES);
+              else mbar_arrive_remote_a(ub, 0);
+            }
+          }
+          __syncwarp();
+          ++pit;
+        }
       }
     }
   } else if (warp == NUM_EPI_WARPS + 1) {
@@ -258,16 +299,61 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const uint32_t mma_t0 = IDB_EPI_PROF ? clock() : 0u;
       const uint32_t smem_base = smem_u32(smem);
       const uint64_t desc_hi = umma_smem_desc_sw128(0);
+      bool up_pending = false;
+      int up_buf = 0;
+      uint32_t up_bphase = 0;
+      auto up_ready = [&](int ubuf, uint32_t ubphase, int uit) -> bool {   // warp-uniform probe
+        uint64_t* lb = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + LORA_BAR_OFFSET);
+        return mbar_try(&lb[ubuf], ubphase) && mbar_try(&lb[8 + (uit & 1)], (uit >> 1) & 1);
+      };
+      auto issue_up = [&](int ubuf, uint32_t ubphase, int uit) {   // D[ubuf] += (x A^T) . U^T, one K = 16 UMMA over the whole tile
+        constexpr uint32_t IDESC_UP = umma_idesc_bf16(BLOCK_M * CG, BLOCK_N, 0, 0);
+        uint64_t* lb = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + LORA_BAR_OFFSET);
+        const int u = uit & 1;
+        mbar_wait(&lb[ubuf], ubphase);             // t_ready: the T tile of that tile is staged (both CTAs)
+        mbar_wait(&lb[8 + u], (uit >> 1) & 1);     // up_full: its up-projection weights have landed
+        tc_fence_after();
+        const uint64_t tdesc = desc_hi | static_cast<uint64_t>(((smem_base + LORA_T_OFFSET) >> 4) & 0x3FFF);
+        const uint64_t udesc = desc_hi | static_cast<uint64_t>(((smem_base + LORA_U_OFFSET + u * LORA_U_BYTES) >> 4) & 0x3FFF);
+        const uint32_t lb0 = smem_base + STAGES * STAGE_BYTES + LORA_BAR_OFFSET;
+        if (elect_one()) {
+          if (CG == 1) {
+            umma_bf16(tmem_base + ubuf * TMEM_BUF_STRIDE, tdesc, udesc, IDESC_UP, 1u);
+            umma_commit_a(lb0 + (4 + ubuf) * 8);   // d_full
+            umma_commit_a(lb0 + (10 + u) * 8);     // up_empty
+          } else {
+            umma2_bf16(tmem_base + ubuf * TMEM_BUF_STRIDE, tdesc, udesc, IDESC_UP, 1u);
+            umma2_commit_mc_a(lb0 + (4 + ubuf) * 8);
+            umma2_commit_mc_a(lb0 + (10 + u) * 8);
+          }
+        }
+        __syncwarp();
+      };
       for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
         const int ks = decode_tile<CG>(p, tile, 0).ks;
         const int kb_begin = ks * p.kb_per_split;
         const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
         const uint32_t c0 = IDB_EPI_PROF ? clock() : 0u;
-        mbar_wait(&tmem_empty[buf], bphase ^ 1);
+        if (LORA) {   // while waiting for the accumulator buffer, fire the previous tile's up-projection as soon as it can go
+          while (!mbar_try(&tmem_empty[buf], bphase ^ 1)) {
+            if (up_pending && up_ready(up_buf, up_bphase, it - 1)) {
+              issue_up(up_buf, up_bphase, it - 1);
+              up_pending = false;
+            }
+          }
+        } else {
+          mbar_wait(&tmem_empty[buf], bphase ^ 1);
+        }
         tc_fence_after();
         if (IDB_EPI_PROF) mma_wait_empty += clock() - c0;
         const uint32_t d_tmem = tmem_base + buf * TMEM_BUF_STRIDE;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
+          // LoRA: D(previous tile) += T U^T once its T tile is staged.  It must be issued before this tile's last
+          // k-block so that this tile's accumulator-ready commit also covers it (the T tile is single-buffered).
+          if (LORA && up_pending && (kb == kb_end - 1 || up_ready(up_buf, up_bphase, it - 1))) {
+            issue_up(up_buf, up_bphase, it - 1);
+            up_pending = false;
+          }
           const uint32_t c2 = IDB_EPI_PROF ? clock() : 0u;
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -307,8 +393,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             phase ^= 1;
           }
         }
+        if (LORA) up_pending = true, up_buf = buf, up_bphase = bphase;
         if (++buf == NBUF) buf = 0, bphase ^= 1;
       }
+      if (LORA && up_pending) issue_up(up_buf, up_bphase, it - 1);
       if (IDB_EPI_PROF && (p.debug & 0x400) && lane == 0 && p.workspace != nullptr) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(p.workspace) + static_cast<size_t>(gridDim.x) * NUM_EPI_WARPS * 8 + blockIdx.x * 4;
         dst[0] = mma_wait_empty, dst[1] = mma_wait_full, dst[2] = clock() - mma_t0, dst[3] = it;
@@ -341,7 +429,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     constexpr int NCH = BLOCK_N / 32;
     constexpr int MAXC = (NCH + 3) / 4;   // chunks per warp per tile
     float* bsm = reinterpret_cast<float*>(smem + BIAS_STG_OFFSET) + warp * (MAXC * 32);
-    float* lsm = reinterpret_cast<float*>(smem + LORA_STG_OFFSET) + warp * (16 * 32);
     uint32_t g = 0;                // residual chunks loaded so far (barrier parity = g & 1)
     int buf = 0;                   // accumulator ring position of the current tile
     uint32_t bphase = 0;
@@ -357,7 +444,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     if (prof) tc = clock();
 
     float pre_bias[MAXC];
-    float4 pre_up[MAXC];
     auto prefetch_tables = [&](int tl, int itn) {   // lane c fetches column col + c of each chunk (coalesced)
       const int n0_ = decode_tile<CG>(p, tl, 0).n_blk * BLOCK_N;
 #pragma unroll
@@ -365,7 +451,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int col = n0_ + (((slot + itn) & 3) + 4 * ci) * 32 + lane;
         const bool ok = (((slot + itn) & 3) + 4 * ci) < NCH && col < p.N;
         pre_bias[ci] = (ok && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
-        if (LORA) pre_up[ci] = (ok && p.lora_rank_pad == 4) ? __ldg(reinterpret_cast<const float4*>(p.lora_up + static_cast<long long>(col) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     if (unit < total_tiles) prefetch_tables(unit, 0);
@@ -395,27 +480,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
       for (int ci = 0; ci < MAXC; ++ci) {
         if (p.bias != nullptr) bsm[ci * 32 + lane] = pre_bias[ci];
-        if (LORA && p.lora_rank_pad == 4) {
-          float* d = lsm + ci * 128 + lane;
-          d[0] = pre_up[ci].x, d[32] = pre_up[ci].y, d[64] = pre_up[ci].z, d[96] = pre_up[ci].w;
-        }
       }
       __syncwarp();
       if (tile + num_units < total_tiles) prefetch_tables(tile + num_units, it + 1);
       IDB_TICK(0);   // tile prologue (bias / LoRA prefetch, residual request)
-      mbar_wait(&tmem_full[buf], bphase);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * TMEM_BUF_STRIDE;
+      if (LORA) {
+        // fused LoRA: columns [BLOCK_N, BLOCK_N + 16) of the accumulator hold T = x A^T (one adapter per N segment).
+        // The slot-0 warps round T to bf16 into a K-major operand tile; the MMA warp then adds T U^T (U = scaled
+        // up-projection rows of this N block) to the accumulator with one more UMMA, and everybody waits for that.
+        uint64_t* lb = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + LORA_BAR_OFFSET);
+        // the first warp of each lane quarter to reach this tile stages T (the others may still be storing the previous tile)
+        int* claim = reinterpret_cast<int*>(smem + STAGES * STAGE_BYTES + LORA_BAR_OFFSET + 12 * 8) + quarter;
+        int mine = 0;
+        if (lane == 0) mine = (atomicCAS(claim, it, it + 1) == it) ? 1 : 0;
+        mine = __shfl_sync(0xffffffffu, mine, 0);
+        if (mine) {
+          mbar_wait(&tmem_full[buf], bphase);
+          tc_fence_after();
+          uint32_t lv[16];
+          IDB_TMEM_LD_X16(t_row + BLOCK_N, lv);
+          tmem_ld_wait();
+          const uint32_t trow = smem_base + LORA_T_OFFSET + r * 128;   // row r of the T tile; 16-byte chunk c sits at c ^ (r & 7)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(trow + ((0 ^ sw) << 4)),
+                       "r"(pack_bf16x2(__uint_as_float(lv[0]), __uint_as_float(lv[1]))),
+                       "r"(pack_bf16x2(__uint_as_float(lv[2]), __uint_as_float(lv[3]))),
+                       "r"(pack_bf16x2(__uint_as_float(lv[4]), __uint_as_float(lv[5]))),
+                       "r"(pack_bf16x2(__uint_as_float(lv[6]), __uint_as_float(lv[7])))
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(trow + ((1 ^ sw) << 4)),
+                       "r"(pack_bf16x2(__uint_as_float(lv[8]), __uint_as_float(lv[9]))),
+                       "r"(pack_bf16x2(__uint_as_float(lv[10]), __uint_as_float(lv[11]))),
+                       "r"(pack_bf16x2(__uint_as_float(lv[12]), __uint_as_float(lv[13]))),
+                       "r"(pack_bf16x2(__uint_as_float(lv[14]), __uint_as_float(lv[15])))
+                       : "memory");
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (CG == 2 && rank != 0) mbar_arrive_remote(&lb[buf], 0);
+            else mbar_arrive(&lb[buf]);
+          }
+        }
+        mbar_wait(&lb[4 + buf], bphase);   // d_full
+      } else {
+        mbar_wait(&tmem_full[buf], bphase);
+      }
       tc_fence_after();
       IDB_TICK(1);   // waiting for the accumulator
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * TMEM_BUF_STRIDE;
-
-      float lt[16];
-      if (LORA) {
-        uint32_t lv[16];
-        IDB_TMEM_LD_X16(t_row + BLOCK_N, lv);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) lt[j] = __uint_as_float(lv[j]);
-      }
 
       int ci = 0;
       for (int chunk = chunk0; chunk < NCH; chunk += 4, ++ci) {
@@ -459,50 +571,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             const float4 rv = __ldg(rp + j);
             fadd2(acc[4 * j], acc[4 * j + 1], acc[4 * j], acc[4 * j + 1], rv.x, rv.y);
             fadd2(acc[4 * j + 2], acc[4 * j + 3], acc[4 * j + 2], acc[4 * j + 3], rv.z, rv.w);
-          }
-        }
-        if (LORA) {
-          if (p.lora_rank_pad == 4) {   // the common case (rank <= 4): weights already staged, fully unrolled
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-              const float4* row = reinterpret_cast<const float4*>(lsm + ci * 128 + rr * 32);
-              const float tr = lt[rr];
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                const float4 u = row[jj];
-                ffma2(acc[4 * jj], acc[4 * jj + 1], tr, tr, u.x, u.y, acc[4 * jj], acc[4 * jj + 1]);
-                ffma2(acc[4 * jj + 2], acc[4 * jj + 3], tr, tr, u.z, u.w, acc[4 * jj + 2], acc[4 * jj + 3]);
-              }
-            }
-          } else {
-            // general rank: lane c fetches column col + c, the warp transposes through smem to [rank][32]
-            const float* up = p.lora_up + static_cast<long long>(col + lane) * p.lora_rank_pad;
-            __syncwarp();
-            for (int r4 = 0; r4 < p.lora_rank_pad; r4 += 4) {
-              const float4 u = __ldg(reinterpret_cast<const float4*>(up + r4));
-              lsm[(r4 + 0) * 32 + lane] = u.x;
-              lsm[(r4 + 1) * 32 + lane] = u.y;
-              lsm[(r4 + 2) * 32 + lane] = u.z;
-              lsm[(r4 + 3) * 32 + lane] = u.w;
-            }
-            __syncwarp();
-            for (int r4 = 0; r4 < p.lora_rank_pad; r4 += 4) {
-              float tq[4];  // lt[] index must be compile-time to stay in registers
-              if (r4 == 0) tq[0] = lt[0], tq[1] = lt[1], tq[2] = lt[2], tq[3] = lt[3];
-              else if (r4 == 4) tq[0] = lt[4], tq[1] = lt[5], tq[2] = lt[6], tq[3] = lt[7];
-              else if (r4 == 8) tq[0] = lt[8], tq[1] = lt[9], tq[2] = lt[10], tq[3] = lt[11];
-              else tq[0] = lt[12], tq[1] = lt[13], tq[2] = lt[14], tq[3] = lt[15];
-#pragma unroll
-              for (int rr = 0; rr < 4; ++rr) {
-                const float4* row = reinterpret_cast<const float4*>(lsm + (r4 + rr) * 32);
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                  const float4 u = row[jj];
-                  ffma2(acc[4 * jj], acc[4 * jj + 1], tq[rr], tq[rr], u.x, u.y, acc[4 * jj], acc[4 * jj + 1]);
-                  ffma2(acc[4 * jj + 2], acc[4 * jj + 3], tq[rr], tq[rr], u.z, u.w, acc[4 * jj + 2], acc[4 * jj + 3]);
-                }
-              }
-            }
           }
         }
         int nc = 32, ocol = col;
@@ -700,7 +768,7 @@ template <int BLOCK_N, int STAGES, bool LORA, int CG>
 static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
   constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
   constexpr int smem_bytes = STAGES * (A_TILE_BYTES + (UMMA_N / CG) * BLOCK_K * 2) + 1024 + 1024 + EPI_STAGING_BYTES +
-                             EPI_BIAS_BYTES + (LORA ? NUM_EPI_WARPS * 16 * 32 * 4 : 0);   // ring + slack + barriers + staging + bias (+ LoRA)
+                             EPI_BIAS_BYTES + (LORA ? 1024 + A_TILE_BYTES + 2 * (BLOCK_N / CG) * BLOCK_K * 2 : 0);   // ring + slack + barriers + staging + bias (+ LoRA T / U tiles)
   static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
   auto kern = gemm_tc_kernel<BLOCK_N, STAGES, LORA, CG>;
   static bool configured = false;  // per instantiation
@@ -860,8 +928,6 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   p.rowvec = a->rowvec;
   p.rowvec_ld = a->rowvec_ld > 0 ? a->rowvec_ld : a->n;
   p.residual = a->residual;
-  p.lora_up = a->lora_up;
-  p.lora_rank_pad = a->lora_rank_pad;
   p.lora_seg_n = lora ? a->lora_seg_n : 1;
   p.flags = a->flags;
   static const int dbg = env_int("IDB_GEMM_DEBUG", 0);
@@ -898,6 +964,11 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     uint64_t strides[1] = {uint64_t(k_total) * 2};
     uint32_t box[2] = {64, 16};
     if (int rc = make_tmap_bf16(&p.tmL, a->lora_down, 2, dims, strides, box)) return rc;
+    // up-projection operand [N, 64] bf16: each CTA stages the rows of its share of the N tile
+    uint64_t udims[2] = {64, uint64_t(a->n)};
+    uint64_t ustrides[1] = {64 * 2};
+    uint32_t ubox[2] = {64, uint32_t(block_n / cg)};
+    if (int rc = make_tmap_bf16(&p.tmU, a->lora_up, 2, udims, ustrides, ubox)) return rc;
   }
 
   // W box: in a pair each CTA stages half of the N tile
@@ -942,7 +1013,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   const int grid = cg * (total_tiles < units ? total_tiles : units);
   int rc;
   if (lora && cg == 2) rc = launch_gemm<160, 4, true, 2>(pk, grid, stream);
-  else if (lora) rc = launch_gemm<160, 3, true, 1>(pk, grid, stream);
+  else if (lora) rc = launch_gemm<160, 2, true, 1>(pk, grid, stream);
   else if (cg == 1 && block_n == 256) rc = launch_gemm<256, 3, false, 1>(pk, grid, stream);
   else if (cg == 1 && block_n == 160) rc = launch_gemm<160, 4, false, 1>(pk, grid, stream);
   else if (cg == 1) rc = launch_gemm<128, 4, false, 1>(pk, grid, stream);

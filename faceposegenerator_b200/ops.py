@@ -53,8 +53,11 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
     if w.shape[1] != taps * C0 + c1:
         raise ValueError(f"w has K={w.shape[1]}, expected {taps * C0 + c1}")
     n_out = N // 2 if geglu else N
-    for t, nm in ((bias, "bias"), (residual, "residual"), (lora_up, "lora_up")):
+    for t, nm in ((bias, "bias"), (residual, "residual")):
         _chk(t, f32, nm, allow_none=True)
+    _chk(lora_up, bf16, "lora_up", allow_none=True)
+    if lora_up is not None and tuple(lora_up.shape) != (N, 64):
+        raise ValueError("lora_up must be bf16 [N, 64] (packing.pack_lora)")
     if rowvec is not None:  # may be a column slice of a wider [batch, ld] table (rowvec_ld = ld)
         if not rowvec.is_cuda or rowvec.dtype != f32 or rowvec.stride(-1) != 1:
             raise ValueError("rowvec must be a CUDA fp32 tensor with unit inner stride")
@@ -79,7 +82,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
         a0=a0.data_ptr(), a0_mode=mode, c0=C0, a1=_lib.ptr(a1), c1=c1, batch=B, height=H, width=W_,
         w=w.data_ptr(), n=N, bias=_lib.ptr(bias), rowvec=_lib.ptr(rowvec), rowvec_ld=rowvec_ld, residual=_lib.ptr(residual),
         lora_down=_lib.ptr(lora_down), lora_up=_lib.ptr(lora_up),
-        lora_rank_pad=0 if lora_up is None else lora_up.shape[1], lora_seg_n=lora_seg_n,
+        lora_rank_pad=0 if lora_up is None else 16, lora_seg_n=lora_seg_n,
         flags=EPI_GEGLU if geglu else 0, out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
         k_splits=k_splits, workspace=_lib.ptr(workspace),
         workspace_bytes=0 if workspace is None else workspace.numel() * 4, stats_partials=_lib.ptr(stats))

@@ -5,8 +5,8 @@ caller-owned tensors; base weights are never modified afterwards).
    channel-minor, optionally with the 1x1 conv_shortcut appended on K;
  - GEGLU `ff.net.0.proj` rows interleaved in 16-blocks [a | g] so `a * gelu(g)` is local
    to one 32-column epilogue chunk;
- - LoRA A zero-padded to 16 rows per adapter (16 extra UMMA N-columns), B*scale as fp32
-   [N, rank_pad].
+ - LoRA A zero-padded to 16 rows per adapter (16 extra UMMA N-columns), B*scale as bf16
+   [N, 64] K-major operand rows (the up-projection is one more UMMA per tile).
 """
 from __future__ import annotations
 
@@ -40,10 +40,14 @@ def interleave_geglu(w: torch.Tensor, bias: Optional[torch.Tensor]):
     return wi, bi
 
 
+LORA_UP_COLS = 64   # bf16 columns of the packed up-projection operand (128-byte rows)
+
+
 def pack_lora(adapters: Sequence[Optional[Tuple[torch.Tensor, torch.Tensor, float]]], device=None,
               seg_n: Optional[int] = None, k: Optional[int] = None):
     """adapters: one (down [r, K], up [seg_n, r], scale) per N-segment of a fused projection
-    (None = segment without adapter).  Returns (down bf16 [nseg*16, K], up fp32 [nseg*seg_n, rank_pad])."""
+    (None = segment without adapter).  Returns (down bf16 [nseg*16, K], up bf16 [nseg*seg_n, 64]):
+    `up` row n holds B[n, :] * scale in its first `rank` columns (one 128-byte K-major operand row)."""
     live = [a for a in adapters if a is not None]
     if not live:
         return None, None
@@ -54,11 +58,11 @@ def pack_lora(adapters: Sequence[Optional[Tuple[torch.Tensor, torch.Tensor, floa
     k = k or live[0][0].shape[1]
     seg_n = seg_n or live[0][1].shape[0]
     down = torch.zeros((len(adapters) * 16, k), dtype=f32)
-    up = torch.zeros((len(adapters) * seg_n, rank_pad), dtype=f32)
+    up = torch.zeros((len(adapters) * seg_n, LORA_UP_COLS), dtype=f32)
     for s, a in enumerate(adapters):
         if a is None:
             continue
         d, u, scale = a
         down[s * 16:s * 16 + d.shape[0]] = d.float().cpu()
         up[s * seg_n:(s + 1) * seg_n, :u.shape[1]] = u.float().cpu() * float(scale)
-    return down.to(device=device, dtype=bf16).contiguous(), up.to(device=device).contiguous()
+    return down.to(device=device, dtype=bf16).contiguous(), up.to(device=device, dtype=bf16).contiguous()

@@ -84,10 +84,13 @@ typedef struct {
   int64_t rowvec_ld;    /* elements between consecutive images of rowvec (0 => N) */
   const float* residual;/* fp32 [M, N_out] */
   /* fused LoRA (optional): down is bf16 [n_seg*16, K] (each adapter's A zero-padded to 16
-   * rows; segment s = column / lora_seg_n), up is fp32 [N, lora_rank_pad] (B * scale,
-   * rank zero-padded to a multiple of 4, <= 16). */
+   * rows; segment s = column / lora_seg_n), up is bf16 [N, 64] (row n = B[n, :] * scale of
+   * its segment's adapter in columns [0, rank), zeros elsewhere; 64 columns = one 128-byte
+   * K-major operand row).  x A^T is accumulated in fp32 next to the base product, rounded to
+   * bf16 and multiplied by `up` with one more tensor-core instruction per tile.
+   * lora_rank_pad: rank rounded up to a multiple of 4 (<= 16; informational). */
   const void* lora_down;
-  const float* lora_up;
+  const void* lora_up;
   int32_t lora_rank_pad;
   int32_t lora_seg_n;
   int32_t flags;        /* IDB_EPI_* */

@@ -107,23 +107,26 @@ def test_linear_fused_lora(ops, cuda_dev, C, Kin, nseg):
     w = torch.cat(ws, 0).contiguous()
     ld, lu = pack_lora(list(zip(downs, ups, [1.0] * nseg)), device=cuda_dev)
     o32, _ = ops.gemm_conv(x, w, bias=bias, lora_down=ld, lora_up=lu, lora_seg_n=C, want_f32=True)
-    refs = []
+    refs, exact = [], []
     for s in range(nseg):
         base = x.float() @ ws[s].float().t()
         t = x.float() @ rb(downs[s]).float().t()
-        refs.append(base + t @ ups[s].t())
+        exact.append(base + t @ ups[s].t())
+        # the kernel's arithmetic: x A^T accumulated in fp32, rounded to bf16, times bf16(B * scale), fp32 accumulate
+        refs.append(base + rb(t).float() @ rb(ups[s]).float().t())
     ref = torch.cat(refs, 1) + bias
-    assert rel(o32, ref) < 3e-5, rel(o32, ref)
+    assert rel(o32, ref) < 1e-4, rel(o32, ref)   # (a few T elements sit on bf16 rounding boundaries)
+    assert rel(o32, torch.cat(exact, 1) + bias) < 3e-3   # bf16 rounding of the rank-r factors only (this adapter is as large as the base)
     # the adapter really contributes
     assert rel(o32, torch.cat([x.float() @ wsi.float().t() for wsi in ws], 1) + bias) > 1e-3
     # bf16 output + residual (attention out-projection path), and a single-M-tile problem (1-CTA kernel)
     res = torch.randn(M, nseg * C, device=cuda_dev, generator=g)
     o32r, _ = ops.gemm_conv(x, w, bias=bias, residual=res, lora_down=ld, lora_up=lu, lora_seg_n=C, want_f32=True)
-    assert rel(o32r, ref + res) < 3e-5
+    assert rel(o32r, ref + res) < 1e-4
     _, o16 = ops.gemm_conv(x, w, bias=bias, lora_down=ld, lora_up=lu, lora_seg_n=C, want_bf16=True)
     assert rel(o16.float(), ref) < 4e-3
     o32s, _ = ops.gemm_conv(x[:100].contiguous(), w, bias=bias, lora_down=ld, lora_up=lu, lora_seg_n=C, want_f32=True)
-    assert rel(o32s, ref[:100]) < 3e-5
+    assert rel(o32s, ref[:100]) < 1e-4
 
 
 @pytest.mark.parametrize("M,K,N,splits", [(512, 11520, 1280, 4), (128, 23040, 1280, 8), (2048, 640, 640, 3)])

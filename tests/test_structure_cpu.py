@@ -209,9 +209,10 @@ def test_packing_layouts():
     assert wi[:, 0].tolist()[:48] == list(range(16)) + list(range(32, 48)) + list(range(16, 32))
     assert torch.equal(bi, wi[:, 0])
     ld, lu = pack_lora([(torch.ones(4, 64), torch.ones(320, 4), 2.0), None], seg_n=320, k=64)
-    assert ld.shape == (32, 64) and lu.shape == (640, 4)
+    assert ld.shape == (32, 64) and lu.shape == (640, 64) and lu.dtype == torch.bfloat16
     assert float(ld[:4].float().sum()) == 256 and float(ld[4:].float().abs().sum()) == 0
-    assert float(lu[:320].sum()) == 2.0 * 320 * 4 and float(lu[320:].abs().sum()) == 0
+    assert float(lu[:320, :4].float().sum()) == 2.0 * 320 * 4 and float(lu[320:].float().abs().sum()) == 0
+    assert float(lu[:, 4:].float().abs().sum()) == 0
     assert pack_lora([None, None]) == (None, None)
 
 

@@ -19,7 +19,8 @@ def run(name, M, K, N, *, f32out=False, b16out=False, res_=False, stats=False, l
     if stats: kw["stats"] = torch.empty((M + 31) // 32, n_out, 2, dtype=f32, device=dev)
     if lora:
         kw["lora_down"] = torch.randn(16 * lora, K, device=dev).to(bf16)
-        kw["lora_up"] = torch.randn(N, 4, device=dev) * 0.05
+        up = torch.zeros(N, 64, device=dev); up[:, :4] = torch.randn(N, 4, device=dev) * 0.05
+        kw["lora_up"] = up.to(bf16)
         kw["lora_seg_n"] = N // lora
     if geglu: kw["geglu"] = True
     big = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
