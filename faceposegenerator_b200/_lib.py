@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libidb_b200.so")
 
 A_1X1, A_3X3, A_3X3_S2 = 0, 1, 2
 EPI_GEGLU = 1
+EPI_F16 = 2
 
 c_void_p, c_int32, c_int64, c_float, c_size_t = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
@@ -32,6 +33,7 @@ class GemmConvArgs(C.Structure):
         ("out_f32", c_void_p), ("out_bf16", c_void_p),
         ("k_splits", c_int32), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("stats_partials", c_void_p),
+        ("prelu", c_void_p),
     ]
 
 
@@ -93,6 +95,10 @@ EXPORTS = {
     "idb_upsample2x": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "idb_cast_bf16": (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
     "idb_vae_latent_prep": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int32, c_int32, c_void_p]),
+    "idb_channel_affine": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, c_void_p]),
+    "idb_crop_resize_norm": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                       c_void_p]),
     "idb_cfg_ddpm_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_int32,
                                     c_void_p, c_void_p, c_int64, c_void_p]),
 }

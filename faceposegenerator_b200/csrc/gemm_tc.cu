@@ -78,6 +78,7 @@ struct GemmParams {
   const float* rowvec;
   long long rowvec_ld;
   const float* residual;
+  const float* prelu;
   int lora_seg_n;
   int flags;
   int debug;  // profiling only (IDB_GEMM_DEBUG): 1 = no MMA issue, 2 = no TMA loads, 4 = TMEM read only, 5 = no epilogue, 6 = no TMA stores
@@ -299,6 +300,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const uint32_t mma_t0 = IDB_EPI_PROF ? clock() : 0u;
       const uint32_t smem_base = smem_u32(smem);
       const uint64_t desc_hi = umma_smem_desc_sw128(0);
+      // fp16 operands: a_format / b_format fields (bits 7 and 10) are 0 = F16 instead of 1 = BF16
+      const uint32_t idesc = (p.flags & IDB_EPI_F16) ? (IDESC & ~((1u << 7) | (1u << 10))) : IDESC;
       bool up_pending = false;
       int up_buf = 0;
       uint32_t up_bphase = 0;
@@ -368,15 +371,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           if (elect_one()) {
             if ((p.debug & 15) != 1 && (p.debug & 15) != 3) {
               if (CG == 1) {
-                umma_bf16(d_tmem, adesc, bdesc, IDESC, acc0);
-                umma_bf16(d_tmem, adesc + 2, bdesc + 2, IDESC, 1u);   // +32 B per UMMA_K=16 step in the swizzle atom
-                umma_bf16(d_tmem, adesc + 4, bdesc + 4, IDESC, 1u);
-                umma_bf16(d_tmem, adesc + 6, bdesc + 6, IDESC, 1u);
+                umma_bf16(d_tmem, adesc, bdesc, idesc, acc0);
+                umma_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);   // +32 B per UMMA_K=16 step in the swizzle atom
+                umma_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                umma_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
               } else {
-                umma2_bf16(d_tmem, adesc, bdesc, IDESC, acc0);
-                umma2_bf16(d_tmem, adesc + 2, bdesc + 2, IDESC, 1u);
-                umma2_bf16(d_tmem, adesc + 4, bdesc + 4, IDESC, 1u);
-                umma2_bf16(d_tmem, adesc + 6, bdesc + 6, IDESC, 1u);
+                umma2_bf16(d_tmem, adesc, bdesc, idesc, acc0);
+                umma2_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+                umma2_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+                umma2_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
               }
             }
             if (CG == 1) {
@@ -420,6 +423,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const int r0 = quarter * 32;   // first row of this warp's box inside the tile rectangle
     const int bx0 = r0 % p.BW, by0 = (r0 / p.BW) % p.BH, bb0 = r0 / (p.BW * p.BH);
     const bool geglu = (p.flags & IDB_EPI_GEGLU) != 0;
+    const bool f16 = (p.flags & IDB_EPI_F16) != 0;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t sbuf = smem_base + STG_OFFSET + warp * EPI_BUF_BYTES;
     const uint32_t rbar = smem_base + STAGES * STAGE_BYTES + RES_BAR_OFFSET + warp * 8;
@@ -573,6 +577,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             fadd2(acc[4 * j + 2], acc[4 * j + 3], acc[4 * j + 2], acc[4 * j + 3], rv.z, rv.w);
           }
         }
+        if (p.prelu != nullptr) {   // per-channel PReLU (IResNet)
+          const float4* sp = reinterpret_cast<const float4*>(p.prelu + col);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sl = __ldg(sp + j);
+            acc[4 * j] = acc[4 * j] > 0.f ? acc[4 * j] : acc[4 * j] * sl.x;
+            acc[4 * j + 1] = acc[4 * j + 1] > 0.f ? acc[4 * j + 1] : acc[4 * j + 1] * sl.y;
+            acc[4 * j + 2] = acc[4 * j + 2] > 0.f ? acc[4 * j + 2] : acc[4 * j + 2] * sl.z;
+            acc[4 * j + 3] = acc[4 * j + 3] > 0.f ? acc[4 * j + 3] : acc[4 * j + 3] * sl.w;
+          }
+        }
         int nc = 32, ocol = col;
         if (geglu) {  // chunk = [a(16) | g(16)] -> 16 outputs at column col/2
 #pragma unroll
@@ -660,8 +675,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           for (int j = 0; j < 4; ++j) {
             if (j * 8 < nc)
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row + (j << 4)),
-                           "r"(pack_bf16x2(acc[8 * j], acc[8 * j + 1])), "r"(pack_bf16x2(acc[8 * j + 2], acc[8 * j + 3])),
-                           "r"(pack_bf16x2(acc[8 * j + 4], acc[8 * j + 5])), "r"(pack_bf16x2(acc[8 * j + 6], acc[8 * j + 7]))
+                           "r"(pack_16x2(acc[8 * j], acc[8 * j + 1], f16)), "r"(pack_16x2(acc[8 * j + 2], acc[8 * j + 3], f16)),
+                           "r"(pack_16x2(acc[8 * j + 4], acc[8 * j + 5], f16)), "r"(pack_16x2(acc[8 * j + 6], acc[8 * j + 7], f16))
                            : "memory");
           }
           IDB_TICK(5);   // staging
@@ -706,9 +721,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 // ---------------------------------------------------------------------------------------- split-K finalize
 __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int k_splits, long long M, int N, int hw,
                                        const float* __restrict__ bias, const float* __restrict__ rowvec,
-                                       long long rowvec_ld,
+                                       long long rowvec_ld, const float* __restrict__ prelu,
                                        const float* __restrict__ residual, float* __restrict__ out_f32,
-                                       __nv_bfloat16* __restrict__ out_bf16) {
+                                       __nv_bfloat16* __restrict__ out_bf16, int f16) {
   const long long total4 = M * N / 4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -728,12 +743,17 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int k_split
       const float4 v = *reinterpret_cast<const float4*>(rowvec + (row / hw) * rowvec_ld + col);
       a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
     }
+    if (prelu) {
+      const float4 sl = *reinterpret_cast<const float4*>(prelu + col);
+      a.x = a.x > 0.f ? a.x : a.x * sl.x, a.y = a.y > 0.f ? a.y : a.y * sl.y;
+      a.z = a.z > 0.f ? a.z : a.z * sl.z, a.w = a.w > 0.f ? a.w : a.w * sl.w;
+    }
     if (residual) {
       const float4 v = *reinterpret_cast<const float4*>(residual + e);
       a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
     }
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + e) = a;
-    if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + e) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
+    if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + e) = make_uint2(pack_16x2(a.x, a.y, f16 != 0), pack_16x2(a.z, a.w, f16 != 0));
   }
 }
 
@@ -829,6 +849,8 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   if (lora && (geglu || a->a1)) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: LoRA with GEGLU / second segment");
   if (geglu && a->out_f32) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: GEGLU writes bf16 only");
   if (a->stats_partials && !a->out_f32) return fail(IDB_E_BADARG, "idb_gemm_conv: stats_partials needs the fp32 output");
+  if (a->prelu && geglu) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: PReLU with GEGLU");
+  if ((a->flags & IDB_EPI_F16) && lora) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: fp16 operands with fused LoRA");
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -869,7 +891,8 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   if (force_cg == 1 || force_cg == 2) cg = force_cg;
   // N tile: minimise  waves x per-tile MMA time / L2-feed efficiency.  The operand feed from L2 caps
   // the tensor pipe at about 8 KB/clk chip-wide: eff = min(1, 8000 / (148 * bytes per clk per SM)).
-  const int sms = num_sms();
+  static const int max_sms = env_int("IDB_GEMM_MAXSM", 0);   // profiling only
+  const int sms = (max_sms > 0 && max_sms < num_sms()) ? max_sms : num_sms();
   const int units = sms / cg;
   const int m_units = (p.n_tiles_m + cg - 1) / cg;
   int block_n = 0;
@@ -928,6 +951,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   p.rowvec = a->rowvec;
   p.rowvec_ld = a->rowvec_ld > 0 ? a->rowvec_ld : a->n;
   p.residual = a->residual;
+  p.prelu = a->prelu;
   p.lora_seg_n = lora ? a->lora_seg_n : 1;
   p.flags = a->flags;
   static const int dbg = env_int("IDB_GEMM_DEBUG", 0);
@@ -1027,7 +1051,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     int blocks = static_cast<int>((total4 + 255) / 256);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
     splitk_finalize_kernel<<<blocks, 256, 0, stream>>>(p.workspace, p.k_splits, p.M, p.N, p.Ho * p.Wo, p.bias, p.rowvec,
-                                                       p.rowvec_ld, p.residual, p.out_f32, p.out_bf16);
+                                                       p.rowvec_ld, p.prelu, p.residual, p.out_f32, p.out_bf16, (p.flags & IDB_EPI_F16) ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("splitk_finalize launch: ") + cudaGetErrorString(e));
     if (p.stats != nullptr) {

@@ -536,6 +536,67 @@ __global__ void cfg_ddpm_step_kernel(const float* __restrict__ eps2, const float
   }
 }
 
+// ---------------------------------------------------------------------------------------- IResNet glue
+// y[b, yo, xo, c] = bf16(x[b, s*yo, s*xo, c] * scale[c] + shift[c])   (eval-mode BatchNorm2d in front of a conv,
+// and/or the stride-s sampling of a 1x1 stride-s shortcut conv; scale / shift may be NULL = plain cast)
+__global__ void channel_affine_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int f16, int B,
+                                      int H, int W, int C, int stride) {
+  const int Ho = H / stride, Wo = W / stride, CQ = C / 4;
+  const long long total = static_cast<long long>(B) * Ho * Wo * CQ;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cq = static_cast<int>(i % CQ);
+    long long pix = i / CQ;
+    const int xo = static_cast<int>(pix % Wo);
+    pix /= Wo;
+    const int yo = static_cast<int>(pix % Ho);
+    const int b = static_cast<int>(pix / Ho);
+    const float4 v = *reinterpret_cast<const float4*>(x + ((static_cast<long long>(b) * H + yo * stride) * W + xo * stride) * C + cq * 4);
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (scale) sc = *reinterpret_cast<const float4*>(scale + cq * 4);
+    if (shift) sh = *reinterpret_cast<const float4*>(shift + cq * 4);
+    *reinterpret_cast<uint2*>(out + i * 4) = make_uint2(pack_16x2(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), f16 != 0),
+                                                        pack_16x2(fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w), f16 != 0));
+  }
+}
+
+// ArcFace input from decoded images (train_ID-Booth.py:433-455): crop [y0:y1, x0:x1] of the [0,1] NHWC image,
+// bilinear resize (align_corners = False, no antialias = torchvision resize(antialias=None)) to S x S,
+// ((v * 255) / 255 - 0.5) / 0.5, written as the bf16 NHWC stem operand with C_pad channels (3 real, rest 0).
+__global__ void crop_resize_norm_kernel(const float* __restrict__ img, const int* __restrict__ bbox, __nv_bfloat16* __restrict__ out,
+                                        int f16, int n, int H, int W, int S, int c_pad) {
+  const long long total = static_cast<long long>(n) * S * S;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int xo = static_cast<int>(i % S), yo = static_cast<int>((i / S) % S), b = static_cast<int>(i / (static_cast<long long>(S) * S));
+    const int x0 = max(0, bbox[4 * b]), y0 = max(0, bbox[4 * b + 1]);
+    const int x1 = min(bbox[4 * b + 2], W), y1 = min(bbox[4 * b + 3], H);
+    const int cw = x1 - x0, ch = y1 - y0;
+    // PyTorch upsample_bilinear2d, align_corners = False: src = max(0, (dst + 0.5) * scale - 0.5)
+    const float sx = fmaxf(0.f, (xo + 0.5f) * (static_cast<float>(cw) / S) - 0.5f);
+    const float sy = fmaxf(0.f, (yo + 0.5f) * (static_cast<float>(ch) / S) - 0.5f);
+    const int ix = min(static_cast<int>(sx), cw - 1), iy = min(static_cast<int>(sy), ch - 1);
+    const int ix1 = min(ix + 1, cw - 1), iy1 = min(iy + 1, ch - 1);
+    const float lx = sx - ix, ly = sy - iy;
+    const float* base = img + static_cast<long long>(b) * H * W * 3;
+    float v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float p00 = base[((y0 + iy) * static_cast<long long>(W) + x0 + ix) * 3 + c];
+      const float p01 = base[((y0 + iy) * static_cast<long long>(W) + x0 + ix1) * 3 + c];
+      const float p10 = base[((y0 + iy1) * static_cast<long long>(W) + x0 + ix) * 3 + c];
+      const float p11 = base[((y0 + iy1) * static_cast<long long>(W) + x0 + ix1) * 3 + c];
+      const float r = (1.f - ly) * ((1.f - lx) * p00 + lx * p01) + ly * ((1.f - lx) * p10 + lx * p11);
+      v[c] = (r - 0.5f) / 0.5f;
+    }
+    unsigned short* o = reinterpret_cast<unsigned short*>(out) + i * c_pad;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) o[c] = static_cast<unsigned short>(pack_16x2(v[c], 0.f, f16 != 0) & 0xffffu);
+    for (int c = 3; c < c_pad; ++c) o[c] = 0;
+  }
+}
+
 static int grid_for(long long work_items, int block, int max_blocks) {
   long long g = (work_items + block - 1) / block;
   if (g > max_blocks) g = max_blocks;
@@ -729,5 +790,31 @@ extern "C" int idb_cfg_ddpm_step(const float* eps2, const float* x, const float*
   cfg_ddpm_step_kernel<<<grid_for(n_per_branch / 4, 256, num_sms() * 8), 256, 0, stream>>>(
       eps2, x, noise, coef, guidance_scale, use_cfg, v_prediction, x_prev, x0_out, n_per_branch);
   IDB_CHECK_LAUNCH("cfg_ddpm_step");
+  return IDB_OK;
+}
+
+extern "C" int idb_channel_affine(const float* x, const float* scale, const float* shift, void* out_bf16, int32_t out_f16,
+                                  int32_t batch, int32_t h, int32_t wd, int32_t c, int32_t stride, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = require_sm100()) return rc;
+  if (!x || !out_bf16 || c % 4 || stride < 1 || h % stride || wd % stride)
+    return fail(IDB_E_BADARG, "idb_channel_affine: bad arguments (C % 4 == 0, H and W divisible by stride)");
+  const long long total = static_cast<long long>(batch) * (h / stride) * (wd / stride) * (c / 4);
+  channel_affine_kernel<<<grid_for(total, 256, num_sms() * 16), 256, 0, stream>>>(
+      x, scale, shift, static_cast<__nv_bfloat16*>(out_bf16), out_f16, batch, h, wd, c, stride);
+  IDB_CHECK_LAUNCH("channel_affine");
+  return IDB_OK;
+}
+
+extern "C" int idb_crop_resize_norm(const float* img_nhwc, const int32_t* bbox_xyxy, void* out_bf16, int32_t out_f16, int32_t n,
+                                    int32_t h, int32_t wd, int32_t size, int32_t c_pad, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = require_sm100()) return rc;
+  if (!img_nhwc || !bbox_xyxy || !out_bf16 || n <= 0 || size <= 0 || c_pad < 3)
+    return fail(IDB_E_BADARG, "idb_crop_resize_norm: bad arguments");
+  const long long total = static_cast<long long>(n) * size * size;
+  crop_resize_norm_kernel<<<grid_for(total, 128, num_sms() * 8), 128, 0, stream>>>(
+      img_nhwc, bbox_xyxy, static_cast<__nv_bfloat16*>(out_bf16), out_f16, n, h, wd, size, c_pad);
+  IDB_CHECK_LAUNCH("crop_resize_norm");
   return IDB_OK;
 }

@@ -11,9 +11,9 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import A_1X1, A_3X3, A_3X3_S2, EPI_GEGLU  # noqa: F401  (re-exported)
+from ._lib import A_1X1, A_3X3, A_3X3_S2, EPI_F16, EPI_GEGLU  # noqa: F401  (re-exported)
 
-bf16, f32 = torch.bfloat16, torch.float32
+bf16, f16, f32 = torch.bfloat16, torch.float16, torch.float32
 
 
 def _chk(t: Optional[torch.Tensor], dtype, name: str, allow_none: bool = False):
@@ -33,9 +33,12 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
               bias=None, rowvec=None, rowvec_ld: int = 0, residual=None, lora_down=None, lora_up=None, lora_seg_n: int = 0,
               geglu: bool = False, out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
               want_f32: bool = False, want_bf16: bool = False, k_splits: int = 1,
-              workspace: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, want_stats: bool = False):
-    """a0: bf16 [B,H,W,C0] (or [M,K] for a Linear); w: bf16 [N, Ktot].  Returns (out_f32, out_bf16)."""
-    _chk(a0, bf16, "a0"); _chk(w, bf16, "w")
+              workspace: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, want_stats: bool = False,
+              prelu: Optional[torch.Tensor] = None, half: bool = False):
+    """a0: bf16 [B,H,W,C0] (or [M,K] for a Linear); w: bf16 [N, Ktot].  Returns (out_f32, out_bf16).
+    half=True: the 16-bit tensors (a0, a1, w, out_bf16) are IEEE fp16 instead of bf16 (IDB_EPI_F16)."""
+    t16 = f16 if half else bf16
+    _chk(a0, t16, "a0"); _chk(w, t16, "w")
     if a0.dim() == 2:
         B, H, W_, C0 = 1, 1, a0.shape[0], a0.shape[1]
     else:
@@ -46,15 +49,17 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
     taps = 1 if mode == A_1X1 else 9
     c1 = 0
     if a1 is not None:
-        _chk(a1, bf16, "a1")
+        _chk(a1, t16, "a1")
         c1 = a1.shape[-1]
         if a1.numel() != M * c1:
             raise ValueError("a1 must have the output geometry")
     if w.shape[1] != taps * C0 + c1:
         raise ValueError(f"w has K={w.shape[1]}, expected {taps * C0 + c1}")
     n_out = N // 2 if geglu else N
-    for t, nm in ((bias, "bias"), (residual, "residual")):
+    for t, nm in ((bias, "bias"), (residual, "residual"), (prelu, "prelu")):
         _chk(t, f32, nm, allow_none=True)
+    if prelu is not None and prelu.numel() != N:
+        raise ValueError("prelu must hold one slope per output channel")
     _chk(lora_up, bf16, "lora_up", allow_none=True)
     if lora_up is not None and tuple(lora_up.shape) != (N, 64):
         raise ValueError("lora_up must be bf16 [N, 64] (packing.pack_lora)")
@@ -71,8 +76,8 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
     if out_f32 is None and want_f32:
         out_f32 = torch.empty((M, n_out), dtype=f32, device=a0.device)
     if out_bf16 is None and (want_bf16 or (out_f32 is None)):
-        out_bf16 = torch.empty((M, n_out), dtype=bf16, device=a0.device)
-    _chk(out_f32, f32, "out_f32", allow_none=True); _chk(out_bf16, bf16, "out_bf16", allow_none=True)
+        out_bf16 = torch.empty((M, n_out), dtype=t16, device=a0.device)
+    _chk(out_f32, f32, "out_f32", allow_none=True); _chk(out_bf16, t16, "out_bf16", allow_none=True)
     if k_splits > 1 and workspace is None:
         workspace = torch.empty((k_splits, M, N), dtype=f32, device=a0.device)
     if stats is None and want_stats:   # row-block channel statistics of the fp32 output (consumed by groupnorm)
@@ -83,9 +88,10 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
         w=w.data_ptr(), n=N, bias=_lib.ptr(bias), rowvec=_lib.ptr(rowvec), rowvec_ld=rowvec_ld, residual=_lib.ptr(residual),
         lora_down=_lib.ptr(lora_down), lora_up=_lib.ptr(lora_up),
         lora_rank_pad=0 if lora_up is None else 16, lora_seg_n=lora_seg_n,
-        flags=EPI_GEGLU if geglu else 0, out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
+        flags=(EPI_GEGLU if geglu else 0) | (EPI_F16 if half else 0), out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
         k_splits=k_splits, workspace=_lib.ptr(workspace),
-        workspace_bytes=0 if workspace is None else workspace.numel() * 4, stats_partials=_lib.ptr(stats))
+        workspace_bytes=0 if workspace is None else workspace.numel() * 4, stats_partials=_lib.ptr(stats),
+        prelu=_lib.ptr(prelu))
     _lib.call("idb_gemm_conv", C.byref(args), _lib.stream_ptr(),
               desc=None if _lib.trace is None else dict(M=M, N=N, K=taps * C0 + c1, mode=mode, lora=lora_down is not None,
                                                         geglu=geglu, f32=out_f32 is not None, b16=out_bf16 is not None,
@@ -243,3 +249,29 @@ def cfg_ddpm_step(eps2, x, noise, coef, *, guidance_scale: float, use_cfg: bool,
     _lib.call("idb_cfg_ddpm_step", eps2.data_ptr(), x.data_ptr(), _lib.ptr(noise), coef.data_ptr(), guidance_scale,
               int(use_cfg), int(v_prediction), x_prev.data_ptr(), _lib.ptr(x0_out), x.numel(), _lib.stream_ptr())
     return x_prev
+
+
+def channel_affine(x, scale=None, shift=None, *, stride: int = 1, out=None, half: bool = False):
+    """x fp32 NHWC [B,H,W,C] -> bf16 [B,H/s,W/s,C] = x[:, ::s, ::s] * scale + shift (eval BatchNorm2d / stride-s sampling)."""
+    _chk(x, f32, "x"); _chk(scale, f32, "scale", allow_none=True); _chk(shift, f32, "shift", allow_none=True)
+    B, H, W_, Cc = x.shape
+    if out is None:
+        out = torch.empty((B, H // stride, W_ // stride, Cc), dtype=f16 if half else bf16, device=x.device)
+    _chk(out, f16 if half else bf16, "out")
+    _lib.call("idb_channel_affine", x.data_ptr(), _lib.ptr(scale), _lib.ptr(shift), out.data_ptr(), int(half), B, H, W_, Cc,
+              stride, _lib.stream_ptr())
+    return out
+
+
+def crop_resize_norm(images, bbox, *, size: int = 112, c_pad: int = 64, out=None, half: bool = False):
+    """images fp32 NHWC [n,H,W,3] in [0,1], bbox int32 [n,4] (x0,y0,x1,y1) -> bf16 [n,size,size,c_pad] ArcFace input."""
+    _chk(images, f32, "images"); _chk(bbox, torch.int32, "bbox")
+    n, H, W_, c = images.shape
+    if c != 3 or tuple(bbox.shape) != (n, 4):
+        raise ValueError("images must be [n,H,W,3] and bbox [n,4]")
+    if out is None:
+        out = torch.empty((n, size, size, c_pad), dtype=f16 if half else bf16, device=images.device)
+    _chk(out, f16 if half else bf16, "out")
+    _lib.call("idb_crop_resize_norm", images.data_ptr(), bbox.data_ptr(), out.data_ptr(), int(half), n, H, W_, size, c_pad,
+              _lib.stream_ptr())
+    return out

@@ -239,3 +239,65 @@ def load_lora_state(path_or_dir: str, weight_name: str = LORA_FILE) -> dict:
         r = d.shape[0]
         out[mod] = (d, ups[mod], alphas.get(mod, float(r)) / r)
     return out
+
+
+# ------------------------------------------------------------------ ArcFace IResNet (config 5)
+def iresnet_manifest(arch: str = "r100"):
+    """(name, shape) of every state-dict entry of the reference IResNet
+    (`/root/reference/ArcFace_files/backbones/iresnet.py:67-162`; iresnet100 = [3, 13, 30, 3]): 925 entries,
+    65,156,160 parameters for r100."""
+    layers = {"r18": (2, 2, 2, 2), "r34": (3, 4, 6, 3), "r50": (3, 4, 14, 3), "r100": (3, 13, 30, 3)}[arch]
+    out = []
+
+    def bn(p, c):
+        out.extend([(p + ".weight", (c,)), (p + ".bias", (c,)), (p + ".running_mean", (c,)), (p + ".running_var", (c,)),
+                    (p + ".num_batches_tracked", ())])
+    out.append(("conv1.weight", (64, 3, 3, 3)))
+    bn("bn1", 64)
+    out.append(("prelu.weight", (64,)))
+    inp = 64
+    for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), layers), start=1):
+        for b in range(nblk):
+            p = f"layer{li}.{b}"
+            bn(p + ".bn1", inp)
+            out.append((p + ".conv1.weight", (planes, inp, 3, 3)))
+            bn(p + ".bn2", planes)
+            out.append((p + ".prelu.weight", (planes,)))
+            out.append((p + ".conv2.weight", (planes, planes, 3, 3)))
+            bn(p + ".bn3", planes)
+            if b == 0:
+                out.append((p + ".downsample.0.weight", (planes, inp, 1, 1)))
+                bn(p + ".downsample.1", planes)
+            inp = planes
+    bn("bn2", 512)
+    out.extend([("fc.weight", (512, 25088)), ("fc.bias", (512,))])
+    bn("features", 512)
+    return out
+
+
+def random_iresnet_state_dict(arch: str = "r100", seed: int = 0):
+    """Deterministic variance-preserving IResNet weights keyed by parameter name (no checkpoint is available
+    offline; the reference loads ArcFace_r100_ms1mv3_backbone.pth, ArcFace_functions.py:29-30)."""
+    import hashlib
+    sd = {}
+    for k, shape in iresnet_manifest(arch):
+        g = torch.Generator().manual_seed(int.from_bytes(hashlib.sha256(f"ir{seed}:{k}".encode()).digest()[:8], "little") >> 1)
+        if k.endswith("num_batches_tracked"):
+            sd[k] = torch.zeros((), dtype=torch.long)
+        elif k.endswith("running_mean"):
+            sd[k] = 0.1 * torch.randn(shape, generator=g)
+        elif k.endswith("running_var"):
+            sd[k] = 1.0 + 0.2 * torch.rand(shape, generator=g)
+        elif "prelu" in k:
+            sd[k] = 0.25 + 0.05 * torch.randn(shape, generator=g)
+        elif k.endswith(".bias"):
+            sd[k] = 0.05 * torch.randn(shape, generator=g)
+        elif len(shape) == 1:
+            sd[k] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            gain = 0.7 if ("conv2" in k or "downsample" in k) else 1.2
+            sd[k] = torch.randn(shape, generator=g) * gain * fan_in ** -0.5
+    return sd

@@ -62,7 +62,9 @@ int idb_num_sms(void);
  * ---------------------------------------------------------------------------------------- */
 enum { IDB_A_1X1 = 0, IDB_A_3X3 = 1, IDB_A_3X3_S2 = 2 };
 enum {
-  IDB_EPI_GEGLU = 1 /* W rows interleaved in 16-blocks [a(16) | g(16)]; out[:, j] = a_j * gelu_erf(g_j); N_out = N/2 */
+  IDB_EPI_GEGLU = 1, /* W rows interleaved in 16-blocks [a(16) | g(16)]; out[:, j] = a_j * gelu_erf(g_j); N_out = N/2 */
+  IDB_EPI_F16 = 2    /* the 16-bit tensors of this call (a0, a1, w, out_bf16) are IEEE fp16 instead of bf16 (the ArcFace IResNet
+                        runs under fp16 autocast in the reference, iresnet.py:149); not combined with LoRA */
 };
 
 typedef struct {
@@ -107,6 +109,9 @@ typedef struct {
    * (sum, sum of squares), written by the epilogue for free; idb_groupnorm consumes them instead of
    * re-reading the tensor.  Needs out_f32, Wo a power of two (or a multiple of 128) and Ho*Wo % 32 == 0. */
   float* stats_partials;
+  /* optional: per-output-channel PReLU slopes [N], applied after bias / rowvec and before the residual
+   * (ArcFace IResNet: bn2 folded into conv1, then nn.PReLU(planes)).  Not combined with GEGLU. */
+  const float* prelu;
 } idb_gemm_conv_args;
 
 int idb_gemm_conv(const idb_gemm_conv_args* args, void* stream);
@@ -218,6 +223,21 @@ int idb_vae_latent_prep(const float* z_nchw, const float* w, const float* bias, 
 int idb_cfg_ddpm_step(const float* eps2, const float* x, const float* noise, const float* coef,
                       float guidance_scale, int32_t use_cfg, int32_t v_prediction,
                       float* x_prev, float* x0_out /* or NULL */, int64_t n_per_branch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ArcFace IResNet-100 glue (reference: ArcFace_files/backbones/iresnet.py:29-162, train_ID-Booth.py:433-455).
+ * idb_channel_affine: out[b, yo, xo, c] = bf16(x[b, s*yo, s*xo, c] * scale[c] + shift[c]) -- an eval-mode
+ *   BatchNorm2d in front of a conv (IBasicBlock.bn1, IResNet.bn2) and / or the stride-s sampling of the 1x1
+ *   stride-s `downsample` conv; scale / shift may be NULL.  x fp32 NHWC [B,H,W,C], out bf16 (fp16 when out_f16)
+ *   [B,H/s,W/s,C].
+ * idb_crop_resize_norm: crop bbox (x0,y0,x1,y1 per image, int32, clamped to the image) from fp32 NHWC [n,H,W,3]
+ *   images in [0,1], bilinear resize (align_corners = False, no antialias) to size x size, (v - 0.5) / 0.5, written
+ *   as bf16 NHWC [n, size, size, c_pad] (channels >= 3 zero): the IResNet stem operand.
+ * ---------------------------------------------------------------------------------------- */
+int idb_channel_affine(const float* x, const float* scale, const float* shift, void* out_16, int32_t out_f16, int32_t batch,
+                       int32_t h, int32_t w, int32_t c, int32_t stride, void* stream);
+int idb_crop_resize_norm(const float* img_nhwc, const int32_t* bbox_xyxy, void* out_16, int32_t out_f16, int32_t n, int32_t h,
+                         int32_t w, int32_t size, int32_t c_pad, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,108 @@
+"""ArcFace IResNet-100 + the x0 -> ArcFace glue on the CUDA path against the PINNED oracle
+(oracle/iresnet.py, itself checked against outputs of the reference module: tests/golden/iresnet100_golden.pt)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+@pytest.fixture(scope="module")
+def ops(cuda_dev):
+    from faceposegenerator_b200 import ops
+    return ops
+
+
+@pytest.fixture(scope="module")
+def golden_sd():
+    from faceposegenerator_b200.weights import iresnet_manifest
+    from oracle.iresnet import keyed_state_dict
+    shapes = dict(iresnet_manifest("r100"))
+    return keyed_state_dict({k: torch.zeros(s, dtype=torch.long if k.endswith("tracked") else torch.float32)
+                             for k, s in shapes.items()}, seed=0)
+
+
+@pytest.fixture(scope="module")
+def model(golden_sd, cuda_dev):
+    from faceposegenerator_b200.iresnet import IResNet
+    return IResNet(golden_sd, "r100", device=cuda_dev)
+
+
+def test_iresnet100_vs_reference_golden(model, golden_sd, cuda_dev):
+    """Embedding of the reference module's own output fixture (same weights, same seeded input).
+    bf16 operands / fp32 accumulation through 100 conv layers: rel-L2 <= 1e-2 (north_star tolerance for bf16)."""
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "iresnet100_golden.pt"))
+    x = torch.randn(2, 3, 112, 112, generator=torch.Generator().manual_seed(0))
+    y = model(x.to(cuda_dev)).cpu()
+    assert y.shape == (2, 512)
+    r = rel(y, gold["embedding"])
+    cos = F.cosine_similarity(y, gold["embedding"], dim=-1)
+    print(f"iresnet100 embedding rel-L2 {r:.3e}, cosine {cos.tolist()}")
+    assert r < 1e-2, r
+    assert float(cos.min()) > 0.9999
+
+
+def test_iresnet100_batch_and_oracle(model, golden_sd, cuda_dev):
+    """Config-5 batch (4 images) against the fp32 oracle on fresh inputs; rows are independent."""
+    from oracle.iresnet import iresnet_forward
+    x = torch.randn(4, 3, 112, 112, generator=torch.Generator().manual_seed(7)).clamp(-1, 1)
+    with torch.no_grad():
+        ref = iresnet_forward(golden_sd, x)
+    y = model(x.to(cuda_dev)).cpu()
+    assert rel(y, ref) < 1e-2, rel(y, ref)
+    y1 = model(x[2:3].to(cuda_dev)).cpu()
+    assert rel(y1, y[2:3]) < 2e-3
+
+
+def test_crop_resize_norm_vs_torch(ops, cuda_dev):
+    """train_ID-Booth.py:1088-1092 + :445-455: crop the bbox, resize(112, antialias=None), (x/255 - 0.5)/0.5."""
+    g = torch.Generator().manual_seed(3)
+    img = torch.rand(3, 256, 256, 3, generator=g)
+    boxes = torch.tensor([[48, 40, 208, 216], [-5, 10, 300, 250], [96, 96, 160, 161]], dtype=torch.int32)
+    out = ops.crop_resize_norm(img.to(cuda_dev), boxes.to(cuda_dev), size=112, c_pad=64).float().cpu()
+    assert out.shape == (3, 112, 112, 64) and float(out[..., 3:].abs().max()) == 0.0
+    for i in range(3):
+        x0, y0, x1, y1 = [int(v) for v in boxes[i]]
+        im = (img[i] * 255)
+        crop = im[max(0, y0):min(y1, 256), max(0, x0):min(x1, 256)]              # HWC, like the reference
+        t = crop.permute(2, 0, 1)[None]
+        t = F.interpolate(t, size=(112, 112), mode="bilinear", align_corners=False, antialias=False)[0]
+        ref = ((t / 255) - 0.5) / 0.5
+        got = out[i, :, :, :3].permute(2, 0, 1)
+        assert float((got - ref).abs().max()) < 1e-2      # bf16 output rounding (values in [-1, 1])
+        assert rel(got, ref) < 4e-3
+
+
+def test_channel_affine(ops, cuda_dev):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(3, 14, 14, 256, device=cuda_dev, generator=g)
+    sc = torch.randn(256, device=cuda_dev, generator=g)
+    sh = torch.randn(256, device=cuda_dev, generator=g)
+    y = ops.channel_affine(x, sc, sh).float()
+    assert rel(y, x * sc + sh) < 4e-3
+    y2 = ops.channel_affine(x, stride=2).float()
+    assert y2.shape == (3, 7, 7, 256) and rel(y2, x[:, ::2, ::2]) < 4e-3
+
+
+def test_identity_loss_end_to_end(model, golden_sd, cuda_dev):
+    """x0-image -> ArcFace embedding -> 1 - cos (train_ID-Booth.py:1093-1098) with a fixed bbox (SURVEY 8d cfg 5)."""
+    from faceposegenerator_b200.iresnet import arcface_embedding_from_images, identity_loss
+    from oracle.iresnet import iresnet_forward
+    g = torch.Generator().manual_seed(11)
+    img = torch.rand(2, 512, 512, 3, generator=g)
+    bbox = torch.tensor([[96, 96, 416, 416]] * 2, dtype=torch.int32)
+    emb = arcface_embedding_from_images(model, img.to(cuda_dev), bbox.to(cuda_dev)).cpu()
+    crop = (img * 255)[:, 96:416, 96:416].permute(0, 3, 1, 2)
+    xin = ((F.interpolate(crop, size=(112, 112), mode="bilinear", align_corners=False) / 255) - 0.5) / 0.5
+    with torch.no_grad():
+        ref = iresnet_forward(golden_sd, xin)
+    assert rel(emb, ref) < 1.5e-2
+    gt = ref[[1, 0]]
+    assert torch.allclose(identity_loss(emb, gt), identity_loss(ref, gt), atol=5e-3)

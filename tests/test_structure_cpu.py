@@ -136,32 +136,9 @@ def test_iresnet_oracle_vs_reference_golden():
     (fixture made by tests/golden/make_iresnet_golden.py)."""
     from oracle.iresnet import iresnet_forward, keyed_state_dict
     gold = torch.load(os.path.join(ROOT, "tests", "golden", "iresnet100_golden.pt"))
-    # rebuild the key/shape set without importing the reference: shapes follow iresnet.py:67-162
-    shapes = {}
-
-    def bn(p, c):
-        shapes.update({p + ".weight": (c,), p + ".bias": (c,), p + ".running_mean": (c,), p + ".running_var": (c,),
-                       p + ".num_batches_tracked": ()})
-    shapes["conv1.weight"] = (64, 3, 3, 3)
-    bn("bn1", 64)
-    shapes["prelu.weight"] = (64,)
-    inp = 64
-    for li, (planes, nblk) in enumerate(zip((64, 128, 256, 512), (3, 13, 30, 3)), start=1):
-        for b in range(nblk):
-            p = f"layer{li}.{b}"
-            bn(p + ".bn1", inp)
-            shapes[p + ".conv1.weight"] = (planes, inp, 3, 3)
-            bn(p + ".bn2", planes)
-            shapes[p + ".prelu.weight"] = (planes,)
-            shapes[p + ".conv2.weight"] = (planes, planes, 3, 3)
-            bn(p + ".bn3", planes)
-            if b == 0:
-                shapes[p + ".downsample.0.weight"] = (planes, inp, 1, 1)
-                bn(p + ".downsample.1", planes)
-            inp = planes
-    bn("bn2", 512)
-    shapes["fc.weight"], shapes["fc.bias"] = (512, 25088), (512,)
-    bn("features", 512)
+    # the key/shape set without importing the reference: shapes follow iresnet.py:67-162
+    from faceposegenerator_b200.weights import iresnet_manifest
+    shapes = dict(iresnet_manifest("r100"))
     assert len(shapes) == gold["n_state"] == 925
     sd = keyed_state_dict({k: torch.zeros(s, dtype=torch.long if k.endswith("tracked") else torch.float32)
                            for k, s in shapes.items()}, seed=0)
