@@ -845,6 +845,207 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
   }
 }
 
+
+// ---------------------------------------------------------------------------------------- short-context variant
+// Cross-attention over the text context (Tkv = 77): ONE K/V tile, so a CTA keeps K and V resident and walks a
+// chunk of consecutive 128-row query tiles of one (image, head) instead of paying the launch / TMEM-alloc /
+// barrier-init / K,V-load prologue per query tile.  S uses only NKV = ceil16(Tkv) <= 96 accumulator columns and is
+// double-buffered in TMEM (S0 | S1 | O = 96 + 96 + 64 columns), Q tiles are double-buffered in smem, so the MMA
+// warp computes S(i+1) while the softmax warps work on tile i.  2 CTAs per SM.
+constexpr int ATX_THREADS = 192;
+constexpr int ATX_SMEM = 2 * ATT_TILE /*K,V*/ + 2 * ATT_TILE /*Q x2*/ + 2 * ATT_TILE /*P*/ + 1024 + 128;
+constexpr int ATX_TMEM_COLS = 256;
+constexpr int ATX_S_STRIDE = 96;
+constexpr int ATX_O_COL = 192;
+
+__global__ void __launch_bounds__(ATX_THREADS, 2) attention_x_kernel(const __grid_constant__ AttnParams p, int qpc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + ATT_TILE;
+  uint8_t* sQ = sV + ATT_TILE;                  // [2]
+  uint8_t* sP = sQ + 2 * ATT_TILE;              // [2 k-atoms][128 x 64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_TILE);
+  uint64_t* kv_full = bars;          // 1
+  uint64_t* q_full = bars + 1;       // [2]
+  uint64_t* q_empty = bars + 3;      // [2]
+  uint64_t* s_full = bars + 5;       // [2]
+  uint64_t* p_full = bars + 7;       // 1 (count 4)
+  uint64_t* o_done = bars + 8;       // 1
+  uint64_t* o_free = bars + 9;       // 1 (count 4)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int n_qtiles = (p.Tq + ATT_BM - 1) / ATT_BM;
+  const int qt0 = blockIdx.x * qpc;
+  const int nq = min(qpc, n_qtiles - qt0);     // query tiles of this CTA (>= 1 by grid construction)
+  const int nkv = (p.Tkv + 15) & ~15;          // accumulator columns / PV depth actually used
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    mbar_init(p_full, 4);
+    mbar_init(o_done, 1);
+    mbar_init(o_free, 4);
+    mbar_fence_init();
+  }
+  if (warp == 5) tmem_alloc<ATX_TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ================================================================ TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * ATT_TILE);
+      tma_load_3d(sK, &p.tmK, kv_full, p.col0_k + head * ATT_D, 0, b);
+      tma_load_3d(sV, &p.tmV, kv_full, p.col0_v + head * ATT_D, 0, b);
+      for (int i = 0; i < nq; ++i) {
+        const int slot = i & 1;
+        mbar_wait(&q_empty[slot], ((i >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[slot], ATT_TILE);
+        tma_load_3d(sQ + slot * ATT_TILE, &p.tmQ, &q_full[slot], p.col0_q + head * ATT_D, (qt0 + i) * ATT_BM, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ================================================================ MMA issuer
+    const uint32_t idesc_s = umma_idesc_bf16(ATT_BM, nkv, 0, 0);
+    constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // B (= V) is MN-major
+    const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK));
+    const uint64_t pdesc = umma_smem_desc_sw128(smem_u32(sP));
+    const uint32_t vbase = smem_u32(sV);
+    auto issue_qk = [&](int i) {   // S[i & 1] = Q_i K^T
+      const int slot = i & 1;
+      mbar_wait(&q_full[slot], (i >> 1) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ + slot * ATT_TILE));
+        const uint32_t tS = tmem_base + slot * ATX_S_STRIDE;
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k) umma_bf16(tS, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&q_empty[slot]);
+        umma_commit(&s_full[slot]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(kv_full, 0);
+    tc_fence_after();
+    issue_qk(0);
+    for (int i = 0; i < nq; ++i) {
+      // S buffer (i + 1) & 1 was last read by the softmax of tile i - 1, which finished before p_full(i - 1)
+      if (i + 1 < nq) issue_qk(i + 1);
+      mbar_wait(p_full, i & 1);            // P_i staged
+      if (i > 0) mbar_wait(o_free, (i - 1) & 1);   // O_{i-1} has been read out
+      tc_fence_after();
+      if (lane == 0) {
+        for (int kk = 0; kk < nkv / 16; ++kk) {
+          const uint64_t ad = pdesc + static_cast<uint64_t>(((kk >> 2) * ATT_TILE + (kk & 3) * 32) >> 4);
+          const uint64_t bd = umma_smem_desc_sw128(vbase + kk * 2048);
+          umma_bf16(tmem_base + ATX_O_COL, ad, bd, IDESC_O, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(o_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================================================================ softmax + epilogue warps (thread = query row)
+    const int r = warp * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const float c = p.scale_log2;
+    uint8_t* prow = sP + r * 128;
+    const int sw = r & 7;
+    for (int i = 0; i < nq; ++i) {
+      const uint32_t tS = tmem_base + lane_off + (i & 1) * ATX_S_STRIDE;
+      mbar_wait(&s_full[i & 1], (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t s0[32], s1[32], s2[32];
+      IDB_TMEM_LD_X32(tS, s0);
+      IDB_TMEM_LD_X32(tS + 32, s1);
+      if (nkv > 64) IDB_TMEM_LD_X32(tS + 64, s2);
+      tmem_ld_wait();
+      float m = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        if (k >= p.Tkv) s0[k] = 0xff800000u;
+        if (32 + k >= p.Tkv) s1[k] = 0xff800000u;
+        if (nkv <= 64 || 64 + k >= p.Tkv) s2[k] = 0xff800000u;
+        m = fmaxf(m, fmaxf(__uint_as_float(s0[k]), fmaxf(__uint_as_float(s1[k]), __uint_as_float(s2[k]))));
+      }
+      const float neg_m = -m * c;
+      float l = 0.f;
+      if (i > 0) mbar_wait(o_done, (i - 1) & 1);   // PV_{i-1} retired: the P buffer is free
+      auto emit = [&](uint32_t (&sv)[32], int ch) {
+        float pv[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          pv[k] = ex2(fmaf(__uint_as_float(sv[k]), c, neg_m));   // masked keys: exp2(-inf) = 0
+          l += pv[k];
+        }
+        uint8_t* base = prow + (ch >> 1) * ATT_TILE;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (ch & 1) * 4 + q;
+          uint4 w = make_uint4(pack_bf16x2(pv[8 * q], pv[8 * q + 1]), pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]),
+                               pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]), pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]));
+          *reinterpret_cast<uint4*>(base + ((chunk ^ sw) << 4)) = w;
+        }
+      };
+      emit(s0, 0);
+      emit(s1, 1);
+      if (nkv > 64) emit(s2, 2);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // ---- O_i / l -> global
+      mbar_wait(o_done, i & 1);
+      tc_fence_after();
+      const float inv_l = 1.0f / l;
+      const int row = (qt0 + i) * ATT_BM + r;
+      __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Tq + row) * p.ld_out + head * ATT_D;
+      uint32_t v0[32], v1[32];
+      IDB_TMEM_LD_X32(tmem_base + lane_off + ATX_O_COL, v0);
+      IDB_TMEM_LD_X32(tmem_base + lane_off + ATX_O_COL + 32, v1);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free);
+      if (row < p.Tq) {
+        uint4* dst = reinterpret_cast<uint4*>(orow);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          dst[q] = make_uint4(pack_bf16x2(__uint_as_float(v0[8 * q]) * inv_l, __uint_as_float(v0[8 * q + 1]) * inv_l),
+                              pack_bf16x2(__uint_as_float(v0[8 * q + 2]) * inv_l, __uint_as_float(v0[8 * q + 3]) * inv_l),
+                              pack_bf16x2(__uint_as_float(v0[8 * q + 4]) * inv_l, __uint_as_float(v0[8 * q + 5]) * inv_l),
+                              pack_bf16x2(__uint_as_float(v0[8 * q + 6]) * inv_l, __uint_as_float(v0[8 * q + 7]) * inv_l));
+          dst[4 + q] = make_uint4(pack_bf16x2(__uint_as_float(v1[8 * q]) * inv_l, __uint_as_float(v1[8 * q + 1]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v1[8 * q + 2]) * inv_l, __uint_as_float(v1[8 * q + 3]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v1[8 * q + 4]) * inv_l, __uint_as_float(v1[8 * q + 5]) * inv_l),
+                                  pack_bf16x2(__uint_as_float(v1[8 * q + 6]) * inv_l, __uint_as_float(v1[8 * q + 7]) * inv_l));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc<ATX_TMEM_COLS>(tmem_base);
+  }
+}
+
 }  // namespace idb
 
 using namespace idb;
@@ -897,6 +1098,24 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
   }
   static const int force_variant = getenv("IDB_ATTN_VARIANT") ? atoi(getenv("IDB_ATTN_VARIANT")) : 0;
   const bool use256 = force_variant ? (force_variant == 256) : (a->t_q >= 1024 && a->t_kv >= 512);
+  if (a->t_kv <= 96 && force_variant == 0) {   // short context (cross-attention): K/V resident, chunks of query tiles per CTA
+    static bool configured4 = false;
+    if (!configured4) {
+      cudaError_t e4 = cudaFuncSetAttribute(attention_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATX_SMEM);
+      if (e4 != cudaSuccess) return fail(IDB_E_CUDA, std::string("cudaFuncSetAttribute(attention_x): ") + cudaGetErrorString(e4));
+      configured4 = true;
+    }
+    const int n_qtiles = (a->t_q + ATT_BM - 1) / ATT_BM;
+    const long long units = static_cast<long long>(n_qtiles) * a->heads * a->batch;
+    int qpc = static_cast<int>((units + 2LL * num_sms() - 1) / (2LL * num_sms()));   // one resident wave at 2 CTAs / SM
+    if (qpc < 1) qpc = 1;
+    if (qpc > n_qtiles) qpc = n_qtiles;
+    dim3 grid4((n_qtiles + qpc - 1) / qpc, a->heads, a->batch);
+    attention_x_kernel<<<grid4, ATX_THREADS, ATX_SMEM, stream>>>(p, qpc);
+    cudaError_t e4 = cudaGetLastError();
+    if (e4 != cudaSuccess) return fail(IDB_E_CUDA, std::string("attention_x launch: ") + cudaGetErrorString(e4));
+    return IDB_OK;
+  }
   static const int rs_poly = getenv("IDB_ATTN_RSPOLY") ? atoi(getenv("IDB_ATTN_RSPOLY")) : 3;
   if (use256 && force_variant != 256) {   // row-split 256-query kernel (16 softmax warps)
     void (*kern)(AttnParams) = attention_rs_kernel<3>;
