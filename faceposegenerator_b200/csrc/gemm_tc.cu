@@ -100,7 +100,12 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
   return c;
 }
 
-template <int BLOCK_N, int STAGES, bool LORA, int CG>
+// EPI: compile-time specialisation of the epilogue (the small-K layers are bound by its instruction count):
+//   0 = generic (every feature decided at run time; also split-K partials, both outputs, profiling switches)
+//   1 = 16-bit output only, no GEGLU        (q/k/v, FF-out; bias / residual / PReLU still optional at run time)
+//   2 = 16-bit output of GEGLU(acc + bias)  (FF-in)
+//   3 = fp32 output only                    (residual-stream producers; bias / rowvec / residual / stats / PReLU optional)
+template <int BLOCK_N, int STAGES, bool LORA, int CG, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
   constexpr int B_ROWS = UMMA_N / CG;                 // B rows this CTA stages (half the tile in a pair)
@@ -422,13 +427,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const int rb = r / (p.BW * p.BH);
     const int r0 = quarter * 32;   // first row of this warp's box inside the tile rectangle
     const int bx0 = r0 % p.BW, by0 = (r0 / p.BW) % p.BH, bb0 = r0 / (p.BW * p.BH);
-    const bool geglu = (p.flags & IDB_EPI_GEGLU) != 0;
+    const bool geglu = EPI ? (EPI == 2) : ((p.flags & IDB_EPI_GEGLU) != 0);
+    const bool has_f32 = EPI ? (EPI == 3) : (p.out_f32 != nullptr);
+    const bool has_b16 = EPI ? (EPI != 3) : (p.out_bf16 != nullptr);
+    const bool ksplit = EPI ? false : (p.k_splits > 1);
+    const int dbg = EPI ? 0 : p.debug;
+    const bool has_rowvec = (EPI == 1 || EPI == 2) ? false : (p.rowvec != nullptr);
+    const bool has_prelu = (EPI == 2) ? false : (p.prelu != nullptr);
+    const bool has_stats = (EPI == 1 || EPI == 2) ? false : (p.stats != nullptr);
     const bool f16 = (p.flags & IDB_EPI_F16) != 0;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t sbuf = smem_base + STG_OFFSET + warp * EPI_BUF_BYTES;
     const uint32_t rbar = smem_base + STAGES * STAGE_BYTES + RES_BAR_OFFSET + warp * 8;
-    const bool both = p.out_f32 != nullptr && p.out_bf16 != nullptr;   // rare: staged and stored one after the other
-    const bool res_tma = p.residual != nullptr && !geglu && p.k_splits == 1 && (p.debug & 15) == 0;
+    const bool both = has_f32 && has_b16;   // rare: staged and stored one after the other
+    const bool res_tma = p.residual != nullptr && !geglu && !ksplit && (dbg & 15) == 0;
     const int sw = lane & 7;       // SWIZZLE_128B phase of this lane's 128-byte fp32 staging row
     constexpr int NCH = BLOCK_N / 32;
     constexpr int MAXC = (NCH + 3) / 4;   // chunks per warp per tile
@@ -436,7 +448,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     uint32_t g = 0;                // residual chunks loaded so far (barrier parity = g & 1)
     int buf = 0;                   // accumulator ring position of the current tile
     uint32_t bphase = 0;
-    const bool prof = IDB_EPI_PROF && (p.debug & 0x400) != 0;   // per-warp clock() breakdown of the epilogue phases -> p.workspace (build with -DIDB_EPI_PROF=1)
+    const bool prof = IDB_EPI_PROF && (dbg & 0x400) != 0;   // per-warp clock() breakdown of the epilogue phases -> p.workspace (build with -DIDB_EPI_PROF=1)
     uint32_t tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t tc = 0;
 #define IDB_TICK(k)                       \
@@ -537,7 +549,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       for (int chunk = chunk0; chunk < NCH; chunk += 4, ++ci) {
         const int col = n0 + chunk * 32;
         uint32_t v[32];
-        if ((p.debug & 15) == 5) continue;   // profiling: no TMEM read, no stores
+        if ((dbg & 15) == 5) continue;   // profiling: no TMEM read, no stores
         if (res_tma && ci > 0 && col < p.N && lane == 0) {   // (the first chunk's residual was requested above)
           tma_store_wait_read();
           mbar_expect_tx_a(rbar, EPI_BUF_BYTES);
@@ -546,12 +558,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         IDB_TMEM_LD_X32(t_row + chunk * 32, v);
         tmem_ld_wait();
         IDB_TICK(2);   // TMEM load
-        if (col >= p.N || (p.debug & 15) == 4) continue;   // warp-uniform (debug 4: TMEM read only)
+        if (col >= p.N || (dbg & 15) == 4) continue;   // warp-uniform (debug 4: TMEM read only)
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
 
-        if (p.k_splits > 1) {  // raw partial sums (tiny-M layers only); the finalize kernel applies the epilogue
+        if (ksplit) {  // raw partial sums (tiny-M layers only); the finalize kernel applies the epilogue
           if (row_ok) {
             float4* dst = reinterpret_cast<float4*>(p.workspace + (static_cast<long long>(ks) * p.M + orow) * p.N + col);
 #pragma unroll
@@ -559,7 +571,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
           continue;
         }
-        if (p.bias != nullptr && !(p.debug & 0x20)) {
+        if (p.bias != nullptr && !(dbg & 0x20)) {
           const float4* bp = reinterpret_cast<const float4*>(bsm + ci * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -568,7 +580,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             fadd2(acc[4 * j + 2], acc[4 * j + 3], acc[4 * j + 2], acc[4 * j + 3], bv.z, bv.w);
           }
         }
-        if (p.rowvec != nullptr && row_ok) {
+        if (has_rowvec && row_ok) {
           const float4* rp = reinterpret_cast<const float4*>(p.rowvec + static_cast<long long>(b) * p.rowvec_ld + col);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -577,7 +589,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             fadd2(acc[4 * j + 2], acc[4 * j + 3], acc[4 * j + 2], acc[4 * j + 3], rv.z, rv.w);
           }
         }
-        if (p.prelu != nullptr) {   // per-channel PReLU (IResNet)
+        if (has_prelu) {   // per-channel PReLU (IResNet)
           const float4* sp = reinterpret_cast<const float4*>(p.prelu + col);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -630,11 +642,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           __syncwarp();
         }
         IDB_TICK(4);   // residual wait + add, or wait for the previous store's smem read
-        if (p.stats != nullptr && !row_ok) {
+        if (has_stats && !row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) acc[j] = 0.f;
         }
-        if (p.out_f32 != nullptr && !(p.debug & 0x40)) {   // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row `lane` lands at j ^ (lane & 7)
+        if (has_f32 && !(dbg & 0x40)) {   // 128-byte rows, SWIZZLE_128B: 16-byte chunk j of row `lane` lands at j ^ (lane & 7)
           const uint32_t row = sbuf + lane * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -643,7 +655,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                            "f"(acc[4 * j + 1]), "f"(acc[4 * j + 2]), "f"(acc[4 * j + 3])
                            : "memory");
           }
-          if (p.stats != nullptr) {
+          if (has_stats) {
             // GroupNorm statistics of the tensor being written, for free: lane c reduces column c of the
             // staged 32 x 32 fp32 chunk (rows outside the image were staged as zeros)
             __syncwarp();
@@ -659,17 +671,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             if (ocol + lane < p.N_out) p.stats[rowblock * p.N_out + ocol + lane] = make_float2(cs, cs2);
           }
           IDB_TICK(5);   // staging (+ statistics)
-          if (!(p.debug & 0x10)) fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
+          if (!(dbg & 0x10)) fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
           IDB_TICK(6);   // proxy fence
           if (lane == 0) {
-            if (!(p.debug & 0x80)) tma_store_4d(&p.tmOutF, sbuf, ocol, cx, cy, cb);
+            if (!(dbg & 0x80)) tma_store_4d(&p.tmOutF, sbuf, ocol, cx, cy, cb);
             tma_store_commit();
             if (both) tma_store_wait_read();   // the bf16 copy is staged in the same buffer next
           }
           if (both) __syncwarp();
         }
-        if (p.out_bf16 != nullptr && !(p.debug & 0x40)) {  // dense rows of nc * 2 bytes
+        if (has_b16 && !(dbg & 0x40)) {  // dense rows of nc * 2 bytes
           const uint32_t row = sbuf + lane * (nc * 2);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -680,11 +692,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                            : "memory");
           }
           IDB_TICK(5);   // staging
-          if (!(p.debug & 0x10)) fence_proxy_async_smem();
+          if (!(dbg & 0x10)) fence_proxy_async_smem();
           __syncwarp();
           IDB_TICK(6);   // proxy fence
           if (lane == 0) {
-            if (!(p.debug & 0x80)) tma_store_4d(&p.tmOutB, sbuf, ocol, cx, cy, cb);
+            if (!(dbg & 0x80)) tma_store_4d(&p.tmOutB, sbuf, ocol, cx, cy, cb);
             tma_store_commit();
           }
         }
@@ -784,13 +796,13 @@ static int pow2_divisor(int v, int cap) {
   return d;
 }
 
-template <int BLOCK_N, int STAGES, bool LORA, int CG>
-static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
+template <int BLOCK_N, int STAGES, bool LORA, int CG, int EPI>
+static int launch_gemm_e(const GemmParams& p, int grid, cudaStream_t stream) {
   constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
   constexpr int smem_bytes = STAGES * (A_TILE_BYTES + (UMMA_N / CG) * BLOCK_K * 2) + 1024 + 1024 + EPI_STAGING_BYTES +
                              EPI_BIAS_BYTES + (LORA ? 1024 + A_TILE_BYTES + 2 * (BLOCK_N / CG) * BLOCK_K * 2 : 0);   // ring + slack + barriers + staging + bias (+ LoRA T / U tiles)
   static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
-  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, LORA, CG>;
+  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, LORA, CG, EPI>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -813,6 +825,18 @@ static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("gemm_tc launch: ") + cudaGetErrorString(e));
   return IDB_OK;
+}
+
+// epi: 0 generic, 1 / 2 / 3 specialised (see gemm_tc_kernel); only the CTA-pair kernels the UNet spends its time in are
+// specialised, everything else runs the generic epilogue
+template <int BLOCK_N, int STAGES, bool LORA, int CG>
+static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream, int epi) {
+  if (CG == 2) {
+    if (epi == 1) return launch_gemm_e<BLOCK_N, STAGES, LORA, CG, (CG == 2 ? 1 : 0)>(p, grid, stream);
+    if (epi == 2 && !LORA) return launch_gemm_e<BLOCK_N, STAGES, LORA, CG, (CG == 2 && !LORA ? 2 : 0)>(p, grid, stream);
+    if (epi == 3) return launch_gemm_e<BLOCK_N, STAGES, LORA, CG, (CG == 2 ? 3 : 0)>(p, grid, stream);
+  }
+  return launch_gemm_e<BLOCK_N, STAGES, LORA, CG, 0>(p, grid, stream);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -1035,15 +1059,23 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   if (p.k_splits > 1) pk.stats = nullptr;   // statistics come from rowblock_stats_kernel after the finalize
   const int total_tiles = m_units * p.n_tiles_n * p.k_splits;
   const int grid = cg * (total_tiles < units ? total_tiles : units);
+  // epilogue specialisation (generic whenever a profiling switch, split-K or both outputs are in play)
+  int epi = 0;
+  static const int no_spec = env_int("IDB_GEMM_NOSPEC", 0);
+  if (!no_spec && dbg == 0 && p.k_splits == 1 && !(a->out_f32 && a->out_bf16)) {
+    if (a->out_f32) epi = 3;
+    else if (geglu) epi = (a->residual || a->rowvec || a->prelu) ? 0 : 2;
+    else epi = (a->rowvec || a->stats_partials) ? 0 : 1;
+  }
   int rc;
-  if (lora && cg == 2) rc = launch_gemm<160, 4, true, 2>(pk, grid, stream);
-  else if (lora) rc = launch_gemm<160, 2, true, 1>(pk, grid, stream);
-  else if (cg == 1 && block_n == 256) rc = launch_gemm<256, 3, false, 1>(pk, grid, stream);
-  else if (cg == 1 && block_n == 160) rc = launch_gemm<160, 4, false, 1>(pk, grid, stream);
-  else if (cg == 1) rc = launch_gemm<128, 4, false, 1>(pk, grid, stream);
-  else if (block_n == 256) rc = launch_gemm<256, 4, false, 2>(pk, grid, stream);
-  else if (block_n == 160) rc = launch_gemm<160, 6, false, 2>(pk, grid, stream);
-  else rc = launch_gemm<128, 6, false, 2>(pk, grid, stream);
+  if (lora && cg == 2) rc = launch_gemm<160, 4, true, 2>(pk, grid, stream, epi);
+  else if (lora) rc = launch_gemm<160, 2, true, 1>(pk, grid, stream, epi);
+  else if (cg == 1 && block_n == 256) rc = launch_gemm<256, 3, false, 1>(pk, grid, stream, epi);
+  else if (cg == 1 && block_n == 160) rc = launch_gemm<160, 4, false, 1>(pk, grid, stream, epi);
+  else if (cg == 1) rc = launch_gemm<128, 4, false, 1>(pk, grid, stream, epi);
+  else if (block_n == 256) rc = launch_gemm<256, 4, false, 2>(pk, grid, stream, epi);
+  else if (block_n == 160) rc = launch_gemm<160, 6, false, 2>(pk, grid, stream, epi);
+  else rc = launch_gemm<128, 6, false, 2>(pk, grid, stream, epi);
   if (rc) return rc;
 
   if (p.k_splits > 1) {
