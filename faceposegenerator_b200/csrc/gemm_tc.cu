@@ -39,7 +39,7 @@ constexpr int NUM_THREADS = (NUM_EPI_WARPS + 2) * 32;
 constexpr int TMEM_COLS = 512;
 constexpr int EPI_BUF_BYTES = 32 * 32 * 4;                          // per-warp staging buffer: a 32 x 32 fp32 chunk (SWIZZLE_128B rows) or a bf16 chunk
 constexpr int EPI_STAGING_BYTES = NUM_EPI_WARPS * EPI_BUF_BYTES;    // 65,536 B
-constexpr int EPI_BIAS_BYTES = NUM_EPI_WARPS * 2 * 32 * 4;          // per-warp bias of its (<= 2) chunks of the tile
+constexpr int epi_bias_bytes(int tile_n) { return NUM_EPI_WARPS * ((tile_n / 32 + 3) / 4) * 32 * 4; }   // per-warp bias of its chunks of the tile
 constexpr int RES_BAR_OFFSET = 512;                                 // residual-load mbarriers [warp] inside the barrier KiB
 
 // Division of small non-negative integers by a launch-time constant: q = (x * ceil(2^40 / d)) >> 40, exact for
@@ -105,11 +105,18 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
 //   1 = 16-bit output only, no GEGLU        (q/k/v, FF-out; bias / residual / PReLU still optional at run time)
 //   2 = 16-bit output of GEGLU(acc + bias)  (FF-in)
 //   3 = fp32 output only                    (residual-stream producers; bias / rowvec / residual / stats / PReLU optional)
-template <int BLOCK_N, int STAGES, bool LORA, int CG, int EPI>
+// NSUB = 2 ("dual-N"): one tile is 2 x BLOCK_N output columns = two accumulators that share every A tile, i.e. two
+// UMMAs per K step.  Operand bytes per MAC drop by a further (128 + N) / (128 + N/2) over the CTA pair, which is what
+// the big-K convolutions are bound by (L2 -> SM operand feed); the three BLOCK_N-column TMEM buffers are used as a ring
+// of which a tile occupies two, so the next tile's mainloop starts once the epilogue has drained the first half.
+template <int BLOCK_N, int STAGES, bool LORA, int CG, int EPI, int NSUB>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
-  constexpr int B_ROWS = UMMA_N / CG;                 // B rows this CTA stages (half the tile in a pair)
-  constexpr int B_TILE_BYTES = B_ROWS * BLOCK_K * 2;
+  constexpr int TILE_N = BLOCK_N * NSUB;
+  constexpr int B_ROWS = UMMA_N / CG;                 // B rows this CTA stages per accumulator (half of them in a pair)
+  constexpr int B_SUB_BYTES = B_ROWS * BLOCK_K * 2;
+  constexpr int B_TILE_BYTES = NSUB * B_SUB_BYTES;
+  static_assert(NSUB == 1 || (NSUB == 2 && !LORA && CG == 2 && 3 * BLOCK_N <= TMEM_COLS), "dual-N: CTA pairs, no LoRA, three TMEM buffers");
   constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
   constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M * CG, UMMA_N, 0, 0);
   static_assert(B_ROWS % 8 == 0, "B tile must be whole 8-row swizzle groups");
@@ -117,17 +124,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   constexpr int BIAS_STG_OFFSET = STG_OFFSET + EPI_STAGING_BYTES;
   // LoRA only: the x A^T tile (bf16, 128 rows x 128 B, K-major SWIZZLE_128B, first 32 B of a row used) and two buffers
   // for the up-projection weight tile of the current N block (same layout, BLOCK_N / CG rows)
-  constexpr int LORA_T_OFFSET = (BIAS_STG_OFFSET + EPI_BIAS_BYTES + 1023) / 1024 * 1024;
+  constexpr int LORA_T_OFFSET = (BIAS_STG_OFFSET + epi_bias_bytes(TILE_N) + 1023) / 1024 * 1024;
   constexpr int LORA_U_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;
   constexpr int LORA_U_OFFSET = LORA_T_OFFSET + A_TILE_BYTES;
   constexpr int LORA_BAR_OFFSET = 704;   // t_ready[4], d_full[4], up_full[2], up_empty[2] inside the barrier KiB
   static_assert(!LORA || LORA_U_BYTES % 1024 == 0, "up-projection tile must keep 1024B alignment");
-  static_assert(BLOCK_N <= 256, "each epilogue warp stages at most two chunks per tile");
+  static_assert(TILE_N <= 512, "each epilogue warp stages at most four chunks per tile");
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
   // accumulator ring in TMEM: as many buffers as fit the 512 columns, so the MMA warp can run further ahead of the
   // (latency-bound) epilogue of small-K tiles
   constexpr int TMEM_BUF_STRIDE = (UMMA_N + 31) / 32 * 32;
-  constexpr int NBUF = (TMEM_COLS / TMEM_BUF_STRIDE) > 4 ? 4 : (TMEM_COLS / TMEM_BUF_STRIDE);
+  constexpr int NBUF = NSUB == 2 ? 3 : ((TMEM_COLS / TMEM_BUF_STRIDE) > 4 ? 4 : (TMEM_COLS / TMEM_BUF_STRIDE));
   static_assert(NBUF >= 2, "need at least a double-buffered accumulator");
   static_assert(STAGE_BYTES % 1024 == 0, "stage must keep 1024B alignment for SWIZZLE_128B");
 
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int n_blk = tc_.n_blk, ks = tc_.ks;
         const int tx = tc_.tx, ty = tc_.ty, tb = tc_.tb;   // tb >= number of batch tiles for a padding block: TMA zero-fills
         const int x0 = tx * p.BW, y0 = ty * p.BH, b0 = tb * p.BB;
-        const int n0 = n_blk * BLOCK_N + rank * B_ROWS;
+        const int n0 = n_blk * TILE_N + rank * B_ROWS;
         const int lora_row = LORA ? p.fd_seg.div(n_blk * BLOCK_N) * 16 : 0;   // this tile's adapter (16 padded down-projection rows)
         const int kb_begin = ks * p.kb_per_split;
         const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
@@ -253,6 +260,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               else tma2_load_4d_a(sa, tmA, fb, c0, c1, c2, c3);
               if (!LORA) {
                 tma2_load_2d_a(sb, &p.tmW, fb, kb * BLOCK_K, n0);
+                if (NSUB == 2) tma2_load_2d_a(sb + B_SUB_BYTES, &p.tmW, fb, kb * BLOCK_K, n0 + BLOCK_N);   // second accumulator's rows
               } else if (rank == 0) {   // B rows [0, UMMA_N/2) of the pair's tile: all base-weight rows
                 tma2_load_2d_a(sb, &p.tmW, fb, kb * BLOCK_K, n0);
               } else {                  // B rows [UMMA_N/2, UMMA_N): the remaining base rows, then the 16 LoRA-down rows
@@ -310,6 +318,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       bool up_pending = false;
       int up_buf = 0;
       uint32_t up_bphase = 0;
+      int dpos = 0;                      // dual-N: next free position of the 3-buffer accumulator ring
+      uint32_t duse[3] = {0, 0, 0};      // dual-N: how often each buffer has been handed to a tile
       auto up_ready = [&](int ubuf, uint32_t ubphase, int uit) -> bool {   // warp-uniform probe
         uint64_t* lb = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + LORA_BAR_OFFSET);
         return mbar_try(&lb[ubuf], ubphase) && mbar_try(&lb[8 + (uit & 1)], (uit >> 1) & 1);
@@ -342,7 +352,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int kb_begin = ks * p.kb_per_split;
         const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
         const uint32_t c0 = IDB_EPI_PROF ? clock() : 0u;
-        if (LORA) {   // while waiting for the accumulator buffer, fire the previous tile's up-projection as soon as it can go
+        int buf_b = 0;
+        if (NSUB == 2) {   // this tile's two accumulators: ring positions dpos, dpos + 1 (mod 3); each waits for its own drain
+          buf = dpos;
+          buf_b = dpos == 2 ? 0 : dpos + 1;
+          mbar_wait(&tmem_empty[buf], (duse[buf] & 1) ^ 1);
+          mbar_wait(&tmem_empty[buf_b], (duse[buf_b] & 1) ^ 1);
+          ++duse[buf], ++duse[buf_b];
+          dpos = buf_b == 2 ? 0 : buf_b + 1;
+        } else if (LORA) {   // while waiting for the accumulator buffer, fire the previous tile's up-projection as soon as it can go
           while (!mbar_try(&tmem_empty[buf], bphase ^ 1)) {
             if (up_pending && up_ready(up_buf, up_bphase, it - 1)) {
               issue_up(up_buf, up_bphase, it - 1);
@@ -371,7 +389,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           const uint64_t adesc = desc_hi | static_cast<uint64_t>((sa >> 4) & 0x3FFF);
           const uint64_t bdesc = desc_hi | static_cast<uint64_t>(((sa + A_TILE_BYTES) >> 4) & 0x3FFF);
           const uint32_t eb = smem_base + STAGES * STAGE_BYTES + (STAGES + stage) * 8;        // &empty_bar[stage]
-          const uint32_t tf = smem_base + STAGES * STAGE_BYTES + (2 * STAGES + buf) * 8;      // &tmem_full[buf]
+          const uint32_t tf = smem_base + STAGES * STAGE_BYTES + (2 * STAGES + (NSUB == 2 ? (it & 1) : buf)) * 8;   // &tmem_full[..]
+          const uint64_t bdesc2 = bdesc + static_cast<uint64_t>(B_SUB_BYTES >> 4);
+          const uint32_t d_tmem2 = tmem_base + buf_b * TMEM_BUF_STRIDE;
           const uint32_t acc0 = (kb > kb_begin) ? 1u : 0u;
           if (elect_one()) {
             if ((p.debug & 15) != 1 && (p.debug & 15) != 3) {
@@ -385,6 +405,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
                 umma2_bf16(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
                 umma2_bf16(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
                 umma2_bf16(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+                if (NSUB == 2) {
+                  umma2_bf16(d_tmem2, adesc, bdesc2, idesc, acc0);
+                  umma2_bf16(d_tmem2, adesc + 2, bdesc2 + 2, idesc, 1u);
+                  umma2_bf16(d_tmem2, adesc + 4, bdesc2 + 4, idesc, 1u);
+                  umma2_bf16(d_tmem2, adesc + 6, bdesc2 + 6, idesc, 1u);
+                }
               }
             }
             if (CG == 1) {
@@ -402,7 +428,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
         }
         if (LORA) up_pending = true, up_buf = buf, up_bphase = bphase;
-        if (++buf == NBUF) buf = 0, bphase ^= 1;
+        if (NSUB == 1 && ++buf == NBUF) buf = 0, bphase ^= 1;
       }
       if (LORA && up_pending) issue_up(up_buf, up_bphase, it - 1);
       if (IDB_EPI_PROF && (p.debug & 0x400) && lane == 0 && p.workspace != nullptr) {
@@ -442,12 +468,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const bool both = has_f32 && has_b16;   // rare: staged and stored one after the other
     const bool res_tma = p.residual != nullptr && !geglu && !ksplit && (dbg & 15) == 0;
     const int sw = lane & 7;       // SWIZZLE_128B phase of this lane's 128-byte fp32 staging row
-    constexpr int NCH = BLOCK_N / 32;
+    constexpr int NCH = TILE_N / 32;
+    constexpr int SUBCH = BLOCK_N / 32;   // chunks per accumulator
     constexpr int MAXC = (NCH + 3) / 4;   // chunks per warp per tile
     float* bsm = reinterpret_cast<float*>(smem + BIAS_STG_OFFSET) + warp * (MAXC * 32);
     uint32_t g = 0;                // residual chunks loaded so far (barrier parity = g & 1)
     int buf = 0;                   // accumulator ring position of the current tile
     uint32_t bphase = 0;
+    int dpos = 0;                  // dual-N: ring position / per-buffer use counts, mirrored from the MMA warp
+    uint32_t duse[3] = {0, 0, 0};
     const bool prof = IDB_EPI_PROF && (dbg & 0x400) != 0;   // per-warp clock() breakdown of the epilogue phases -> p.workspace (build with -DIDB_EPI_PROF=1)
     uint32_t tp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint32_t tc = 0;
@@ -461,7 +490,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
     float pre_bias[MAXC];
     auto prefetch_tables = [&](int tl, int itn) {   // lane c fetches column col + c of each chunk (coalesced)
-      const int n0_ = decode_tile<CG>(p, tl, 0).n_blk * BLOCK_N;
+      const int n0_ = decode_tile<CG>(p, tl, 0).n_blk * TILE_N;
 #pragma unroll
       for (int ci = 0; ci < MAXC; ++ci) {
         const int col = n0_ + (((slot + itn) & 3) + 4 * ci) * 32 + lane;
@@ -479,7 +508,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const int x = tx * p.BW + rx, y = ty * p.BH + ry, b = tb * p.BB + rb;
       const bool row_ok = (x < p.Wo) && (y < p.Ho) && (b < p.B);
       const long long orow = (static_cast<long long>(b) * p.Ho + y) * p.Wo + x;
-      const int n0 = n_blk * BLOCK_N;
+      const int n0 = n_blk * TILE_N;
       const int chunk0 = (slot + it) & 3;
       const int cx = tx * p.BW + bx0, cy = ty * p.BH + by0, cb = tb * p.BB + bb0;   // this warp's 32-row box
 
@@ -500,7 +529,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       __syncwarp();
       if (tile + num_units < total_tiles) prefetch_tables(tile + num_units, it + 1);
       IDB_TICK(0);   // tile prologue (bias / LoRA prefetch, residual request)
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + buf * TMEM_BUF_STRIDE;
+      int buf_b = 0;
+      uint32_t full_phase = bphase;
+      int full_idx = buf;
+      if (NSUB == 2) {
+        buf = dpos;
+        buf_b = dpos == 2 ? 0 : dpos + 1;
+        ++duse[buf], ++duse[buf_b];
+        dpos = buf_b == 2 ? 0 : buf_b + 1;
+        full_idx = it & 1;
+        full_phase = (it >> 1) & 1;
+      }
+      const uint32_t t_lanes = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      const uint32_t t_row = t_lanes + buf * TMEM_BUF_STRIDE;
       if (LORA) {
         // fused LoRA: columns [BLOCK_N, BLOCK_N + 16) of the accumulator hold T = x A^T (one adapter per N segment).
         // The slot-0 warps round T to bf16 into a K-major operand tile; the MMA warp then adds T U^T (U = scaled
@@ -540,10 +581,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         }
         mbar_wait(&lb[4 + buf], bphase);   // d_full
       } else {
-        mbar_wait(&tmem_full[buf], bphase);
+        mbar_wait(&tmem_full[full_idx], full_phase);
       }
       tc_fence_after();
       IDB_TICK(1);   // waiting for the accumulator
+      bool released_a = false;
 
       int ci = 0;
       for (int chunk = chunk0; chunk < NCH; chunk += 4, ++ci) {
@@ -555,7 +597,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           mbar_expect_tx_a(rbar, EPI_BUF_BYTES);
           tma_load_4d_a(sbuf, &p.tmRes, rbar, col, cx, cy, cb);
         }
-        IDB_TMEM_LD_X32(t_row + chunk * 32, v);
+        if (NSUB == 2 && chunk >= SUBCH && !released_a) {   // done with the first accumulator: the next tile's mainloop may reuse it
+          released_a = true;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (rank != 0) mbar_arrive_remote(&tmem_empty[buf], 0);
+            else mbar_arrive(&tmem_empty[buf]);
+          }
+        }
+        IDB_TMEM_LD_X32(NSUB == 2 ? (t_lanes + (chunk >= SUBCH ? buf_b : buf) * TMEM_BUF_STRIDE + (chunk >= SUBCH ? chunk - SUBCH : chunk) * 32)
+                                  : (t_row + chunk * 32), v);
         tmem_ld_wait();
         IDB_TICK(2);   // TMEM load
         if (col >= p.N || (dbg & 15) == 4) continue;   // warp-uniform (debug 4: TMEM read only)
@@ -702,14 +754,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         }
         IDB_TICK(7);   // store issue
       }
-      // this warp is done reading the accumulator buffer
+      // this warp is done reading the accumulator buffer(s)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CG == 2 && rank != 0) mbar_arrive_remote(&tmem_empty[buf], 0);   // the leader's MMA warp waits on ITS barrier
-        else mbar_arrive(&tmem_empty[buf]);
+        if (NSUB == 2) {
+          if (!released_a) {
+            if (rank != 0) mbar_arrive_remote(&tmem_empty[buf], 0);
+            else mbar_arrive(&tmem_empty[buf]);
+          }
+          if (rank != 0) mbar_arrive_remote(&tmem_empty[buf_b], 0);
+          else mbar_arrive(&tmem_empty[buf_b]);
+        } else if (CG == 2 && rank != 0) {
+          mbar_arrive_remote(&tmem_empty[buf], 0);   // the leader's MMA warp waits on ITS barrier
+        } else {
+          mbar_arrive(&tmem_empty[buf]);
+        }
       }
-      if (++buf == NBUF) buf = 0, bphase ^= 1;
+      if (NSUB == 1 && ++buf == NBUF) buf = 0, bphase ^= 1;
     }
     if (prof && lane == 0 && p.workspace != nullptr) {
       uint32_t* dst = reinterpret_cast<uint32_t*>(p.workspace) + (static_cast<size_t>(blockIdx.x) * NUM_EPI_WARPS + warp) * 8;
@@ -796,13 +858,13 @@ static int pow2_divisor(int v, int cap) {
   return d;
 }
 
-template <int BLOCK_N, int STAGES, bool LORA, int CG, int EPI>
+template <int BLOCK_N, int STAGES, bool LORA, int CG, int EPI, int NSUB = 1>
 static int launch_gemm_e(const GemmParams& p, int grid, cudaStream_t stream) {
   constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
-  constexpr int smem_bytes = STAGES * (A_TILE_BYTES + (UMMA_N / CG) * BLOCK_K * 2) + 1024 + 1024 + EPI_STAGING_BYTES +
-                             EPI_BIAS_BYTES + (LORA ? 1024 + A_TILE_BYTES + 2 * (BLOCK_N / CG) * BLOCK_K * 2 : 0);   // ring + slack + barriers + staging + bias (+ LoRA T / U tiles)
+  constexpr int smem_bytes = STAGES * (A_TILE_BYTES + NSUB * (UMMA_N / CG) * BLOCK_K * 2) + 1024 + 1024 + EPI_STAGING_BYTES +
+                             epi_bias_bytes(BLOCK_N * NSUB) + (LORA ? 1024 + A_TILE_BYTES + 2 * (BLOCK_N / CG) * BLOCK_K * 2 : 0);   // ring + slack + barriers + staging + bias (+ LoRA T / U tiles)
   static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
-  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, LORA, CG, EPI>;
+  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, LORA, CG, EPI, NSUB>;
   static bool configured = false;  // per instantiation
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
@@ -920,6 +982,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   const int units = sms / cg;
   const int m_units = (p.n_tiles_m + cg - 1) / cg;
   int block_n = 0;
+  bool dual = false;
   if (lora) {
     block_n = 160;
   } else {
@@ -938,8 +1001,20 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     if (block_n == 0) block_n = (a->n > 160) ? 256 : (a->n > 128 ? 160 : 128);
     static const int force_bn = env_int("IDB_GEMM_BN", 0);   // profiling only
     if ((force_bn == 128 || force_bn == 160 || force_bn == 256) && a->n % force_bn == 0) block_n = force_bn;
+    // dual-N (2 x 160 columns per tile, two accumulators sharing every A tile): fewer operand bytes per MAC for the
+    // big-K layers, as long as the halved tile count still fills the machine
+    static const int force_dual = env_int("IDB_GEMM_DUAL", -1);   // profiling only: 0 = never, 1 = whenever legal
+    const bool dual_ok = cg == 2 && !geglu && a->n % 320 == 0 && force_bn == 0;
+    if (dual_ok && force_dual != 0) {
+      const long long tiles = static_cast<long long>(m_units) * (a->n / 320);
+      const double cost = static_cast<double>((tiles + units - 1) / units) * (320 + 24) * (128.0 + 160.0) / 320.0;
+      const double feed = (128.0 + block_n / 2.0) / block_n;
+      const long long tiles1 = static_cast<long long>(m_units) * ((a->n + block_n - 1) / block_n);
+      const double cost1 = static_cast<double>((tiles1 + units - 1) / units) * (block_n + 24) * feed;
+      if (force_dual == 1 || (p.nkb0 + p.nkb1 >= 32 && cost < cost1)) dual = true, block_n = 160;
+    }
   }
-  p.n_tiles_n = (a->n + block_n - 1) / block_n;
+  p.n_tiles_n = (a->n + block_n * (dual ? 2 : 1) - 1) / (block_n * (dual ? 2 : 1));
 
   const int nkb = p.nkb0 + p.nkb1;
   int ksp = a->k_splits;
@@ -1073,6 +1148,9 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   else if (cg == 1 && block_n == 256) rc = launch_gemm<256, 3, false, 1>(pk, grid, stream, epi);
   else if (cg == 1 && block_n == 160) rc = launch_gemm<160, 4, false, 1>(pk, grid, stream, epi);
   else if (cg == 1) rc = launch_gemm<128, 4, false, 1>(pk, grid, stream, epi);
+  else if (dual && epi == 1) rc = launch_gemm_e<160, 4, false, 2, 1, 2>(pk, grid, stream);
+  else if (dual && epi == 3) rc = launch_gemm_e<160, 4, false, 2, 3, 2>(pk, grid, stream);
+  else if (dual) rc = launch_gemm_e<160, 4, false, 2, 0, 2>(pk, grid, stream);
   else if (block_n == 256) rc = launch_gemm<256, 4, false, 2>(pk, grid, stream, epi);
   else if (block_n == 160) rc = launch_gemm<160, 6, false, 2>(pk, grid, stream, epi);
   else rc = launch_gemm<128, 6, false, 2>(pk, grid, stream, epi);

@@ -143,7 +143,8 @@ def test_linear_split_k(ops, cuda_dev, M, K, N, splits):
 
 
 # ------------------------------------------------------------------ convolutions
-@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 128), (2, 64, 64, 320, 320), (3, 8, 8, 1280, 1280),
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 128), (2, 64, 64, 320, 320), (3, 8, 8, 1280, 1280), (8, 64, 64, 320, 320),
+                                            (8, 32, 32, 640, 640),
                                             (1, 32, 32, 640, 640), (2, 24, 24, 64, 128), (1, 128, 128, 128, 128),
                                             (1, 12, 20, 64, 64)])
 def test_conv3x3(ops, cuda_dev, B, H, W, Cin, Cout):
