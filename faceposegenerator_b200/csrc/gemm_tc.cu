@@ -1011,7 +1011,10 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
       const double feed = (128.0 + block_n / 2.0) / block_n;
       const long long tiles1 = static_cast<long long>(m_units) * ((a->n + block_n - 1) / block_n);
       const double cost1 = static_cast<double>((tiles1 + units - 1) / units) * (block_n + 24) * feed;
-      if (force_dual == 1 || (p.nkb0 + p.nkb1 >= 32 && cost < cost1)) dual = true, block_n = 160;
+      // tiny-M layers (8x8 latents) run split-K anyway: with dual-N tiles each split streams the weights once per
+      // 256 rows instead of once per 128-column tile
+      const bool splitk_regime = a->k_splits == 0 && a->workspace && tiles * 2 <= units && p.nkb0 + p.nkb1 >= 64;
+      if (force_dual == 1 || (p.nkb0 + p.nkb1 >= 32 && cost < cost1) || splitk_regime) dual = true, block_n = 160;
     }
   }
   p.n_tiles_n = (a->n + block_n * (dual ? 2 : 1) - 1) / (block_n * (dual ? 2 : 1));
