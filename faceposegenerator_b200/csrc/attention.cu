@@ -589,7 +589,8 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
   uint64_t* s_full = kv_empty + AT2_RING;   // [2]
   uint64_t* p_full = s_full + 2;            // [2]
   uint64_t* o_done = p_full + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_free = o_done + 2;            // [2] every softmax warp of the lane has its last S values in registers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
   float* xch_m = reinterpret_cast<float*>(sP + 4 * ATT_TILE + 1024 + 256);   // [parity][x][row][half]
   float* xch_l = xch_m + AT3_XCHG / 4;                                         // [x][row][half] (final row sums)
 
@@ -613,6 +614,7 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
       mbar_init(&s_full[x], 1);
       mbar_init(&p_full[x], 8);
       mbar_init(&o_done[x], 1);
+      mbar_init(&s_free[x], 8);
     }
     mbar_fence_init();
   }
@@ -698,9 +700,14 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
     issue_qk(1, 0);
     for (int j = 0; j < n_tiles; ++j) {
       for (int x = 0; x < 2; ++x) {
-        mbar_wait(&p_full[x], j & 1);  // P_x(j) staged, S_x consumed, O_x rescaled
+        // S_x(j) is in the softmax warps' registers about half-way through their tile: the next Q K^T overlaps the rest
+        if (j + 1 < n_tiles) {
+          mbar_wait(&s_free[x], j & 1);
+          tc_fence_after();
+          issue_qk(x, j + 1);
+        }
+        mbar_wait(&p_full[x], j & 1);  // P_x(j) staged, O_x rescaled
         tc_fence_after();
-        if (j + 1 < n_tiles) issue_qk(x, j + 1);
         issue_pv(x, j);
       }
     }
@@ -778,6 +785,11 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
         uint32_t sv[32];
         IDB_TMEM_LD_X32(tS + half * 32, sv);
         tmem_ld_wait();
+        if (half == 1) {   // last read of S_x(j) by this warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_free[x]);
+        }
         if (kv_valid < 64) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
