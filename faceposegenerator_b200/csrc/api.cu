@@ -2,6 +2,8 @@
 #include <mutex>
 
 #include "../../include/idb.h"
+#include <cstdlib>
+
 #include "idb_host.h"
 
 namespace idb {
@@ -63,6 +65,11 @@ static EncodeTiledFn encode_fn() {
       fn = reinterpret_cast<EncodeTiledFn>(p);
   });
   return fn;
+}
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("IDB_PDL") && atoi(getenv("IDB_PDL")) == 0);
+  return on;
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

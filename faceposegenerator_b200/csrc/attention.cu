@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();   // q / k / v come from the preceding kernels
 
   if (warp == 4) {
     // ================================================================ TMA producer
@@ -327,6 +329,8 @@ __global__ void __launch_bounds__(AT2_THREADS, 1) attention256_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();   // q / k / v come from the preceding kernels
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 8) {
@@ -623,6 +627,8 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();   // q / k / v come from the preceding kernels
   const uint32_t smem_base = smem_u32(smem);
 
   if (warp == 16) {
@@ -916,6 +922,8 @@ __global__ void __launch_bounds__(ATX_THREADS, 2) attention_x_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();   // q / k / v come from the preceding kernels
 
   if (warp == 4) {
     // ================================================================ TMA producer
@@ -1123,7 +1131,7 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
     if (qpc < 1) qpc = 1;
     if (qpc > n_qtiles) qpc = n_qtiles;
     dim3 grid4((n_qtiles + qpc - 1) / qpc, a->heads, a->batch);
-    attention_x_kernel<<<grid4, ATX_THREADS, ATX_SMEM, stream>>>(p, qpc);
+    launch_pdl(attention_x_kernel, dim3(grid4), dim3(ATX_THREADS), ATX_SMEM, stream, p, qpc);
     cudaError_t e4 = cudaGetLastError();
     if (e4 != cudaSuccess) return fail(IDB_E_CUDA, std::string("attention_x launch: ") + cudaGetErrorString(e4));
     return IDB_OK;
@@ -1144,7 +1152,7 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
       configured3 = true;
     }
     dim3 grid3((a->t_q + 2 * ATT_BM - 1) / (2 * ATT_BM), a->heads, a->batch);
-    kern<<<grid3, AT3_THREADS, AT3_SMEM, stream>>>(p);
+    launch_pdl(kern, dim3(grid3), dim3(AT3_THREADS), AT3_SMEM, stream, p);
     cudaError_t e3 = cudaGetLastError();
     if (e3 != cudaSuccess) return fail(IDB_E_CUDA, std::string("attention_rs launch: ") + cudaGetErrorString(e3));
     return IDB_OK;
@@ -1168,13 +1176,13 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
       configured2 = true;
     }
     dim3 grid2((a->t_q + 2 * ATT_BM - 1) / (2 * ATT_BM), a->heads, a->batch);
-    kern<<<grid2, AT2_THREADS, AT2_SMEM, stream>>>(p);
+    launch_pdl(kern, dim3(grid2), dim3(AT2_THREADS), AT2_SMEM, stream, p);
     cudaError_t e2 = cudaGetLastError();
     if (e2 != cudaSuccess) return fail(IDB_E_CUDA, std::string("attention256 launch: ") + cudaGetErrorString(e2));
     return IDB_OK;
   }
   dim3 grid((a->t_q + ATT_BM - 1) / ATT_BM, a->heads, a->batch);
-  attention_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(p);
+  launch_pdl(attention_kernel, dim3(grid), dim3(ATT_THREADS), ATT_SMEM, stream, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("attention launch: ") + cudaGetErrorString(e));
   return IDB_OK;

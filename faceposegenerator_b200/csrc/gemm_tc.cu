@@ -192,6 +192,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();   // the next kernel's CTAs may take over SMs as ours retire (they block in their own pdl_wait)
+  pdl_wait();      // everything above touched only this CTA's smem / TMEM and the kernel parameters
 
   const int m_units = (p.n_tiles_m + CG - 1) / CG;   // M tiles per unit: a pair covers 2 consecutive M blocks
   const int total_tiles = m_units * p.n_tiles_n * p.k_splits;
@@ -798,6 +800,8 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int k_split
                                        long long rowvec_ld, const float* __restrict__ prelu,
                                        const float* __restrict__ residual, float* __restrict__ out_f32,
                                        __nv_bfloat16* __restrict__ out_bf16, int f16) {
+  pdl_trigger();
+  pdl_wait();
   const long long total4 = M * N / 4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -835,6 +839,8 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int k_split
 // row-block numbering matches the tile order of the fused epilogue only for raster-ordered tiles,
 // which is what the host guarantees before using this path (BW * BH multiple of 32 rows per image).
 __global__ void rowblock_stats_kernel(const float* __restrict__ x, long long M, int N, float2* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   const long long rowblock = blockIdx.x;   // grid = (row blocks, ceil(N / 128)), one thread per column
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= N) return;
@@ -877,13 +883,15 @@ static int launch_gemm_e(const GemmParams& p, int grid, cudaStream_t stream) {
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("gemm_tc launch: ") + cudaGetErrorString(e));
   return IDB_OK;
@@ -1163,13 +1171,13 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     const long long total4 = p.M * p.N / 4;
     int blocks = static_cast<int>((total4 + 255) / 256);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;
-    splitk_finalize_kernel<<<blocks, 256, 0, stream>>>(p.workspace, p.k_splits, p.M, p.N, p.Ho * p.Wo, p.bias, p.rowvec,
+    launch_pdl(splitk_finalize_kernel, dim3(blocks), dim3(256), 0, stream, p.workspace, p.k_splits, p.M, p.N, p.Ho * p.Wo, p.bias, p.rowvec,
                                                        p.rowvec_ld, p.prelu, p.residual, p.out_f32, p.out_bf16, (p.flags & IDB_EPI_F16) ? 1 : 0);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("splitk_finalize launch: ") + cudaGetErrorString(e));
     if (p.stats != nullptr) {
       const unsigned nrb = static_cast<unsigned>((p.M + 31) / 32);
-      rowblock_stats_kernel<<<dim3(nrb, (p.N + 127) / 128), 128, 0, stream>>>(p.out_f32, p.M, p.N, p.stats);
+      launch_pdl(rowblock_stats_kernel, dim3(dim3(nrb, (p.N + 127) / 128)), dim3(128), 0, stream, p.out_f32, p.M, p.N, p.stats);
       e = cudaGetLastError();
       if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("rowblock_stats launch: ") + cudaGetErrorString(e));
     }

@@ -29,6 +29,14 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the library is launched with programmaticStreamSerialization: the next kernel's CTAs may be
+// scheduled (and run their prologue: barrier init, TMEM allocation, descriptor prefetch) while this grid drains.
+// pdl_wait() blocks until the preceding grid has completed and its memory is visible; it must precede the first
+// access to anything an earlier kernel produced.  pdl_trigger() lets the dependent grid be scheduled early.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -45,6 +45,8 @@ __device__ __forceinline__ float4 gn_load(const GnParams& p, int b, int pix, int
 // Deterministic: per-thread partial sums go to smem and are combined in a fixed order (no float
 // atomics), so repeated runs / different GPUs give bit-identical statistics.
 __global__ void gn_stats_kernel(const GnParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float gn_sm[];  // [PY][C] sums, then [PY][C] sums of squares
   const int chunk = blockIdx.x, b = blockIdx.y;
   const int cq = threadIdx.x % p.CQ, py = threadIdx.x / p.CQ;
@@ -133,6 +135,8 @@ __global__ void gn_stats_kernel(const GnParams p) {
 // (fixed summation order -> deterministic).  grid = (groups, batch), 256 threads per (image, group).
 __global__ void gn_finalize_kernel(const float2* __restrict__ s0, int c0, const float2* __restrict__ s1, int c1,
                                    int rb_per_image, int cpg, int hw, float eps, float* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   const int g = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = gridDim.x;
   __shared__ double sh_s[8], sh_ss[8];
@@ -187,6 +191,8 @@ __device__ __forceinline__ void gn_emit(const GnParams& p, int b, int pix, int c
 }
 
 __global__ void gn_apply_kernel(const GnParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float g_mean[GN_MAX_GROUPS], g_rstd[GN_MAX_GROUPS];
   const int chunk = blockIdx.x, b = blockIdx.y;
   if (threadIdx.x < p.groups) {
@@ -225,6 +231,8 @@ template <int MAXQ>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, long long rows, int C,
                                  float eps) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -272,6 +280,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 
 // ---------------------------------------------------------------------------------------- row softmax (VAE attention)
 __global__ void softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int cols, float scale) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const float* sr = s + row * cols;
@@ -309,6 +319,8 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* 
 
 // ---------------------------------------------------------------------------------------- time embedding
 __global__ void sinusoid_kernel(const float* __restrict__ t, float* __restrict__ out, int batch, int dim) {
+  pdl_trigger();
+  pdl_wait();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= batch * half) return;
@@ -323,6 +335,8 @@ __global__ void sinusoid_kernel(const float* __restrict__ t, float* __restrict__
 __global__ void skinny_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                      const float* __restrict__ bias, float* __restrict__ y, int batch, int K, int N,
                                      int silu_out) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
@@ -360,6 +374,8 @@ constexpr int CIN_TILE_W = 32;
 __global__ void conv_small_cin_kernel(const float* __restrict__ x, int x_nchw, const float* __restrict__ w,
                                       const float* __restrict__ bias, float* __restrict__ out_f32,
                                       __nv_bfloat16* __restrict__ out_bf16, int B, int H, int W, int Cout) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float4 patch[3][CIN_TILE_W + 2];
   const int tiles_x = (W + CIN_TILE_W - 1) / CIN_TILE_W;
   const int tx = blockIdx.x % tiles_x;
@@ -407,6 +423,8 @@ template <int COUT>
 __global__ void conv_small_cout_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                        const float* __restrict__ bias, float* __restrict__ out, int postprocess, int B,
                                        int H, int W, int Cin) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sw[];  // [COUT][9][Cin]
   for (int i = threadIdx.x * 4; i < COUT * 9 * Cin; i += blockDim.x * 4)
     *reinterpret_cast<float4*>(sw + i) = *reinterpret_cast<const float4*>(w + i);
@@ -459,6 +477,8 @@ __global__ void conv_small_cout_kernel(const __nv_bfloat16* __restrict__ x, cons
 
 __global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int H, int W,
                                   int C) {
+  pdl_trigger();
+  pdl_wait();
   const int cq_n = C / 4;
   const long long total = static_cast<long long>(B) * 2 * H * 2 * W * cq_n;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -475,6 +495,8 @@ __global__ void upsample2x_kernel(const float* __restrict__ x, __nv_bfloat16* __
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n4) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
@@ -485,6 +507,8 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 __global__ void vae_latent_prep_kernel(const float* __restrict__ z, const float* __restrict__ w,
                                        const float* __restrict__ bias, float inv_scaling, float* __restrict__ out, int B,
                                        int hw) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(B) * hw) return;
   const int b = static_cast<int>(i / hw), pix = static_cast<int>(i % hw);
@@ -507,6 +531,8 @@ __global__ void cfg_ddpm_step_kernel(const float* __restrict__ eps2, const float
                                      const float* __restrict__ noise, const float* __restrict__ coef, float gs,
                                      int use_cfg, int vpred, float* __restrict__ x_prev, float* __restrict__ x0_out,
                                      long long n) {
+  pdl_trigger();
+  pdl_wait();
   const float sa = coef[0], sb = coef[1], c0 = coef[2], ct = coef[3], sigma = coef[4];
   const float inv_sa = 1.0f / sa;
   const long long n4 = n >> 2;
@@ -542,6 +568,8 @@ __global__ void cfg_ddpm_step_kernel(const float* __restrict__ eps2, const float
 __global__ void channel_affine_kernel(const float* __restrict__ x, const float* __restrict__ scale,
                                       const float* __restrict__ shift, __nv_bfloat16* __restrict__ out, int f16, int B,
                                       int H, int W, int C, int stride) {
+  pdl_trigger();
+  pdl_wait();
   const int Ho = H / stride, Wo = W / stride, CQ = C / 4;
   const long long total = static_cast<long long>(B) * Ho * Wo * CQ;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -566,6 +594,8 @@ __global__ void channel_affine_kernel(const float* __restrict__ x, const float* 
 // ((v * 255) / 255 - 0.5) / 0.5, written as the bf16 NHWC stem operand with C_pad channels (3 real, rest 0).
 __global__ void crop_resize_norm_kernel(const float* __restrict__ img, const int* __restrict__ bbox, __nv_bfloat16* __restrict__ out,
                                         int f16, int n, int H, int W, int S, int c_pad) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = static_cast<long long>(n) * S * S;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -646,16 +676,16 @@ extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
   dim3 grid(p.nchunks, a->batch);
   const bool have_stats = a->x0_stats != nullptr && (a->x1 == nullptr || a->x1_stats != nullptr) && a->hw % 32 == 0;
   if (have_stats) {   // statistics already produced by the GEMM epilogues of the sources
-    gn_finalize_kernel<<<dim3(a->groups, a->batch), 256, 0, stream>>>(
+    launch_pdl(gn_finalize_kernel, dim3(dim3(a->groups, a->batch)), dim3(256), 0, stream, 
         reinterpret_cast<const float2*>(a->x0_stats), p.c0, reinterpret_cast<const float2*>(a->x1_stats), p.c1,
         a->hw / 32, p.cpg, a->hw, a->eps, p.stats);
     IDB_CHECK_LAUNCH("gn_finalize");
   } else {
     const size_t stats_smem = static_cast<size_t>(2) * p.PY * C * sizeof(float);
-    gn_stats_kernel<<<grid, threads, stats_smem, stream>>>(p);
+    launch_pdl(gn_stats_kernel, dim3(grid), dim3(threads), stats_smem, stream, p);
     IDB_CHECK_LAUNCH("gn_stats");
   }
-  gn_apply_kernel<<<grid, threads, 0, stream>>>(p);
+  launch_pdl(gn_apply_kernel, dim3(grid), dim3(threads), 0, stream, p);
   IDB_CHECK_LAUNCH("gn_apply");
   return IDB_OK;
 }
@@ -670,10 +700,10 @@ extern "C" int idb_layernorm(const float* x, const float* gamma, const float* be
   const int grid = static_cast<int>((rows + warps - 1) / warps);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out_bf16);
   const int quads_per_lane = (c / 4 + 31) / 32;  // registers (and therefore occupancy) scale with this
-  if (quads_per_lane <= 3) layernorm_kernel<3><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, o, rows, c, eps);
-  else if (quads_per_lane <= 5) layernorm_kernel<5><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, o, rows, c, eps);
-  else if (quads_per_lane <= 10) layernorm_kernel<10><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, o, rows, c, eps);
-  else layernorm_kernel<16><<<grid, warps * 32, 0, stream>>>(x, gamma, beta, o, rows, c, eps);
+  if (quads_per_lane <= 3) launch_pdl(layernorm_kernel<3>, dim3(grid), dim3(warps * 32), 0, stream, x, gamma, beta, o, rows, c, eps);
+  else if (quads_per_lane <= 5) launch_pdl(layernorm_kernel<5>, dim3(grid), dim3(warps * 32), 0, stream, x, gamma, beta, o, rows, c, eps);
+  else if (quads_per_lane <= 10) launch_pdl(layernorm_kernel<10>, dim3(grid), dim3(warps * 32), 0, stream, x, gamma, beta, o, rows, c, eps);
+  else launch_pdl(layernorm_kernel<16>, dim3(grid), dim3(warps * 32), 0, stream, x, gamma, beta, o, rows, c, eps);
   IDB_CHECK_LAUNCH("layernorm");
   return IDB_OK;
 }
@@ -682,7 +712,7 @@ extern "C" int idb_softmax_rows(const float* s, void* p_bf16, int64_t rows, int3
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = require_sm100()) return rc;
   if (!s || !p_bf16 || cols % 4 || rows <= 0) return fail(IDB_E_BADARG, "idb_softmax_rows: bad arguments");
-  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, stream>>>(s, static_cast<__nv_bfloat16*>(p_bf16), cols, scale);
+  launch_pdl(softmax_rows_kernel, dim3(static_cast<unsigned>(rows)), dim3(256), 0, stream, s, static_cast<__nv_bfloat16*>(p_bf16), cols, scale);
   IDB_CHECK_LAUNCH("softmax_rows");
   return IDB_OK;
 }
@@ -696,16 +726,16 @@ extern "C" int idb_time_embed(const idb_time_embed_args* a, void* stream_) {
   float* h1 = sin_buf + static_cast<long long>(a->batch) * a->dim_sin;
   float* se = h1 + static_cast<long long>(a->batch) * a->dim_emb;
   const int half_total = a->batch * a->dim_sin / 2;
-  sinusoid_kernel<<<(half_total + 127) / 128, 128, 0, stream>>>(a->timesteps, sin_buf, a->batch, a->dim_sin);
+  launch_pdl(sinusoid_kernel, dim3((half_total + 127) / 128), dim3(128), 0, stream, a->timesteps, sin_buf, a->batch, a->dim_sin);
   IDB_CHECK_LAUNCH("sinusoid");
   const int wpb = 8;
-  skinny_linear_kernel<<<(a->dim_emb + wpb - 1) / wpb, wpb * 32, 0, stream>>>(sin_buf, a->w1, a->b1, h1, a->batch,
+  launch_pdl(skinny_linear_kernel, dim3((a->dim_emb + wpb - 1) / wpb), dim3(wpb * 32), 0, stream, sin_buf, a->w1, a->b1, h1, a->batch,
                                                                               a->dim_sin, a->dim_emb, 1);
   IDB_CHECK_LAUNCH("time linear_1");
-  skinny_linear_kernel<<<(a->dim_emb + wpb - 1) / wpb, wpb * 32, 0, stream>>>(h1, a->w2, a->b2, se, a->batch, a->dim_emb,
+  launch_pdl(skinny_linear_kernel, dim3((a->dim_emb + wpb - 1) / wpb), dim3(wpb * 32), 0, stream, h1, a->w2, a->b2, se, a->batch, a->dim_emb,
                                                                               a->dim_emb, 1);
   IDB_CHECK_LAUNCH("time linear_2");
-  skinny_linear_kernel<<<(a->n_all + wpb - 1) / wpb, wpb * 32, 0, stream>>>(se, a->w_all, a->b_all, a->proj_out, a->batch,
+  launch_pdl(skinny_linear_kernel, dim3((a->n_all + wpb - 1) / wpb), dim3(wpb * 32), 0, stream, se, a->w_all, a->b_all, a->proj_out, a->batch,
                                                                             a->dim_emb, a->n_all, 0);
   IDB_CHECK_LAUNCH("time_emb_proj");
   return IDB_OK;
@@ -720,7 +750,7 @@ extern "C" int idb_conv3x3_small_cin(const float* x, int32_t x_nchw, const float
   if (cin != 4 || cout > 1024) return fail(IDB_E_UNSUPPORTED, "idb_conv3x3_small_cin: Cin must be 4, Cout <= 1024");
   const long long blocks = static_cast<long long>(batch) * h * ((wd + CIN_TILE_W - 1) / CIN_TILE_W);
   const int threads = (cout + 31) / 32 * 32;
-  conv_small_cin_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
+  launch_pdl(conv_small_cin_kernel, dim3(static_cast<unsigned>(blocks)), dim3(threads), 0, stream, 
       x, x_nchw, w, bias, out_f32, static_cast<__nv_bfloat16*>(out_bf16), batch, h, wd, cout);
   IDB_CHECK_LAUNCH("conv_small_cin");
   return IDB_OK;
@@ -740,9 +770,9 @@ extern "C" int idb_conv3x3_small_cout(const void* x_bf16, const float* w, const 
   const unsigned grid = static_cast<unsigned>((npix + wpb * CSC_PPW - 1) / (wpb * CSC_PPW));
   const __nv_bfloat16* xb = static_cast<const __nv_bfloat16*>(x_bf16);
   if (cout == 4)
-    conv_small_cout_kernel<4><<<grid, wpb * 32, smem, stream>>>(xb, w, bias, out, postprocess, batch, h, wd, cin);
+    launch_pdl(conv_small_cout_kernel<4>, dim3(grid), dim3(wpb * 32), smem, stream, xb, w, bias, out, postprocess, batch, h, wd, cin);
   else
-    conv_small_cout_kernel<3><<<grid, wpb * 32, smem, stream>>>(xb, w, bias, out, postprocess, batch, h, wd, cin);
+    launch_pdl(conv_small_cout_kernel<3>, dim3(grid), dim3(wpb * 32), smem, stream, xb, w, bias, out, postprocess, batch, h, wd, cin);
   IDB_CHECK_LAUNCH("conv_small_cout");
   return IDB_OK;
 }
@@ -753,7 +783,7 @@ extern "C" int idb_upsample2x(const float* x, void* out_bf16, int32_t batch, int
   if (int rc = require_sm100()) return rc;
   if (!x || !out_bf16 || c % 4) return fail(IDB_E_BADARG, "idb_upsample2x: bad arguments");
   const long long total = static_cast<long long>(batch) * 4 * h * wd * (c / 4);
-  upsample2x_kernel<<<grid_for(total, 256, num_sms() * 16), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(out_bf16),
+  launch_pdl(upsample2x_kernel, dim3(grid_for(total, 256, num_sms() * 16)), dim3(256), 0, stream, x, static_cast<__nv_bfloat16*>(out_bf16),
                                                                                batch, h, wd, c);
   IDB_CHECK_LAUNCH("upsample2x");
   return IDB_OK;
@@ -763,7 +793,7 @@ extern "C" int idb_cast_bf16(const float* x, void* out_bf16, int64_t n, void* st
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (int rc = require_sm100()) return rc;
   if (!x || !out_bf16 || n % 4) return fail(IDB_E_BADARG, "idb_cast_bf16: bad arguments");
-  cast_bf16_kernel<<<grid_for(n / 4, 256, num_sms() * 16), 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(out_bf16), n / 4);
+  launch_pdl(cast_bf16_kernel, dim3(grid_for(n / 4, 256, num_sms() * 16)), dim3(256), 0, stream, x, static_cast<__nv_bfloat16*>(out_bf16), n / 4);
   IDB_CHECK_LAUNCH("cast_bf16");
   return IDB_OK;
 }
@@ -774,7 +804,7 @@ extern "C" int idb_vae_latent_prep(const float* z_nchw, const float* w, const fl
   if (int rc = require_sm100()) return rc;
   if (!z_nchw || !w || !bias || !out_nhwc) return fail(IDB_E_BADARG, "idb_vae_latent_prep: null pointer");
   const long long total = static_cast<long long>(batch) * hw;
-  vae_latent_prep_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, stream>>>(z_nchw, w, bias, inv_scaling,
+  launch_pdl(vae_latent_prep_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, z_nchw, w, bias, inv_scaling,
                                                                                          out_nhwc, batch, hw);
   IDB_CHECK_LAUNCH("vae_latent_prep");
   return IDB_OK;
@@ -787,7 +817,7 @@ extern "C" int idb_cfg_ddpm_step(const float* eps2, const float* x, const float*
   if (int rc = require_sm100()) return rc;
   if (!eps2 || !x || !coef || !x_prev) return fail(IDB_E_BADARG, "idb_cfg_ddpm_step: null pointer");
   if (n_per_branch <= 0 || n_per_branch % 4) return fail(IDB_E_BADARG, "idb_cfg_ddpm_step: n must be a positive multiple of 4");
-  cfg_ddpm_step_kernel<<<grid_for(n_per_branch / 4, 256, num_sms() * 8), 256, 0, stream>>>(
+  launch_pdl(cfg_ddpm_step_kernel, dim3(grid_for(n_per_branch / 4, 256, num_sms() * 8)), dim3(256), 0, stream, 
       eps2, x, noise, coef, guidance_scale, use_cfg, v_prediction, x_prev, x0_out, n_per_branch);
   IDB_CHECK_LAUNCH("cfg_ddpm_step");
   return IDB_OK;
@@ -800,7 +830,7 @@ extern "C" int idb_channel_affine(const float* x, const float* scale, const floa
   if (!x || !out_bf16 || c % 4 || stride < 1 || h % stride || wd % stride)
     return fail(IDB_E_BADARG, "idb_channel_affine: bad arguments (C % 4 == 0, H and W divisible by stride)");
   const long long total = static_cast<long long>(batch) * (h / stride) * (wd / stride) * (c / 4);
-  channel_affine_kernel<<<grid_for(total, 256, num_sms() * 16), 256, 0, stream>>>(
+  launch_pdl(channel_affine_kernel, dim3(grid_for(total, 256, num_sms() * 16)), dim3(256), 0, stream, 
       x, scale, shift, static_cast<__nv_bfloat16*>(out_bf16), out_f16, batch, h, wd, c, stride);
   IDB_CHECK_LAUNCH("channel_affine");
   return IDB_OK;
@@ -813,7 +843,7 @@ extern "C" int idb_crop_resize_norm(const float* img_nhwc, const int32_t* bbox_x
   if (!img_nhwc || !bbox_xyxy || !out_bf16 || n <= 0 || size <= 0 || c_pad < 3)
     return fail(IDB_E_BADARG, "idb_crop_resize_norm: bad arguments");
   const long long total = static_cast<long long>(n) * size * size;
-  crop_resize_norm_kernel<<<grid_for(total, 128, num_sms() * 8), 128, 0, stream>>>(
+  launch_pdl(crop_resize_norm_kernel, dim3(grid_for(total, 128, num_sms() * 8)), dim3(128), 0, stream, 
       img_nhwc, bbox_xyxy, static_cast<__nv_bfloat16*>(out_bf16), out_f16, n, h, wd, size, c_pad);
   IDB_CHECK_LAUNCH("crop_resize_norm");
   return IDB_OK;

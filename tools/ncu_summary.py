@@ -19,10 +19,12 @@ want = {
     "dram_write": "dram__bytes_write.sum",
     "dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "regs": "launch__registers_per_thread",
+    "dram_rate": "dram__bytes.sum.per_second",
     "sm_pct": "sm__throughput.avg.pct_of_peak_sustained_elapsed",
 }
 scale = {"nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "ns": 1e-3, "us": 1.0, "ms": 1e3,
-         "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+         "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9,
+         "byte/s": 1.0, "Kbyte/s": 1e3, "Mbyte/s": 1e6, "Gbyte/s": 1e9, "Tbyte/s": 1e12}
 
 
 def val(r, key):
@@ -46,6 +48,8 @@ with open(out, "w", newline="") as f:
         k = r[ix["Kernel Name"]][:60]
         d = val(r, "dur_us")
         rd, wr = val(r, "dram_read"), val(r, "dram_write")
+        if rd != rd:   # sections without the split counters: total bytes = rate x duration
+            rd, wr = val(r, "dram_rate") * d * 1e-6, 0.0
         w.writerow([r[ix["ID"]], k, r[ix["Grid Size"]], f"{d:.1f}", f"{val(r, 'tensor_pct'):.1f}", f"{val(r, 'tensor_pct_elapsed'):.1f}",
                     f"{rd / 1e6:.2f}", f"{wr / 1e6:.2f}", f"{(rd + wr) / d / 1e3:.0f}" if d > 0 else "", f"{val(r, 'dram_pct'):.1f}",
                     f"{val(r, 'sm_pct'):.1f}", f"{val(r, 'regs'):.0f}"])
