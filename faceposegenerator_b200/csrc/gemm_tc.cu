@@ -1021,7 +1021,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
       const double cost1 = static_cast<double>((tiles1 + units - 1) / units) * (block_n + 24) * feed;
       // tiny-M layers (8x8 latents) run split-K anyway: with dual-N tiles each split streams the weights once per
       // 256 rows instead of once per 128-column tile
-      const bool splitk_regime = a->k_splits == 0 && a->workspace && tiles * 2 <= units && p.nkb0 + p.nkb1 >= 64;
+      const bool splitk_regime = a->k_splits == 0 && a->workspace && tiles1 * 2 <= units && p.nkb0 + p.nkb1 >= 64;   // (split anyway)
       if (force_dual == 1 || (p.nkb0 + p.nkb1 >= 32 && cost < cost1) || splitk_regime) dual = true, block_n = 160;
     }
   }
