@@ -99,6 +99,7 @@ EXPORTS = {
                                      c_int32, c_void_p]),
     "idb_crop_resize_norm": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32,
                                        c_void_p]),
+    "idb_latent_operand": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "idb_cfg_ddpm_step": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int32, c_int32,
                                     c_void_p, c_void_p, c_int64, c_void_p]),
 }

@@ -526,6 +526,32 @@ __global__ void vae_latent_prep_kernel(const float* __restrict__ z, const float*
   *reinterpret_cast<float4*>(out + i * 4) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
+// conv_in operand: latents fp32 NCHW [B,4,H,W] -> bf16 NHWC [B,H,W,64]: channels 0-3 = hi(x), 4-7 = lo(x) = bf16(x - hi),
+// 8-11 = hi(x), rest zero.  Against weights packed [w_hi | w_hi | w_lo] the tensor-core conv computes
+// x_hi w_hi + x_lo w_hi + x_hi w_lo, i.e. the fp32 product to ~2^-17 (the 4-channel conv stays at full precision).
+__global__ void latent_operand_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int hw) {
+  pdl_trigger();
+  pdl_wait();
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;   // (pixel, 16-byte chunk of the 128-byte row)
+  if (i >= static_cast<long long>(B) * hw * 8) return;
+  const int chunk = static_cast<int>(i & 7);
+  const long long pixi = i >> 3;
+  uint4 w = make_uint4(0u, 0u, 0u, 0u);
+  if (chunk < 2) {
+    const int b = static_cast<int>(pixi / hw), pix = static_cast<int>(pixi % hw);
+    float v[4], hi[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      v[c] = x[(static_cast<long long>(b) * 4 + c) * hw + pix];
+      hi[c] = __bfloat162float(__float2bfloat16(v[c]));
+    }
+    if (chunk == 0) w = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]),
+                                   pack_bf16x2(v[0] - hi[0], v[1] - hi[1]), pack_bf16x2(v[2] - hi[2], v[3] - hi[3]));
+    else w = make_uint4(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]), 0u, 0u);
+  }
+  *reinterpret_cast<uint4*>(out + pixi * 64 + chunk * 8) = w;
+}
+
 // ---------------------------------------------------------------------------------------- CFG + DDPM step
 __global__ void cfg_ddpm_step_kernel(const float* __restrict__ eps2, const float* __restrict__ x,
                                      const float* __restrict__ noise, const float* __restrict__ coef, float gs,
@@ -807,6 +833,17 @@ extern "C" int idb_vae_latent_prep(const float* z_nchw, const float* w, const fl
   launch_pdl(vae_latent_prep_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, z_nchw, w, bias, inv_scaling,
                                                                                          out_nhwc, batch, hw);
   IDB_CHECK_LAUNCH("vae_latent_prep");
+  return IDB_OK;
+}
+
+extern "C" int idb_latent_operand(const float* x_nchw, void* out_bf16_nhwc64, int32_t batch, int32_t hw, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (int rc = require_sm100()) return rc;
+  if (!x_nchw || !out_bf16_nhwc64 || batch <= 0 || hw <= 0) return fail(IDB_E_BADARG, "idb_latent_operand: bad arguments");
+  const long long total = static_cast<long long>(batch) * hw * 8;
+  launch_pdl(latent_operand_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0, stream, x_nchw,
+             static_cast<__nv_bfloat16*>(out_bf16_nhwc64), batch, hw);
+  IDB_CHECK_LAUNCH("latent_operand");
   return IDB_OK;
 }
 

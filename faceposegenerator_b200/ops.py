@@ -240,6 +240,19 @@ def vae_latent_prep(z, w, bias, inv_scaling: float, out=None):
     return out
 
 
+def latent_operand(x, out=None):
+    """x fp32 NCHW [B,4,H,W] -> bf16 NHWC [B,H,W,64] (hi | lo | hi split of the 4 channels) for the tensor-core conv_in."""
+    _chk(x, f32, "x")
+    B, c, H, W_ = x.shape
+    if c != 4:
+        raise ValueError("latent_operand expects 4 channels")
+    if out is None:
+        out = torch.empty((B, H, W_, 64), dtype=bf16, device=x.device)
+    _chk(out, bf16, "out")
+    _lib.call("idb_latent_operand", x.data_ptr(), out.data_ptr(), B, H * W_, _lib.stream_ptr())
+    return out
+
+
 def cfg_ddpm_step(eps2, x, noise, coef, *, guidance_scale: float, use_cfg: bool, v_prediction: bool = False,
                   x_prev=None, x0_out=None):
     """eps2 fp32 [2n or n, ...], x fp32 [n, ...], coef fp32[5] on device."""

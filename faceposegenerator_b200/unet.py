@@ -18,7 +18,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from .packing import interleave_geglu, pack_conv_weight, pack_edge_conv_weight, pack_lora
+from .packing import interleave_geglu, pack_conv_weight, pack_lora
 from .weights import UNET_CONFIG, random_state_dict, unet_manifest
 
 bf16, f32 = torch.bfloat16, torch.float32
@@ -113,7 +113,13 @@ class UNet2DConditionModel:
         ch = tuple(cfg["block_out_channels"])
         n = len(ch)
         temb_rows, temb_bias = [], []
-        self.w_conv_in = pack_edge_conv_weight(sd["conv_in.weight"], self.device)
+        # conv_in (4 -> 320) on the tensor-core kernel: the 4 input channels ride in one 64-channel K block as
+        # [x_hi | x_lo | x_hi] against [w_hi | w_hi | w_lo] (ops.latent_operand), i.e. at fp32-product precision
+        wi = sd["conv_in.weight"].float().permute(0, 2, 3, 1)                     # [320, 3, 3, 4]
+        w_hi = wi.to(bf16).float()
+        wp = torch.zeros(wi.shape[0], 3, 3, 64)
+        wp[..., 0:4], wp[..., 4:8], wp[..., 8:12] = w_hi, w_hi, wi - w_hi
+        self.w_conv_in = wp.reshape(wi.shape[0], -1).to(device=self.device, dtype=bf16).contiguous()
         self.b_conv_in = self._dev(sd["conv_in.bias"])
         self.t_w1, self.t_b1 = self._dev(sd["time_embedding.linear_1.weight"]), self._dev(sd["time_embedding.linear_1.bias"])
         self.t_w2, self.t_b2 = self._dev(sd["time_embedding.linear_2.weight"]), self._dev(sd["time_embedding.linear_2.bias"])
@@ -299,8 +305,9 @@ class UNet2DConditionModel:
             if taps is not None:
                 taps[name] = v[0].permute(0, 3, 1, 2).float().clone()
 
-        h0, _ = ops.conv3x3_small_cin(x, self.w_conv_in, self.b_conv_in, nchw=True)
-        h = (h0, None)   # conv_in is a SIMT kernel: its GroupNorm consumer computes the statistics itself
+        h0, _, h0_st = self._gemm(ops.latent_operand(x), self.w_conv_in, mode=ops.A_3X3, bias=self.b_conv_in, want_f32=True,
+                                  want_stats=True)
+        h = (h0.view(B, H, W, -1), h0_st)
         tap("conv_in", h)
         skips = [h]
         for i, blk in enumerate(self.down):

@@ -220,6 +220,10 @@ int idb_vae_latent_prep(const float* z_nchw, const float* w, const float* bias, 
  * coef: DEVICE fp32[5] = {sqrt_acp, sqrt_1m_acp, c_x0, c_xt, sigma} (a row of the per-step
  * table the scheduler uploads at set_timesteps -- no host sync inside the loop).
  * ---------------------------------------------------------------------------------------- */
+/* UNet conv_in operand: fp32 NCHW latents [B,4,H,W] -> bf16 NHWC [B,H,W,64] = [hi(x) | lo(x) | hi(x) | 0...]; with conv_in
+ * weights packed [w_hi | w_hi | w_lo] per tap, idb_gemm_conv computes the 4-channel 3x3 conv at fp32-product precision. */
+int idb_latent_operand(const float* x_nchw, void* out_bf16_nhwc64, int32_t batch, int32_t hw, void* stream);
+
 int idb_cfg_ddpm_step(const float* eps2, const float* x, const float* noise, const float* coef,
                       float guidance_scale, int32_t use_cfg, int32_t v_prediction,
                       float* x_prev, float* x0_out /* or NULL */, int64_t n_per_branch, void* stream);
