@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libidb_b200.so")
 A_1X1, A_3X3, A_3X3_S2 = 0, 1, 2
 EPI_GEGLU = 1
 EPI_F16 = 2
+EPI_GELU = 4
 
 c_void_p, c_int32, c_int64, c_float, c_size_t = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 
@@ -44,7 +45,7 @@ class AttentionArgs(C.Structure):
         ("v", c_void_p), ("ld_v", c_int64), ("col0_v", c_int32),
         ("out", c_void_p), ("ld_out", c_int64),
         ("batch", c_int32), ("heads", c_int32), ("t_q", c_int32), ("t_kv", c_int32),
-        ("scale", c_float),
+        ("scale", c_float), ("causal", c_int32),
     ]
 
 

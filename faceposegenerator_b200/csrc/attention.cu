@@ -35,6 +35,7 @@ struct AttnParams {
   long long ld_out;
   int B, heads, Tq, Tkv, n_kv_tiles;
   float scale_log2;
+  int causal;
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_constant__ AttnParams p) {
@@ -995,11 +996,13 @@ __global__ void __launch_bounds__(ATX_THREADS, 2) attention_x_kernel(const __gri
       if (nkv > 64) IDB_TMEM_LD_X32(tS + 64, s2);
       tmem_ld_wait();
       float m = -INFINITY;
+      // keys this query row may see: [0, kmax) -- the context length, or the row's own position under a causal mask
+      const int kmax = p.causal ? min(p.Tkv, (qt0 + i) * ATT_BM + r + 1) : p.Tkv;
 #pragma unroll
       for (int k = 0; k < 32; ++k) {
-        if (k >= p.Tkv) s0[k] = 0xff800000u;
-        if (32 + k >= p.Tkv) s1[k] = 0xff800000u;
-        if (nkv <= 64 || 64 + k >= p.Tkv) s2[k] = 0xff800000u;
+        if (k >= kmax) s0[k] = 0xff800000u;
+        if (32 + k >= kmax) s1[k] = 0xff800000u;
+        if (nkv <= 64 || 64 + k >= kmax) s2[k] = 0xff800000u;
         m = fmaxf(m, fmaxf(__uint_as_float(s0[k]), fmaxf(__uint_as_float(s1[k]), __uint_as_float(s2[k]))));
       }
       const float neg_m = -m * c;
@@ -1109,6 +1112,8 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
   p.Tkv = a->t_kv;
   p.n_kv_tiles = (a->t_kv + ATT_BN - 1) / ATT_BN;
   p.scale_log2 = a->scale * 1.4426950408889634f;
+  p.causal = a->causal ? 1 : 0;
+  if (p.causal && a->t_kv > 96) return fail(IDB_E_UNSUPPORTED, "idb_attention: causal masking is implemented for t_kv <= 96 (short-context kernel)");
 
   static bool configured = false;
   if (!configured) {
@@ -1118,7 +1123,7 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
   }
   static const int force_variant = getenv("IDB_ATTN_VARIANT") ? atoi(getenv("IDB_ATTN_VARIANT")) : 0;
   const bool use256 = force_variant ? (force_variant == 256) : (a->t_q >= 1024 && a->t_kv >= 512);
-  if (a->t_kv <= 96 && force_variant == 0) {   // short context (cross-attention): K/V resident, chunks of query tiles per CTA
+  if (a->t_kv <= 96 && (force_variant == 0 || p.causal)) {   // short context (cross-attention): K/V resident, chunks of query tiles per CTA
     static bool configured4 = false;
     if (!configured4) {
       cudaError_t e4 = cudaFuncSetAttribute(attention_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATX_SMEM);

@@ -654,6 +654,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             acc[4 * j + 3] = acc[4 * j + 3] > 0.f ? acc[4 * j + 3] : acc[4 * j + 3] * sl.w;
           }
         }
+        if (!EPI && (p.flags & IDB_EPI_GELU)) {   // plain erf-GELU on every column (CLIP text MLP)
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) geglu2(acc[j], acc[j + 1], 1.0f, 1.0f, acc[j], acc[j + 1]);
+        }
         int nc = 32, ocol = col;
         if (geglu) {  // chunk = [a(16) | g(16)] -> 16 outputs at column col/2
 #pragma unroll
@@ -944,6 +948,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   if (geglu && a->out_f32) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: GEGLU writes bf16 only");
   if (a->stats_partials && !a->out_f32) return fail(IDB_E_BADARG, "idb_gemm_conv: stats_partials needs the fp32 output");
   if (a->prelu && geglu) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: PReLU with GEGLU");
+  if ((a->flags & IDB_EPI_GELU) && (geglu || a->k_splits > 1)) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: GELU with GEGLU / forced split-K");
   if ((a->flags & IDB_EPI_F16) && lora) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: fp16 operands with fused LoRA");
 
   GemmParams p;
@@ -1012,7 +1017,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     // dual-N (2 x 160 columns per tile, two accumulators sharing every A tile): fewer operand bytes per MAC for the
     // big-K layers, as long as the halved tile count still fills the machine
     static const int force_dual = env_int("IDB_GEMM_DUAL", -1);   // profiling only: 0 = never, 1 = whenever legal
-    const bool dual_ok = cg == 2 && !geglu && a->n % 320 == 0 && force_bn == 0;
+    const bool dual_ok = cg == 2 && !geglu && !(a->flags & IDB_EPI_GELU) && a->n % 320 == 0 && force_bn == 0;
     if (dual_ok && force_dual != 0) {
       const long long tiles = static_cast<long long>(m_units) * (a->n / 320);
       const double cost = static_cast<double>((tiles + units - 1) / units) * (320 + 24) * (128.0 + 160.0) / 320.0;
@@ -1032,7 +1037,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   if (ksp == 0) {  // auto: split K when the tile grid leaves most SMs idle
     ksp = 1;
     const long long tiles = static_cast<long long>(m_units) * p.n_tiles_n;
-    if (!lora && !geglu && a->workspace && tiles * 2 <= units && nkb >= 16) {
+    if (!lora && !geglu && !(a->flags & IDB_EPI_GELU) && a->workspace && tiles * 2 <= units && nkb >= 16) {
       long long want = units / tiles;
       if (want > nkb / 8) want = nkb / 8;
       const size_t per_split = static_cast<size_t>(p.M) * a->n * sizeof(float);
@@ -1148,7 +1153,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   // epilogue specialisation (generic whenever a profiling switch, split-K or both outputs are in play)
   int epi = 0;
   static const int no_spec = env_int("IDB_GEMM_NOSPEC", 0);
-  if (!no_spec && dbg == 0 && p.k_splits == 1 && !(a->out_f32 && a->out_bf16)) {
+  if (!no_spec && dbg == 0 && p.k_splits == 1 && !(a->out_f32 && a->out_bf16) && !(a->flags & IDB_EPI_GELU)) {
     if (a->out_f32) epi = 3;
     else if (geglu) epi = (a->residual || a->rowvec || a->prelu) ? 0 : 2;
     else epi = (a->rowvec || a->stats_partials) ? 0 : 1;

@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import A_1X1, A_3X3, A_3X3_S2, EPI_F16, EPI_GEGLU  # noqa: F401  (re-exported)
+from ._lib import A_1X1, A_3X3, A_3X3_S2, EPI_F16, EPI_GEGLU, EPI_GELU  # noqa: F401  (re-exported)
 
 bf16, f16, f32 = torch.bfloat16, torch.float16, torch.float32
 
@@ -34,7 +34,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
               geglu: bool = False, out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
               want_f32: bool = False, want_bf16: bool = False, k_splits: int = 1,
               workspace: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, want_stats: bool = False,
-              prelu: Optional[torch.Tensor] = None, half: bool = False):
+              prelu: Optional[torch.Tensor] = None, half: bool = False, gelu: bool = False):
     """a0: bf16 [B,H,W,C0] (or [M,K] for a Linear); w: bf16 [N, Ktot].  Returns (out_f32, out_bf16).
     half=True: the 16-bit tensors (a0, a1, w, out_bf16) are IEEE fp16 instead of bf16 (IDB_EPI_F16)."""
     t16 = f16 if half else bf16
@@ -88,7 +88,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
         w=w.data_ptr(), n=N, bias=_lib.ptr(bias), rowvec=_lib.ptr(rowvec), rowvec_ld=rowvec_ld, residual=_lib.ptr(residual),
         lora_down=_lib.ptr(lora_down), lora_up=_lib.ptr(lora_up),
         lora_rank_pad=0 if lora_up is None else 16, lora_seg_n=lora_seg_n,
-        flags=(EPI_GEGLU if geglu else 0) | (EPI_F16 if half else 0), out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
+        flags=(EPI_GEGLU if geglu else 0) | (EPI_F16 if half else 0) | (EPI_GELU if gelu else 0), out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
         k_splits=k_splits, workspace=_lib.ptr(workspace),
         workspace_bytes=0 if workspace is None else workspace.numel() * 4, stats_partials=_lib.ptr(stats),
         prelu=_lib.ptr(prelu))
@@ -102,7 +102,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
 
 
 def attention(q, k, v, out=None, *, batch: int, heads: int, t_q: int, t_kv: int, scale: float,
-              col0_q: int = 0, col0_k: int = 0, col0_v: int = 0):
+              col0_q: int = 0, col0_k: int = 0, col0_v: int = 0, causal: bool = False):
     """q: bf16 [B*Tq, ld_q]; k, v: bf16 [B*Tkv, ld]; head h lives at columns col0 + h*64."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
         _chk(t, bf16, nm)
@@ -111,7 +111,7 @@ def attention(q, k, v, out=None, *, batch: int, heads: int, t_q: int, t_kv: int,
     _chk(out, bf16, "out")
     args = _lib.AttentionArgs(q=q.data_ptr(), ld_q=q.shape[-1], col0_q=col0_q, k=k.data_ptr(), ld_k=k.shape[-1],
                               col0_k=col0_k, v=v.data_ptr(), ld_v=v.shape[-1], col0_v=col0_v, out=out.data_ptr(),
-                              ld_out=out.shape[-1], batch=batch, heads=heads, t_q=t_q, t_kv=t_kv, scale=scale)
+                              ld_out=out.shape[-1], batch=batch, heads=heads, t_q=t_q, t_kv=t_kv, scale=scale, causal=int(causal))
     _lib.call("idb_attention", C.byref(args), _lib.stream_ptr(),
               desc=None if _lib.trace is None else dict(B=batch, heads=heads, Tq=t_q, Tkv=t_kv))
     return out

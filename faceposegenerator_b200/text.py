@@ -1,10 +1,12 @@
-"""Prompt -> [n, 77, 1024] context for the UNet.  PLUMBING, not part of the accelerated path:
-SURVEY.md section 8(f)-1 lists the CLIP-H text encoder as the next row; until it is moved onto
-the sm_100a kernels this module runs the 23-layer OpenCLIP-H text tower (A.0 config) with plain
-torch ops on the GPU, random-initialised deterministically when no snapshot exists offline, and
-tokenises with a hashed word-piece stand-in because the CLIP BPE vocabulary is not available
-without network access.  Results are cached per prompt string (the negative prompt of the
-reference sweep is constant, `inference_ID-Booth.py:81`).
+"""Prompt -> [n, 77, 1024] context for the UNet: the 23-layer OpenCLIP-H text tower
+(A.0 config; `encode_prompt` behind `inference_ID-Booth.py:138`, in-tree twin `train_ID-Booth.py:457-491`) on the
+sm_100a kernels: LayerNorm -> fused q/k/v GEMM -> causal attention (`idb_attention`, short-context kernel) ->
+out_proj GEMM (+residual) -> LayerNorm -> fc1 GEMM with an erf-GELU epilogue -> fc2 GEMM (+residual); fp32 residual
+stream, bf16 operands.  Only the embedding gather is a torch indexing op.  Weights are random-initialised
+deterministically when no snapshot exists offline, and the tokenizer is a hashed word-piece stand-in because the CLIP
+BPE vocabulary is not available without network access.  Results are cached per prompt string (the negative prompt
+of the reference sweep is constant, `inference_ID-Booth.py:81`).  The plain-torch fp32 formulation the parity test
+compares against lives in `oracle/clip_text.py`.
 """
 from __future__ import annotations
 
@@ -13,7 +15,6 @@ import re
 from typing import Dict, List
 
 import torch
-import torch.nn.functional as F
 
 TEXT_CONFIG = dict(hidden=1024, intermediate=4096, heads=16, layers=23, max_pos=77, vocab=49408, eps=1e-5)
 BOS, EOS = 49406, 49407
@@ -55,32 +56,48 @@ def text_manifest(cfg: dict = TEXT_CONFIG):
 class CLIPTextEncoder:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device, dtype=torch.bfloat16, cfg: dict = TEXT_CONFIG):
         self.cfg, self.device, self.dtype = cfg, torch.device(device), dtype
-        self.sd = {k: v.to(device=self.device, dtype=dtype) for k, v in state_dict.items()}
+        if self.device.type != "cuda":
+            raise RuntimeError("CLIPTextEncoder runs on CUDA (sm_100a) only; there is no CPU fallback")
         self.tokenizer = HashTokenizer()
         self._cache: Dict[str, torch.Tensor] = {}
+        bf, f32 = torch.bfloat16, torch.float32
+        dev = self.device
+        g = lambda k, dt: state_dict[k].to(device=dev, dtype=dt).contiguous()
+        self.tok = g("text_model.embeddings.token_embedding.weight", f32)
+        self.pos = g("text_model.embeddings.position_embedding.weight", f32)
+        self.layers = []
+        for i in range(cfg["layers"]):
+            p = f"text_model.encoder.layers.{i}"
+            cat = lambda suf, dt: torch.cat([state_dict[f"{p}.self_attn.{n_}.{suf}"] for n_ in ("q_proj", "k_proj", "v_proj")], 0) \
+                .to(device=dev, dtype=dt).contiguous()
+            self.layers.append(dict(
+                ln1=(g(p + ".layer_norm1.weight", f32), g(p + ".layer_norm1.bias", f32)),
+                w_qkv=cat("weight", bf), b_qkv=cat("bias", f32),
+                w_o=g(p + ".self_attn.out_proj.weight", bf), b_o=g(p + ".self_attn.out_proj.bias", f32),
+                ln2=(g(p + ".layer_norm2.weight", f32), g(p + ".layer_norm2.bias", f32)),
+                w_fc1=g(p + ".mlp.fc1.weight", bf), b_fc1=g(p + ".mlp.fc1.bias", f32),
+                w_fc2=g(p + ".mlp.fc2.weight", bf), b_fc2=g(p + ".mlp.fc2.bias", f32)))
+        self.ln_f = (g("text_model.final_layer_norm.weight", f32), g("text_model.final_layer_norm.bias", f32))
 
     @torch.no_grad()
     def forward_ids(self, ids: torch.Tensor) -> torch.Tensor:
-        sd, cfg = self.sd, self.cfg
+        """ids [n, S<=77] -> bf16 [n, S, hidden] on the hand-written kernels."""
+        from . import ops
+        cfg = self.cfg
         ids = ids.to(self.device)
         n, S = ids.shape
-        x = sd["text_model.embeddings.token_embedding.weight"][ids] + \
-            sd["text_model.embeddings.position_embedding.weight"][:S][None]
-        heads, h = cfg["heads"], cfg["hidden"]
-        for i in range(cfg["layers"]):
-            p = f"text_model.encoder.layers.{i}"
-            r = x
-            y = F.layer_norm(x, (h,), sd[p + ".layer_norm1.weight"], sd[p + ".layer_norm1.bias"], cfg["eps"])
-            q, k, v = (F.linear(y, sd[f"{p}.self_attn.{n_}.weight"], sd[f"{p}.self_attn.{n_}.bias"])
-                       .view(n, S, heads, h // heads).transpose(1, 2) for n_ in ("q_proj", "k_proj", "v_proj"))
-            a = F.scaled_dot_product_attention(q, k, v, is_causal=True).transpose(1, 2).reshape(n, S, h)
-            x = r + F.linear(a, sd[p + ".self_attn.out_proj.weight"], sd[p + ".self_attn.out_proj.bias"])
-            r = x
-            y = F.layer_norm(x, (h,), sd[p + ".layer_norm2.weight"], sd[p + ".layer_norm2.bias"], cfg["eps"])
-            y = F.gelu(F.linear(y, sd[p + ".mlp.fc1.weight"], sd[p + ".mlp.fc1.bias"]))
-            x = r + F.linear(y, sd[p + ".mlp.fc2.weight"], sd[p + ".mlp.fc2.bias"])
-        return F.layer_norm(x, (h,), sd["text_model.final_layer_norm.weight"], sd["text_model.final_layer_norm.bias"],
-                            cfg["eps"])
+        h, heads = cfg["hidden"], cfg["heads"]
+        x = (self.tok[ids] + self.pos[:S][None]).reshape(n * S, h).contiguous()       # fp32 residual stream
+        for L in self.layers:
+            y = ops.layernorm(x, *L["ln1"], eps=cfg["eps"])
+            _, qkv = ops.gemm_conv(y, L["w_qkv"], bias=L["b_qkv"], want_bf16=True)
+            a = ops.attention(qkv, qkv, qkv, batch=n, heads=heads, t_q=S, t_kv=S, scale=(h // heads) ** -0.5,
+                              col0_q=0, col0_k=h, col0_v=2 * h, causal=True)
+            x, _ = ops.gemm_conv(a, L["w_o"], bias=L["b_o"], residual=x, want_f32=True)
+            y = ops.layernorm(x, *L["ln2"], eps=cfg["eps"])
+            _, y = ops.gemm_conv(y, L["w_fc1"], bias=L["b_fc1"], gelu=True, want_bf16=True)
+            x, _ = ops.gemm_conv(y, L["w_fc2"], bias=L["b_fc2"], residual=x, want_f32=True)
+        return ops.layernorm(x, *self.ln_f, eps=cfg["eps"]).view(n, S, h)
 
     def encode(self, prompts: List[str]) -> torch.Tensor:
         missing = [p for p in dict.fromkeys(prompts) if p not in self._cache]

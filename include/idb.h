@@ -63,6 +63,7 @@ int idb_num_sms(void);
 enum { IDB_A_1X1 = 0, IDB_A_3X3 = 1, IDB_A_3X3_S2 = 2 };
 enum {
   IDB_EPI_GEGLU = 1, /* W rows interleaved in 16-blocks [a(16) | g(16)]; out[:, j] = a_j * gelu_erf(g_j); N_out = N/2 */
+  IDB_EPI_GELU = 4,  /* out = gelu_erf(acc + bias) (CLIP text MLP fc1); not combined with GEGLU */
   IDB_EPI_F16 = 2    /* the 16-bit tensors of this call (a0, a1, w, out_bf16) are IEEE fp16 instead of bf16 (the ArcFace IResNet
                         runs under fp16 autocast in the reference, iresnet.py:149); not combined with LoRA */
 };
@@ -132,6 +133,7 @@ typedef struct {
   void* out;     int64_t ld_out;
   int32_t batch, heads, t_q, t_kv;
   float scale;
+  int32_t causal;   /* 1: key j is visible to query i only if j <= i (CLIP text tower); supported for t_kv <= 96 */
 } idb_attention_args;
 int idb_attention(const idb_attention_args* args, void* stream);
 

@@ -136,3 +136,25 @@ def test_pipeline_teacher_forced_and_free_running(world):
     drift = [rel(free[i], ref_l[i + 1]) for i in range(30)]
     print("free-running latent rel-L2: final %.3e max %.3e" % (drift[-1], max(drift)))
     assert drift[-1] < 5e-2
+
+
+def test_clip_text_encoder_vs_torch_fp32(cuda_dev):
+    """the CLIP-H text tower on the sm_100a kernels (causal short-context attention, GELU epilogue)
+    against the plain-torch fp32 formulation on the same random-init weights and token ids."""
+    from faceposegenerator_b200.text import CLIPTextEncoder, text_manifest
+    from faceposegenerator_b200.weights import random_state_dict
+    from oracle.clip_text import clip_text_forward
+    sd = random_state_dict(text_manifest(), 0)
+    enc = CLIPTextEncoder(sd, cuda_dev)
+    ids = enc.tokenizer(["a photo of sks person, smiling, outdoors", "blurry, low quality", "x"])
+    out = enc.forward_ids(ids).float()
+    ref = clip_text_forward({k: v.to(cuda_dev).float() for k, v in sd.items()}, ids.to(cuda_dev))
+    assert out.shape == (3, 77, 1024)
+    e = rel(out, ref)
+    print(f"clip text rel-L2 {e:.3e}")
+    assert e < 1e-2
+    # causal: changing a later token must not change earlier positions
+    ids2 = ids.clone()
+    ids2[0, 5] = (ids2[0, 5] + 1) % 49000
+    out2 = enc.forward_ids(ids2).float()
+    assert rel(out2[0, :5], out[0, :5]) < 1e-6 and rel(out2[0, 5:], out[0, 5:]) > 1e-3
