@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libidb_b200.so")
 
-A_1X1, A_3X3, A_3X3_S2 = 0, 1, 2
+A_1X1, A_3X3, A_3X3_S2, A_3X3_S2_ASYM = 0, 1, 2, 3
 EPI_GEGLU = 1
 EPI_F16 = 2
 EPI_GELU = 4

@@ -235,6 +235,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               const int dy = (tap * 11) >> 5, dx = tap - dy * 3;   // tap / 3 for tap in [0, 9)
               if (p.mode0 == IDB_A_3X3) {
                 c0 = cb, c1 = x0 + dx - 1, c2 = y0 + dy - 1, c3 = b0;
+              } else if (p.mode0 == IDB_A_3X3_S2_ASYM) {  // stride 2, padding on the right / bottom only: input (2*yo + dy, 2*xo + dx)
+                const int px = (dx == 1) ? 1 : 0, py = (dy == 1) ? 1 : 0;
+                const int ox = (dx == 2) ? 1 : 0, oy = (dy == 2) ? 1 : 0;
+                five = true;
+                c0 = px * p.c0 + cb, c1 = x0 + ox, c2 = py, c3 = y0 + oy, c4 = b0;
               } else {  // stride 2: input (2*yo + dy - 1, 2*xo + dx - 1) in the [B, H/2, 2, W/2, 2C] view
                 const int px = (dx == 1) ? 0 : 1, py = (dy == 1) ? 0 : 1;
                 const int ox = (dx == 0) ? -1 : 0, oy = (dy == 0) ? -1 : 0;
@@ -935,8 +940,9 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   if (a->a1 && (a->c1 <= 0 || a->c1 % 64)) return fail(IDB_E_BADARG, "idb_gemm_conv: C1 must be a multiple of 64");
   if (a->n <= 0 || a->n % 32) return fail(IDB_E_BADARG, "idb_gemm_conv: N must be a positive multiple of 32");
   if (a->batch <= 0 || a->height <= 0 || a->width <= 0) return fail(IDB_E_BADARG, "idb_gemm_conv: bad geometry");
-  if (a->a0_mode < IDB_A_1X1 || a->a0_mode > IDB_A_3X3_S2) return fail(IDB_E_BADARG, "idb_gemm_conv: bad a0_mode");
-  if (a->a0_mode == IDB_A_3X3_S2 && ((a->height | a->width) & 1))
+  if (a->a0_mode < IDB_A_1X1 || a->a0_mode > IDB_A_3X3_S2_ASYM) return fail(IDB_E_BADARG, "idb_gemm_conv: bad a0_mode");
+  const bool stride2 = a->a0_mode == IDB_A_3X3_S2 || a->a0_mode == IDB_A_3X3_S2_ASYM;
+  if (stride2 && ((a->height | a->width) & 1))
     return fail(IDB_E_BADARG, "idb_gemm_conv: stride-2 conv needs even H and W");
   if (!a->out_f32 && !a->out_bf16) return fail(IDB_E_BADARG, "idb_gemm_conv: no output");
   const bool lora = a->lora_down != nullptr;
@@ -960,8 +966,8 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   p.cpb0 = a->c0 / 64;
   p.nkb0 = taps0 * p.cpb0;
   p.nkb1 = a->a1 ? a->c1 / 64 : 0;
-  p.Ho = (a->a0_mode == IDB_A_3X3_S2) ? H / 2 : H;
-  p.Wo = (a->a0_mode == IDB_A_3X3_S2) ? W / 2 : W;
+  p.Ho = stride2 ? H / 2 : H;
+  p.Wo = stride2 ? W / 2 : W;
   p.B = B;
   p.M = static_cast<long long>(B) * p.Ho * p.Wo;
   p.N = a->n;
@@ -1077,7 +1083,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   p.stats = reinterpret_cast<float2*>(a->stats_partials);
 
   // ---- tensor maps
-  if (a->a0_mode == IDB_A_3X3_S2) {
+  if (stride2) {
     const uint64_t C = a->c0;
     uint64_t dims[5] = {2 * C, uint64_t(W / 2), 2, uint64_t(H / 2), uint64_t(B)};
     uint64_t strides[4] = {2 * C * 2, uint64_t(W) * C * 2, 2 * uint64_t(W) * C * 2, uint64_t(H) * W * C * 2};

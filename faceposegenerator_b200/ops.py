@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import A_1X1, A_3X3, A_3X3_S2, EPI_F16, EPI_GEGLU, EPI_GELU  # noqa: F401  (re-exported)
+from ._lib import A_1X1, A_3X3, A_3X3_S2, A_3X3_S2_ASYM, EPI_F16, EPI_GEGLU, EPI_GELU  # noqa: F401  (re-exported)
 
 bf16, f16, f32 = torch.bfloat16, torch.float16, torch.float32
 
@@ -44,7 +44,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
     else:
         B, H, W_, C0 = a0.shape
     N = w.shape[0]
-    Ho, Wo = (H // 2, W_ // 2) if mode == A_3X3_S2 else (H, W_)
+    Ho, Wo = (H // 2, W_ // 2) if mode in (A_3X3_S2, A_3X3_S2_ASYM) else (H, W_)
     M = B * Ho * Wo
     taps = 1 if mode == A_1X1 else 9
     c1 = 0

@@ -1,7 +1,7 @@
-"""`AutoencoderKL.decode` (diffusers 0.32.2, SD2.1-base VAE) on the same sm_100a kernels as the
-UNet: `vae.decode(z).sample` / `.config.scaling_factor`
-(`/root/reference/train_ID-Booth.py:410-412,435-437`; pipeline tail behind
-`inference_ID-Booth.py:138`).  NHWC, fp32 residual stream, bf16 GEMM/conv operands.
+"""`AutoencoderKL` (diffusers 0.32.2, SD2.1-base VAE) on the same sm_100a kernels as the UNet:
+`vae.decode(z).sample` / `.config.scaling_factor` (`/root/reference/train_ID-Booth.py:410-412,435-437`; pipeline tail
+behind `inference_ID-Booth.py:138`) and `vae.encode(x).latent_dist.sample()` (`train_ID-Booth.py:1001-1002`).
+NHWC, fp32 residual stream, bf16 GEMM/conv operands.
 
 Mid-block attention (1 head, d = 512, 4096 tokens) is expressed with the tcgen05 GEMM:
 S = Q K^T (fp32), row softmax, O = P V with V^T produced directly by a swapped-operand GEMM
@@ -16,7 +16,7 @@ import torch
 
 from . import ops
 from .packing import pack_conv_weight, pack_edge_conv_weight
-from .weights import VAE_CONFIG, random_state_dict, vae_decoder_manifest
+from .weights import VAE_CONFIG, random_state_dict, vae_decoder_manifest, vae_encoder_manifest
 
 bf16, f32 = torch.bfloat16, torch.float32
 
@@ -27,6 +27,32 @@ class DecoderOutput:
 
     def __getitem__(self, i):
         return (self.sample,)[i]
+
+
+class DiagonalGaussianDistribution:
+    """`latent_dist` of `AutoencoderKL.encode` (diffusers): moments [n, 2*lc, h, w] = (mean | logvar)."""
+
+    def __init__(self, moments: torch.Tensor):
+        self.mean, logvar = moments.chunk(2, dim=1)
+        self.logvar = logvar.clamp(-30.0, 20.0)
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+
+    def sample(self, generator=None) -> torch.Tensor:
+        from .scheduler import randn_tensor
+        noise = randn_tensor(self.mean.shape, generator=generator, device=self.mean.device, dtype=self.mean.dtype)
+        return self.mean + self.std * noise
+
+    def mode(self) -> torch.Tensor:
+        return self.mean
+
+
+class EncoderOutput:
+    def __init__(self, latent_dist):
+        self.latent_dist = latent_dist
+
+    def __getitem__(self, i):
+        return (self.latent_dist,)[i]
 
 
 class AutoencoderKL:
@@ -43,8 +69,9 @@ class AutoencoderKL:
         self._pack(state_dict)
 
     @classmethod
-    def from_random(cls, seed: int = 0, config: dict = VAE_CONFIG, device="cuda:0"):
-        return cls(random_state_dict(vae_decoder_manifest(config), seed), config, device)
+    def from_random(cls, seed: int = 0, config: dict = VAE_CONFIG, device="cuda:0", with_encoder: bool = False):
+        m = vae_decoder_manifest(config) + (vae_encoder_manifest(config) if with_encoder else [])
+        return cls(random_state_dict(m, seed), config, device)
 
     def _dev(self, t, dtype=f32):
         return t.to(device=self.device, dtype=dtype).contiguous()
@@ -65,21 +92,7 @@ class AutoencoderKL:
         r.bias2 = self._dev(b2)
         return r
 
-    def _pack(self, sd):
-        sd = dict(sd)
-        a = "decoder.mid_block.attentions.0"
-        for old, new in (("query", "to_q"), ("key", "to_k"), ("value", "to_v"), ("proj_attn", "to_out.0")):
-            for suf in (".weight", ".bias"):  # legacy checkpoint spelling (App. A.4)
-                key = f"{a}.{old}{suf}"
-                if key in sd:
-                    t = sd.pop(key)
-                    sd[f"{a}.{new}{suf}"] = t.reshape(t.shape[0], t.shape[1]) if suf == ".weight" else t
-        self.pq_w = self._dev(sd["post_quant_conv.weight"].reshape(4, 4))
-        self.pq_b = self._dev(sd["post_quant_conv.bias"])
-        self.w_in = pack_edge_conv_weight(sd["decoder.conv_in.weight"], self.device)
-        self.b_in = self._dev(sd["decoder.conv_in.bias"])
-        self.mid0 = self._pack_resnet(sd, "decoder.mid_block.resnets.0")
-        self.mid1 = self._pack_resnet(sd, "decoder.mid_block.resnets.1")
+    def _pack_attn(self, sd, a):
         at = SimpleNamespace()
         at.g, at.b = self._dev(sd[a + ".group_norm.weight"]), self._dev(sd[a + ".group_norm.bias"])
         at.wq, at.bq = self._dev(sd[a + ".to_q.weight"], bf16), self._dev(sd[a + ".to_q.bias"])
@@ -90,7 +103,64 @@ class AutoencoderKL:
         # out = W_o (P V0 + b_v) + b_o  (softmax rows sum to one)
         at.bo = self._dev(sd[a + ".to_out.0.bias"].float() + wo @ sd[a + ".to_v.bias"].float())
         at.c = wo.shape[0]
-        self.attn = at
+        return at
+
+    def _pack_encoder(self, sd):
+        """Encoder + quant_conv (optional: only checkpoints / manifests that carry them)."""
+        cfg = self.cfg
+        ch = tuple(cfg["block_out_channels"])
+        wi = sd["encoder.conv_in.weight"].float()                         # [128, 3, 3, 3] -> Cin padded to 4
+        wp = torch.zeros(wi.shape[0], 4, 3, 3)
+        wp[:, :3] = wi
+        self.e_w_in = pack_edge_conv_weight(wp, self.device)
+        self.e_b_in = self._dev(sd["encoder.conv_in.bias"])
+        self.e_down = []
+        for i in range(len(ch)):
+            blk = SimpleNamespace(resnets=[self._pack_resnet(sd, f"encoder.down_blocks.{i}.resnets.{j}")
+                                           for j in range(cfg["layers_per_block"])], down=None)
+            if i < len(ch) - 1:
+                q = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+                blk.down = (pack_conv_weight(sd[q + ".weight"], device=self.device), self._dev(sd[q + ".bias"]))
+            self.e_down.append(blk)
+        self.e_mid0 = self._pack_resnet(sd, "encoder.mid_block.resnets.0")
+        self.e_attn = self._pack_attn(sd, "encoder.mid_block.attentions.0")
+        self.e_mid1 = self._pack_resnet(sd, "encoder.mid_block.resnets.1")
+        self.e_out_g, self.e_out_b = self._dev(sd["encoder.conv_norm_out.weight"]), self._dev(sd["encoder.conv_norm_out.bias"])
+        # conv_out (512 -> 8) with the 1x1 quant_conv folded in (both linear), Cout padded to one 32-column chunk;
+        # rows 8-15 carry the bf16 rounding residual of the folded weights (w = hi + lo)
+        q = sd["quant_conv.weight"].double().reshape(sd["quant_conv.weight"].shape[0], -1)          # [8, 8]
+        wo = sd["encoder.conv_out.weight"].double().permute(0, 2, 3, 1).reshape(q.shape[1], -1)      # [8, 9*512]
+        wf = (q @ wo).float()
+        bfold = (q @ sd["encoder.conv_out.bias"].double() + sd["quant_conv.bias"].double()).float()
+        hi = wf.to(bf16)
+        co = wf.shape[0]
+        w32 = torch.zeros((32, wf.shape[1]), dtype=bf16)
+        w32[:co], w32[co:2 * co] = hi, (wf - hi.float()).to(bf16)
+        self.e_w_out = w32.to(self.device).contiguous()
+        self.e_b_out = torch.zeros(32, dtype=f32, device=self.device)
+        self.e_b_out[:co] = bfold.to(self.device)
+        self.e_moments = co
+
+    def _pack(self, sd):
+        sd = dict(sd)
+        for a in ("decoder.mid_block.attentions.0", "encoder.mid_block.attentions.0"):
+            for old, new in (("query", "to_q"), ("key", "to_k"), ("value", "to_v"), ("proj_attn", "to_out.0")):
+                for suf in (".weight", ".bias"):  # legacy checkpoint spelling (App. A.4)
+                    key = f"{a}.{old}{suf}"
+                    if key in sd:
+                        t = sd.pop(key)
+                        sd[f"{a}.{new}{suf}"] = t.reshape(t.shape[0], t.shape[1]) if suf == ".weight" else t
+        self.has_encoder = "encoder.conv_in.weight" in sd
+        if self.has_encoder:
+            self._pack_encoder(sd)
+        a = "decoder.mid_block.attentions.0"
+        self.pq_w = self._dev(sd["post_quant_conv.weight"].reshape(4, 4))
+        self.pq_b = self._dev(sd["post_quant_conv.bias"])
+        self.w_in = pack_edge_conv_weight(sd["decoder.conv_in.weight"], self.device)
+        self.b_in = self._dev(sd["decoder.conv_in.bias"])
+        self.mid0 = self._pack_resnet(sd, "decoder.mid_block.resnets.0")
+        self.mid1 = self._pack_resnet(sd, "decoder.mid_block.resnets.1")
+        self.attn = self._pack_attn(sd, a)
         n = len(self.cfg["block_out_channels"])
         self.up = []
         for i in range(n):
@@ -127,9 +197,9 @@ class AutoencoderKL:
             o, _, o_st = self._gemm(n2, r.w2, mode=ops.A_3X3, bias=r.bias2, residual=h, want_f32=True, want_stats=True)
         return o.view(B, H, W, r.cout), o_st
 
-    def _attention(self, hs, gnws):
+    def _attention(self, hs, gnws, at=None):
         h, h_st = hs
-        at = self.attn
+        at = at or self.attn
         B, H, W, Cc = h.shape
         T = H * W
         n, _ = ops.groupnorm(h, at.g, at.b, groups=self.groups, eps=self.eps, silu=False, partials=gnws, x0_stats=h_st)
@@ -182,6 +252,40 @@ class AutoencoderKL:
         if not output_image and in_dtype != f32:
             img = img.to(in_dtype)
         return DecoderOutput(img) if return_dict else (img,)
+
+    # ------------------------------------------------------------------ encode (train_ID-Booth.py:1001-1002)
+    def encode(self, x, return_dict: bool = True):
+        """x: [n, 3, H, W] in [-1, 1] -> `.latent_dist` (DiagonalGaussianDistribution over [n, 4, H/8, W/8])."""
+        if not self.has_encoder:
+            raise RuntimeError("this AutoencoderKL was built without encoder weights")
+        x = x.to(device=self.device, dtype=f32)
+        B, cin, H, W = x.shape
+        if cin != 3 or H % 8 or W % 8:
+            raise ValueError("expected [n, 3, H, W] with H, W multiples of 8")
+        gnws = ops.groupnorm_workspace(B, self.groups, self.device)
+        x4 = torch.zeros((B, H, W, 4), dtype=f32, device=self.device)
+        x4[..., :3] = x.permute(0, 2, 3, 1)
+        h0, _ = ops.conv3x3_small_cin(x4, self.e_w_in, self.e_b_in, nchw=False)
+        h = (h0, None)
+        for blk in self.e_down:
+            for r in blk.resnets:
+                h = self._resnet(r, h, gnws)
+            if blk.down is not None:   # Downsample2D: F.pad(0,1,0,1) + conv3x3 stride 2 -> the kernel's asymmetric stride-2 view
+                ht = h[0]
+                o, _, o_st = self._gemm(ops.cast_bf16(ht), blk.down[0], mode=ops.A_3X3_S2_ASYM, bias=blk.down[1],
+                                        want_f32=True, want_stats=True)
+                h = (o.view(B, ht.shape[1] // 2, ht.shape[2] // 2, ht.shape[3]), o_st)
+        h = self._resnet(self.e_mid0, h, gnws)
+        h = self._attention(h, gnws, self.e_attn)
+        h = self._resnet(self.e_mid1, h, gnws)
+        n, _ = ops.groupnorm(h[0], self.e_out_g, self.e_out_b, groups=self.groups, eps=self.eps, silu=True, partials=gnws,
+                             x0_stats=h[1])
+        o, _ = self._gemm(n, self.e_w_out, mode=ops.A_3X3, bias=self.e_b_out, want_f32=True)
+        co = self.e_moments
+        o = o.view(B, H // 8, W // 8, 32)
+        moments = (o[..., :co] + o[..., co:2 * co]).permute(0, 3, 1, 2).contiguous()     # hi + lo weight halves; NHWC -> NCHW
+        dist = DiagonalGaussianDistribution(moments)
+        return EncoderOutput(dist) if return_dict else (dist,)
 
     def to(self, *a, **k):
         return self

@@ -129,6 +129,32 @@ def vae_decoder_manifest(cfg: dict = VAE_CONFIG) -> List[Tuple[str, Shape]]:
     return m
 
 
+def vae_encoder_manifest(cfg: dict = VAE_CONFIG) -> List[Tuple[str, Shape]]:
+    """AutoencoderKL encoder + quant_conv: 34,163,592 + 72 values (decoder + encoder = 83,653,863, the SD VAE)."""
+    ch = tuple(cfg["block_out_channels"])
+    lc = cfg["latent_channels"]
+    m: List[Tuple[str, Shape]] = [("encoder.conv_in.weight", (ch[0], cfg["in_channels"], 3, 3)), ("encoder.conv_in.bias", (ch[0],))]
+    prev = ch[0]
+    for i, c in enumerate(ch):
+        for j in range(cfg["layers_per_block"]):
+            m += _resnet(f"encoder.down_blocks.{i}.resnets.{j}", prev, c, None)
+            prev = c
+        if i < len(ch) - 1:
+            m += [(f"encoder.down_blocks.{i}.downsamplers.0.conv.weight", (c, c, 3, 3)),
+                  (f"encoder.down_blocks.{i}.downsamplers.0.conv.bias", (c,))]
+    top = ch[-1]
+    m += _resnet("encoder.mid_block.resnets.0", top, top, None)
+    a = "encoder.mid_block.attentions.0"
+    m += [(a + ".group_norm.weight", (top,)), (a + ".group_norm.bias", (top,))]
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        m += [(f"{a}.{n}.weight", (top, top)), (f"{a}.{n}.bias", (top,))]
+    m += _resnet("encoder.mid_block.resnets.1", top, top, None)
+    m += [("encoder.conv_norm_out.weight", (top,)), ("encoder.conv_norm_out.bias", (top,)),
+          ("encoder.conv_out.weight", (2 * lc, top, 3, 3)), ("encoder.conv_out.bias", (2 * lc,)),
+          ("quant_conv.weight", (2 * lc, 2 * lc, 1, 1)), ("quant_conv.bias", (2 * lc,))]
+    return m
+
+
 LORA_TARGETS = ("to_q", "to_k", "to_v", "to_out.0")  # train_ID-Booth.py:676 (add_k/v_proj match nothing)
 
 

@@ -60,7 +60,8 @@ int idb_num_sms(void);
  * (tap-major, channel-minor) per segment.  C of every segment must be a multiple of 64,
  * N a multiple of 32.
  * ---------------------------------------------------------------------------------------- */
-enum { IDB_A_1X1 = 0, IDB_A_3X3 = 1, IDB_A_3X3_S2 = 2 };
+enum { IDB_A_1X1 = 0, IDB_A_3X3 = 1, IDB_A_3X3_S2 = 2,
+       IDB_A_3X3_S2_ASYM = 3 /* stride 2 with the (0,1,0,1) right/bottom padding of the VAE encoder's Downsample2D: in(2y+dy, 2x+dx) */ };
 enum {
   IDB_EPI_GEGLU = 1, /* W rows interleaved in 16-blocks [a(16) | g(16)]; out[:, j] = a_j * gelu_erf(g_j); N_out = N/2 */
   IDB_EPI_GELU = 4,  /* out = gelu_erf(acc + bias) (CLIP text MLP fc1); not combined with GEGLU */

@@ -203,6 +203,27 @@ def vae_decode(sd, z: Tensor, cfg: dict = VAE_SD21, taps: Optional[dict] = None)
     return _conv(sd, "decoder.conv_out", h)
 
 
+def vae_encode_moments(sd, x: Tensor, cfg: dict = VAE_SD21) -> Tensor:
+    """`AutoencoderKL.encode(x)` up to the posterior moments [n, 8, h/8, w/8] = (mean | logvar)
+    (`train_ID-Booth.py:1001-1002`: `vae.encode(pixel_values).latent_dist.sample() * scaling_factor`).  diffusers
+    Encoder: conv_in -> 4 DownEncoderBlock2D (2 resnets; Downsample2D = F.pad(0,1,0,1) + conv3x3 stride 2 padding 0)
+    -> mid (resnet, 1-head attention, resnet) -> GN / SiLU / conv_out -> quant_conv 1x1."""
+    G, eps = cfg["norm_num_groups"], cfg["norm_eps"]
+    h = _conv(sd, "encoder.conv_in", x)
+    n = len(cfg["block_out_channels"])
+    for i in range(n):
+        for j in range(cfg["layers_per_block"]):
+            h = resnet_block(sd, f"encoder.down_blocks.{i}.resnets.{j}", h, None, G, eps)
+        if i < n - 1:
+            h = F.pad(h, (0, 1, 0, 1))
+            h = _conv(sd, f"encoder.down_blocks.{i}.downsamplers.0.conv", h, stride=2, padding=0)
+    h = resnet_block(sd, "encoder.mid_block.resnets.0", h, None, G, eps)
+    h = vae_attention(sd, "encoder.mid_block.attentions.0", h, G, eps)
+    h = resnet_block(sd, "encoder.mid_block.resnets.1", h, None, G, eps)
+    h = _conv(sd, "encoder.conv_out", F.silu(_gn(sd, "encoder.conv_norm_out", h, G, eps)))
+    return _conv(sd, "quant_conv", h, padding=0)
+
+
 def postprocess_np(image: Tensor):
     """`VaeImageProcessor.postprocess(output_type="np")` (a14; mirrored in-tree at
     `train_ID-Booth.py:413-415`)."""

@@ -158,3 +158,27 @@ def test_clip_text_encoder_vs_torch_fp32(cuda_dev):
     ids2[0, 5] = (ids2[0, 5] + 1) % 49000
     out2 = enc.forward_ids(ids2).float()
     assert rel(out2[0, :5], out[0, :5]) < 1e-6 and rel(out2[0, 5:], out[0, 5:]) > 1e-3
+
+
+def test_vae_encode_vs_oracle(cuda_dev):
+    """`vae.encode(x).latent_dist` (train_ID-Booth.py:1001-1002) against the fp32 oracle: posterior moments, and the
+    sample drawn from the same generator state."""
+    from oracle import sd21
+    from faceposegenerator_b200.vae import AutoencoderKL
+    from faceposegenerator_b200.weights import random_state_dict, vae_decoder_manifest, vae_encoder_manifest
+    sd = random_state_dict(vae_decoder_manifest() + vae_encoder_manifest(), 0)
+    vae = AutoencoderKL(sd, device=cuda_dev)
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(9)) * 2 - 1
+    dist = vae.encode(x.to(cuda_dev)).latent_dist
+    with torch.no_grad():
+        ref = sd21.vae_encode_moments(sd, x)
+    mean_r, logvar_r = ref.chunk(2, dim=1)
+    print(f"vae encode mean rel-L2 {rel(dist.mean, mean_r):.3e} logvar rel-L2 {rel(dist.logvar, logvar_r.clamp(-30, 20)):.3e}")
+    assert dist.mean.shape == (1, 4, 32, 32)
+    assert rel(dist.mean, mean_r) < 1e-2
+    assert rel(dist.logvar, logvar_r.clamp(-30, 20)) < 1e-2
+    g1 = torch.Generator(device="cuda").manual_seed(3)
+    s = dist.sample(generator=g1)
+    g2 = torch.Generator(device="cuda").manual_seed(3)
+    noise = torch.randn(dist.mean.shape, generator=g2, device=cuda_dev, dtype=dist.mean.dtype)
+    assert torch.allclose(s, dist.mean + dist.std * noise)

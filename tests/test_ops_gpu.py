@@ -171,6 +171,45 @@ def test_conv3x3_stride2(ops, cuda_dev, B, H, W, C):
     assert rel(o32, ref) < 2e-5, rel(o32, ref)
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 64, 64, 128), (1, 32, 32, 256), (3, 16, 16, 512)])
+def test_conv3x3_stride2_asymmetric(ops, cuda_dev, B, H, W, C):
+    """VAE encoder Downsample2D: F.pad(x, (0, 1, 0, 1)) then conv3x3 stride 2 padding 0."""
+    g = torch.Generator(device="cuda").manual_seed(H + 1)
+    x = rb(torch.randn(B, H, W, C, device=cuda_dev, generator=g))
+    w = rb(torch.randn(C, C, 3, 3, device=cuda_dev, generator=g) / math.sqrt(9 * C))
+    bias = torch.randn(C, device=cuda_dev, generator=g)
+    o32, _ = ops.gemm_conv(x, pack_conv_w(w), mode=ops.A_3X3_S2_ASYM, bias=bias, want_f32=True)
+    ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), w.float(), bias, stride=2, padding=0)
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, C)
+    assert rel(o32, ref) < 2e-5, rel(o32, ref)
+
+
+def test_linear_gelu_epilogue(ops, cuda_dev):
+    """CLIP text MLP fc1: gelu_erf(x W^T + b) in the GEMM epilogue."""
+    M, K, N = 616, 1024, 4096
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = rb(torch.randn(M, K, device=cuda_dev, generator=g))
+    w = rb(torch.randn(N, K, device=cuda_dev, generator=g) / math.sqrt(K))
+    bias = torch.randn(N, device=cuda_dev, generator=g)
+    _, o16 = ops.gemm_conv(x, w, bias=bias, gelu=True, want_bf16=True)
+    ref = F.gelu(x.float() @ w.float().t() + bias)
+    assert rel(o16.float(), ref) < 4e-3
+
+
+def test_attention_causal_short(ops, cuda_dev):
+    """CLIP text tower self-attention: 77 tokens, causal mask, fused q/k/v buffer."""
+    B, heads, T = 3, 16, 77
+    C = heads * 64
+    g = torch.Generator(device="cuda").manual_seed(21)
+    qkv = rb(torch.randn(B * T, 3 * C, device=cuda_dev, generator=g))
+    out = ops.attention(qkv, qkv, qkv, batch=B, heads=heads, t_q=T, t_kv=T, scale=0.125, col0_q=0, col0_k=C, col0_v=2 * C,
+                        causal=True)
+    q, k, v = qkv.float().view(B, T, 3, heads, 64).unbind(2)
+    ref = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True)
+    ref = ref.transpose(1, 2).reshape(B * T, C)
+    assert rel(out.float(), ref) < 6e-3
+
+
 def test_conv3x3_plus_shortcut_segment(ops, cuda_dev):
     """ResnetBlock2D tail: conv2(h) + conv_shortcut(x) + x-independent bias, as ONE GEMM
     whose K axis is [9*Cout | Cin]."""

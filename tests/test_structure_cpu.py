@@ -22,6 +22,7 @@ def test_parameter_counts():
     from faceposegenerator_b200 import weights as w
     assert sum(math.prod(s) for _, s in w.unet_manifest()) == 865_910_724
     assert sum(math.prod(s) for _, s in w.vae_decoder_manifest()) == 49_490_199
+    assert sum(math.prod(s) for _, s in w.vae_encoder_manifest()) == 34_163_592 + 72   # decoder + encoder = 83,653,863
     lm = w.lora_manifest()
     assert len(lm) == 128 and sum(4 * (a + b) for _, a, b in lm) == 829_952
     from faceposegenerator_b200.text import text_manifest
