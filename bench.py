@@ -41,6 +41,16 @@ NUM_STEPS = 30
 GUIDANCE = 5.0
 
 
+def _step_traffic():
+    """DRAM bytes of one UNet step from the committed ncu capture (profiles/r01_step_traffic.json), or None."""
+    fn = os.path.join(ROOT, "profiles", "r01_step_traffic.json")
+    try:
+        with open(fn) as f:
+            return float(json.load(f)["traffic_bytes"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     fn = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(fn):
@@ -266,7 +276,7 @@ def run_native(args):
                     "d2h_bytes_per_step": int(n * 512 * 512 * 3 * 4)},
             "gpu_launches": int(gpu_launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                         "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": None,
+                         "frac": (achieved / peaks["bf16_sustained"]) if achieved else None, "traffic": _step_traffic(),
                          "kernel": "UNet step graph (gemm_tc_kernel / attention_kernel dominate; see profiles/)",
                          "flops_per_launch": rows * UNET_TFLOP_PER_ROW * 1e12,
                          "peak_source": peaks["source"] + ", sustained figure (timed inside a long step)"},
