@@ -177,8 +177,12 @@ def run_native(args):
     pipe.load_lora_weights(random_lora(seed=0))          # synthetic "trained" rank-4 adapters, fused unmerged
     pipe.set_progress_bar_config(disable=True)
 
+    from faceposegenerator_b200.parallel import gather_images, shard_units, unit_seed
     n = IMAGES_PER_CALL
-    g = torch.Generator().manual_seed(1000 + rank)
+    # one step = world * n image units; rank r generates units r, r + G, ... (weak scaling: n units per GPU per step)
+    my_units = shard_units(world * n, rank, world)
+    assert len(my_units) == n
+    g = torch.Generator().manual_seed(unit_seed(my_units[0], 1000))
     # synthetic context (text encoder is outside the timed hot path): N(0,1) prompt / negative embeddings
     pe_host = torch.randn(n, 77, 1024, generator=g).pin_memory()
     ne_host = torch.randn(n, 77, 1024, generator=g).pin_memory()
@@ -194,7 +198,7 @@ def run_native(args):
                    guidance_scale=GUIDANCE, height=512, width=512, output_type="pt", noise_tape=tape_dev)
         img = (out.images.permute(0, 2, 3, 1) * 255).round().to(torch.uint8).contiguous()
         if world > 1:
-            dist.all_gather_into_tensor(gathered, img)
+            gather_images(img, world * n, rank, world, out=gathered)   # one all_gather_into_tensor over NCCL / NVLink
         return img
 
     def call_e2e():
