@@ -49,7 +49,8 @@ def bench_linear(M, K, N, geglu=False, lora=False, tag="linear"):
     kw = {}
     if lora:
         kw = dict(lora_down=torch.randn(16 * (N // 320 if N % 320 == 0 and N > 1280 else 1), K, device=dev).to(bf16),
-                  lora_up=torch.randn(N, 4, device=dev), lora_seg_n=N if N <= 1280 else N // 3)
+                  lora_up=torch.nn.functional.pad(torch.randn(N, 4, device=dev) * 0.05, (0, 60)).to(bf16),
+                  lora_seg_n=N if N <= 1280 else N // 3)
     out = torch.empty(M, N // 2 if geglu else N, dtype=bf16, device=dev)
     ms = timeit(lambda: ops.gemm_conv(x, w, bias=bias, geglu=geglu, out_bf16=out, k_splits=0, workspace=WS, **kw))
     report(f"{tag} M{M} K{K} N{N}" + (" geglu" if geglu else "") + (" lora" if lora else ""), ms, flops=2.0 * M * K * N)
