@@ -817,9 +817,20 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int k_split
     const long long e = i * 4;
     const long long row = e / N;
     const int col = static_cast<int>(e - row * N);
+    // partial sums of the k_splits slices, four independent loads in flight (fixed summation order: deterministic)
+    const long long slice = M * N;
     float4 a = *reinterpret_cast<const float4*>(ws + e);
-    for (int s = 1; s < k_splits; ++s) {
-      const float4 v = *reinterpret_cast<const float4*>(ws + static_cast<long long>(s) * M * N + e);
+    int s = 1;
+    for (; s + 3 < k_splits; s += 4) {
+      const float4 v0 = *reinterpret_cast<const float4*>(ws + (s + 0) * slice + e);
+      const float4 v1 = *reinterpret_cast<const float4*>(ws + (s + 1) * slice + e);
+      const float4 v2 = *reinterpret_cast<const float4*>(ws + (s + 2) * slice + e);
+      const float4 v3 = *reinterpret_cast<const float4*>(ws + (s + 3) * slice + e);
+      a.x += (v0.x + v1.x) + (v2.x + v3.x), a.y += (v0.y + v1.y) + (v2.y + v3.y);
+      a.z += (v0.z + v1.z) + (v2.z + v3.z), a.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; s < k_splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + s * slice + e);
       a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
     }
     if (bias) {
