@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libidb_b200.so")
 
-A_1X1, A_3X3, A_3X3_S2, A_3X3_S2_ASYM = 0, 1, 2, 3
+A_1X1, A_3X3, A_3X3_S2, A_3X3_S2_ASYM, A_2X2 = 0, 1, 2, 3, 4
 EPI_GEGLU = 1
 EPI_F16 = 2
 EPI_GELU = 4
@@ -35,6 +35,8 @@ class GemmConvArgs(C.Structure):
         ("k_splits", c_int32), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("stats_partials", c_void_p),
         ("prelu", c_void_p),
+        ("tap_off_x", c_int32), ("tap_off_y", c_int32),
+        ("out_scale", c_int32), ("out_phase_x", c_int32), ("out_phase_y", c_int32),
     ]
 
 
@@ -59,7 +61,7 @@ class GroupNormArgs(C.Structure):
         ("silu", c_int32),
         ("out_norm", c_void_p), ("out_raw", c_void_p),
         ("partials", c_void_p),
-        ("x0_stats", c_void_p), ("x1_stats", c_void_p),
+        ("x0_stats", c_void_p), ("x1_stats", c_void_p), ("x0_stats_phases", c_int32),
     ]
 
 

@@ -68,6 +68,7 @@ struct GemmParams {
   CUtensorMap tmA0, tmA1, tmW, tmW1, tmL, tmU, tmOutF, tmOutB, tmRes;   // tmU: LoRA up-projection weights [N, 64] bf16
   CUtensorMap _pad_unused;   // tmOut* / tmRes: 4-D [N_out, Wo, Ho, B] maps (32-row boxes); tmW1: W box of the pair's second CTA (LoRA)
   int mode0, cpb0, c0, nkb0, nkb1;
+  int tap_off_x, tap_off_y;   // IDB_A_2X2
   int Ho, Wo, B;
   int BW, BH, BB;
   int tiles_x, tiles_y;
@@ -85,6 +86,7 @@ struct GemmParams {
   float* out_f32;
   __nv_bfloat16* out_bf16;
   float* workspace;
+  long long stats_rowblock0;   // first row block of this call inside stats (phased output)
   float2* stats;   // optional [ceil(M/32)][N] (sum, sum of squares) over each 32-row block of the fp32 output
 };
 
@@ -235,6 +237,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               const int dy = (tap * 11) >> 5, dx = tap - dy * 3;   // tap / 3 for tap in [0, 9)
               if (p.mode0 == IDB_A_3X3) {
                 c0 = cb, c1 = x0 + dx - 1, c2 = y0 + dy - 1, c3 = b0;
+              } else if (p.mode0 == IDB_A_2X2) {   // tap = 2 * dy + dx over the low-resolution image
+                c0 = cb, c1 = x0 + (tap & 1) + p.tap_off_x, c2 = y0 + (tap >> 1) + p.tap_off_y, c3 = b0;
               } else if (p.mode0 == IDB_A_3X3_S2_ASYM) {  // stride 2, padding on the right / bottom only: input (2*yo + dy, 2*xo + dx)
                 const int px = (dx == 1) ? 1 : 0, py = (dy == 1) ? 1 : 0;
                 const int ox = (dx == 2) ? 1 : 0, oy = (dy == 2) ? 1 : 0;
@@ -730,7 +734,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               cs += v;
               cs2 = fmaf(v, v, cs2);
             }
-            const long long rowblock = static_cast<long long>(m_blk) * 4 + quarter;
+            const long long rowblock = p.stats_rowblock0 + static_cast<long long>(m_blk) * 4 + quarter;
             if (ocol + lane < p.N_out) p.stats[rowblock * p.N_out + ocol + lane] = make_float2(cs, cs2);
           }
           IDB_TICK(5);   // staging (+ statistics)
@@ -951,7 +955,14 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   if (a->a1 && (a->c1 <= 0 || a->c1 % 64)) return fail(IDB_E_BADARG, "idb_gemm_conv: C1 must be a multiple of 64");
   if (a->n <= 0 || a->n % 32) return fail(IDB_E_BADARG, "idb_gemm_conv: N must be a positive multiple of 32");
   if (a->batch <= 0 || a->height <= 0 || a->width <= 0) return fail(IDB_E_BADARG, "idb_gemm_conv: bad geometry");
-  if (a->a0_mode < IDB_A_1X1 || a->a0_mode > IDB_A_3X3_S2_ASYM) return fail(IDB_E_BADARG, "idb_gemm_conv: bad a0_mode");
+  if (a->a0_mode < IDB_A_1X1 || a->a0_mode > IDB_A_2X2) return fail(IDB_E_BADARG, "idb_gemm_conv: bad a0_mode");
+  if (a->a0_mode == IDB_A_2X2 && (a->tap_off_x < -1 || a->tap_off_x > 0 || a->tap_off_y < -1 || a->tap_off_y > 0))
+    return fail(IDB_E_BADARG, "idb_gemm_conv: 2x2 tap offsets must be -1 or 0");
+  const bool phased = a->out_scale == 2;
+  if (a->out_scale != 0 && a->out_scale != 1 && a->out_scale != 2) return fail(IDB_E_BADARG, "idb_gemm_conv: out_scale must be 0, 1 or 2");
+  if (phased && ((a->out_phase_x | a->out_phase_y) & ~1)) return fail(IDB_E_BADARG, "idb_gemm_conv: output phase must be 0 or 1");
+  if (phased && (a->residual || (a->out_f32 && a->out_bf16) || a->k_splits > 1))
+    return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: phased output with residual / both outputs / split-K");
   const bool stride2 = a->a0_mode == IDB_A_3X3_S2 || a->a0_mode == IDB_A_3X3_S2_ASYM;
   if (stride2 && ((a->height | a->width) & 1))
     return fail(IDB_E_BADARG, "idb_gemm_conv: stride-2 conv needs even H and W");
@@ -970,9 +981,11 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  const int taps0 = (a->a0_mode == IDB_A_1X1) ? 1 : 9;
+  const int taps0 = (a->a0_mode == IDB_A_1X1) ? 1 : (a->a0_mode == IDB_A_2X2 ? 4 : 9);
   const int H = a->height, W = a->width, B = a->batch;
   p.mode0 = a->a0_mode;
+  p.tap_off_x = a->tap_off_x;
+  p.tap_off_y = a->tap_off_y;
   p.c0 = a->c0;
   p.cpb0 = a->c0 / 64;
   p.nkb0 = taps0 * p.cpb0;
@@ -1043,7 +1056,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
       const double cost1 = static_cast<double>((tiles1 + units - 1) / units) * (block_n + 24) * feed;
       // tiny-M layers (8x8 latents) run split-K anyway: with dual-N tiles each split streams the weights once per
       // 256 rows instead of once per 128-column tile
-      const bool splitk_regime = a->k_splits == 0 && a->workspace && tiles1 * 2 <= units && p.nkb0 + p.nkb1 >= 64;   // (split anyway)
+      const bool splitk_regime = !phased && a->k_splits == 0 && a->workspace && tiles1 * 2 <= units && p.nkb0 + p.nkb1 >= 64;   // (split anyway)
       if (force_dual == 1 || (p.nkb0 + p.nkb1 >= 32 && cost < cost1) || splitk_regime) dual = true, block_n = 160;
     }
   }
@@ -1054,7 +1067,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   if (ksp == 0) {  // auto: split K when the tile grid leaves most SMs idle
     ksp = 1;
     const long long tiles = static_cast<long long>(m_units) * p.n_tiles_n;
-    if (!lora && !geglu && !(a->flags & IDB_EPI_GELU) && a->workspace && tiles * 2 <= units && nkb >= 16) {
+    if (!lora && !geglu && !phased && !(a->flags & IDB_EPI_GELU) && a->workspace && tiles * 2 <= units && nkb >= 16) {
       long long want = units / tiles;
       if (want > nkb / 8) want = nkb / 8;
       const size_t per_split = static_cast<size_t>(p.M) * a->n * sizeof(float);
@@ -1092,6 +1105,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
   p.workspace = a->workspace;
   p.stats = reinterpret_cast<float2*>(a->stats_partials);
+  p.stats_rowblock0 = phased ? static_cast<long long>(2 * a->out_phase_y + a->out_phase_x) * ((p.M + 31) / 32) : 0;
 
   // ---- tensor maps
   if (stride2) {
@@ -1150,13 +1164,18 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     const uint64_t No = uint64_t(p.N_out);
     uint64_t dims[4] = {No, uint64_t(p.Wo), uint64_t(p.Ho), uint64_t(B)};
     uint32_t box[4] = {nc, uint32_t(bw32), uint32_t(bh32), uint32_t(bb32)};
+    // phased output: pixel (y, x) lands at (2y + py, 2x + px) of the [B, 2Ho, 2Wo, N] tensor -> same box, doubled
+    // pixel / row strides and a shifted base
+    const uint64_t sx = phased ? 2 : 1;
+    const uint64_t row_elems = sx * uint64_t(p.Wo) * No;                    // elements per output row of the target tensor
+    const uint64_t base_off = phased ? (uint64_t(a->out_phase_y) * row_elems + uint64_t(a->out_phase_x) * No) : 0;
     if (a->out_f32) {
-      uint64_t strides[3] = {No * 4, uint64_t(p.Wo) * No * 4, uint64_t(p.Ho) * p.Wo * No * 4};
-      if (int rc = make_tmap(&p.tmOutF, a->out_f32, 4, geglu ? 0 : 128, 4, dims, strides, box)) return rc;
+      uint64_t strides[3] = {sx * No * 4, sx * row_elems * 4, sx * uint64_t(p.Ho) * row_elems * 4};
+      if (int rc = make_tmap(&p.tmOutF, a->out_f32 + base_off, 4, geglu ? 0 : 128, 4, dims, strides, box)) return rc;
     }
     if (a->out_bf16) {
-      uint64_t strides[3] = {No * 2, uint64_t(p.Wo) * No * 2, uint64_t(p.Ho) * p.Wo * No * 2};
-      if (int rc = make_tmap(&p.tmOutB, a->out_bf16, 2, 0, 4, dims, strides, box)) return rc;
+      uint64_t strides[3] = {sx * No * 2, sx * row_elems * 2, sx * uint64_t(p.Ho) * row_elems * 2};
+      if (int rc = make_tmap(&p.tmOutB, static_cast<const char*>(a->out_bf16) + base_off * 2, 2, 0, 4, dims, strides, box)) return rc;
     }
     if (a->residual && !geglu) {   // fp32 [M, N_out] like out_f32: prefetched by TMA into the staging buffers
       uint64_t strides[3] = {No * 4, uint64_t(p.Wo) * No * 4, uint64_t(p.Ho) * p.Wo * No * 4};

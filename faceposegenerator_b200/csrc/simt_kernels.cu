@@ -134,7 +134,7 @@ __global__ void gn_stats_kernel(const GnParams p) {
 // Group statistics from the row-block channel sums that the producing GEMM epilogues wrote
 // (fixed summation order -> deterministic).  grid = (groups, batch), 256 threads per (image, group).
 __global__ void gn_finalize_kernel(const float2* __restrict__ s0, int c0, const float2* __restrict__ s1, int c1,
-                                   int rb_per_image, int cpg, int hw, float eps, float* __restrict__ stats) {
+                                   int rb_per_image, int cpg, int hw, float eps, float* __restrict__ stats, int phases0) {
   pdl_trigger();
   pdl_wait();
   const int g = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -149,8 +149,13 @@ __global__ void gn_finalize_kernel(const float2* __restrict__ s0, int c0, const 
   auto cell = [&](int i) -> float2 {
     if (i >= cells) return make_float2(0.f, 0.f);
     const int rb = i / cpg, c = cbase + (i - rb * cpg);
-    const long long row = row0 + rb;
-    return (c < c0) ? s0[row * c0 + c] : s1[row * c1 + (c - c0)];
+    if (c >= c0) return s1[(row0 + rb) * c1 + (c - c0)];
+    if (phases0 <= 1) return s0[(row0 + rb) * c0 + c];
+    // source 0 written as `phases0` phased GEMM outputs: [phase][image][row block of the low-resolution raster]
+    const int rbl = rb_per_image / phases0;
+    const int ph = rb / rbl, r2 = rb - ph * rbl;
+    const long long row = (static_cast<long long>(ph) * gridDim.y + b) * rbl + r2;
+    return s0[row * c0 + c];
   };
   for (int i = threadIdx.x; i < cells; i += 4 * 256) {
     const float2 v0 = cell(i), v1 = cell(i + 256), v2 = cell(i + 512), v3 = cell(i + 768);
@@ -700,11 +705,12 @@ extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
   threads = (threads + 31) / 32 * 32;
   if (threads < 64) threads = 64;  // the apply kernel's first `groups` threads publish mean / rstd
   dim3 grid(p.nchunks, a->batch);
-  const bool have_stats = a->x0_stats != nullptr && (a->x1 == nullptr || a->x1_stats != nullptr) && a->hw % 32 == 0;
+  const bool have_stats = a->x0_stats != nullptr && (a->x1 == nullptr || a->x1_stats != nullptr) && a->hw % 32 == 0 &&
+                          (a->x0_stats_phases <= 1 || (a->x0_stats_phases == 4 && a->hw % 128 == 0));
   if (have_stats) {   // statistics already produced by the GEMM epilogues of the sources
     launch_pdl(gn_finalize_kernel, dim3(dim3(a->groups, a->batch)), dim3(256), 0, stream, 
         reinterpret_cast<const float2*>(a->x0_stats), p.c0, reinterpret_cast<const float2*>(a->x1_stats), p.c1,
-        a->hw / 32, p.cpg, a->hw, a->eps, p.stats);
+        a->hw / 32, p.cpg, a->hw, a->eps, p.stats, a->x0_stats_phases);
     IDB_CHECK_LAUNCH("gn_finalize");
   } else {
     const size_t stats_smem = static_cast<size_t>(2) * p.PY * C * sizeof(float);

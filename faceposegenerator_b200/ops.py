@@ -11,7 +11,7 @@ from typing import Optional
 import torch
 
 from . import _lib
-from ._lib import A_1X1, A_3X3, A_3X3_S2, A_3X3_S2_ASYM, EPI_F16, EPI_GEGLU, EPI_GELU  # noqa: F401  (re-exported)
+from ._lib import A_1X1, A_2X2, A_3X3, A_3X3_S2, A_3X3_S2_ASYM, EPI_F16, EPI_GEGLU, EPI_GELU  # noqa: F401  (re-exported)
 
 bf16, f16, f32 = torch.bfloat16, torch.float16, torch.float32
 
@@ -34,7 +34,8 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
               geglu: bool = False, out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
               want_f32: bool = False, want_bf16: bool = False, k_splits: int = 1,
               workspace: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, want_stats: bool = False,
-              prelu: Optional[torch.Tensor] = None, half: bool = False, gelu: bool = False):
+              prelu: Optional[torch.Tensor] = None, half: bool = False, gelu: bool = False,
+              tap_off=(0, 0), out_phase=None):
     """a0: bf16 [B,H,W,C0] (or [M,K] for a Linear); w: bf16 [N, Ktot].  Returns (out_f32, out_bf16).
     half=True: the 16-bit tensors (a0, a1, w, out_bf16) are IEEE fp16 instead of bf16 (IDB_EPI_F16)."""
     t16 = f16 if half else bf16
@@ -46,7 +47,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
     N = w.shape[0]
     Ho, Wo = (H // 2, W_ // 2) if mode in (A_3X3_S2, A_3X3_S2_ASYM) else (H, W_)
     M = B * Ho * Wo
-    taps = 1 if mode == A_1X1 else 9
+    taps = 1 if mode == A_1X1 else (4 if mode == A_2X2 else 9)
     c1 = 0
     if a1 is not None:
         _chk(a1, t16, "a1")
@@ -91,7 +92,9 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
         flags=(EPI_GEGLU if geglu else 0) | (EPI_F16 if half else 0) | (EPI_GELU if gelu else 0), out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
         k_splits=k_splits, workspace=_lib.ptr(workspace),
         workspace_bytes=0 if workspace is None else workspace.numel() * 4, stats_partials=_lib.ptr(stats),
-        prelu=_lib.ptr(prelu))
+        prelu=_lib.ptr(prelu), tap_off_x=tap_off[1], tap_off_y=tap_off[0],
+        out_scale=2 if out_phase is not None else 0, out_phase_y=0 if out_phase is None else out_phase[0],
+        out_phase_x=0 if out_phase is None else out_phase[1])
     _lib.call("idb_gemm_conv", C.byref(args), _lib.stream_ptr(),
               desc=None if _lib.trace is None else dict(M=M, N=N, K=taps * C0 + c1, mode=mode, lora=lora_down is not None,
                                                         geglu=geglu, f32=out_f32 is not None, b16=out_bf16 is not None,
@@ -123,7 +126,7 @@ def groupnorm_workspace(batch: int, groups: int, device) -> torch.Tensor:
 
 
 def groupnorm(x0, gamma, beta, *, groups: int, eps: float, silu: bool, x1=None, out_norm=None, out_raw=None,
-              want_raw: bool = False, partials=None, x0_stats=None, x1_stats=None):
+              want_raw: bool = False, partials=None, x0_stats=None, x1_stats=None, x0_stats_phases: int = 0):
     """x0: fp32 [B, HW.., C0] NHWC (+ optional x1 [B, HW.., C1] concatenated on channels)."""
     _chk(x0, f32, "x0"); _chk(x1, f32, "x1", allow_none=True)
     _chk(gamma, f32, "gamma"); _chk(beta, f32, "beta")
@@ -141,7 +144,7 @@ def groupnorm(x0, gamma, beta, *, groups: int, eps: float, silu: bool, x1=None, 
     args = _lib.GroupNormArgs(x0=x0.data_ptr(), c0=c0, x1=_lib.ptr(x1), c1=c1, batch=B, hw=hw, groups=groups, eps=eps,
                               gamma=gamma.data_ptr(), beta=beta.data_ptr(), silu=int(silu),
                               out_norm=out_norm.data_ptr(), out_raw=_lib.ptr(out_raw), partials=partials.data_ptr(),
-                              x0_stats=_lib.ptr(x0_stats), x1_stats=_lib.ptr(x1_stats))
+                              x0_stats=_lib.ptr(x0_stats), x1_stats=_lib.ptr(x1_stats), x0_stats_phases=x0_stats_phases)
     _lib.call("idb_groupnorm", C.byref(args), _lib.stream_ptr())
     return out_norm, out_raw
 

@@ -25,6 +25,23 @@ def pack_conv_weight(w: torch.Tensor, shortcut: Optional[torch.Tensor] = None, d
     return p.to(device=device, dtype=bf16).contiguous()
 
 
+def pack_upsample_phase_weights(w: torch.Tensor, device=None):
+    """Upsample2D = nearest-2x + conv3x3(pad 1).  Output pixel (2i+a, 2j+c) only sees the 2x2 low-resolution
+    neighbourhood rows {i+a-1, i+a}, cols {j+c-1, j+c}; the 3x3 taps that land on the same input pixel are summed in
+    fp32: a = 0: rows (w0 | w1+w2), a = 1: rows (w0+w1 | w2); same for columns.
+    Returns w_ph[a][c]: bf16 [Cout, 4*Cin] (tap = 2u + v major, channel minor) for idb_gemm_conv(IDB_A_2X2) with
+    tap offsets (a - 1, c - 1)."""
+    w = w.float()                                        # [Cout, Cin, 3, 3]
+    rows = ((w[:, :, 0:1], w[:, :, 1:2] + w[:, :, 2:3]), (w[:, :, 0:1] + w[:, :, 1:2], w[:, :, 2:3]))
+    out = []
+    for a in range(2):
+        r = torch.cat(rows[a], dim=2)                    # [Cout, Cin, 2, 3]
+        cols = ((r[..., 0:1], r[..., 1:2] + r[..., 2:3]), (r[..., 0:1] + r[..., 1:2], r[..., 2:3]))
+        out.append([torch.cat(cols[c], dim=3).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+                    .to(device=device, dtype=bf16).contiguous() for c in range(2)])
+    return out
+
+
 def pack_edge_conv_weight(w: torch.Tensor, device=None) -> torch.Tensor:
     """[Cout, Cin, 3, 3] -> fp32 [Cout, 3, 3, Cin] for the tiny-Cin / tiny-Cout SIMT kernels."""
     return w.permute(0, 2, 3, 1).to(device=device, dtype=f32).contiguous()

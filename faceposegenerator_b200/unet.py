@@ -18,7 +18,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import ops
-from .packing import interleave_geglu, pack_conv_weight, pack_lora
+from .packing import interleave_geglu, pack_conv_weight, pack_lora, pack_upsample_phase_weights
 from .weights import UNET_CONFIG, random_state_dict, unet_manifest
 
 bf16, f32 = torch.bfloat16, torch.float32
@@ -148,7 +148,8 @@ class UNet2DConditionModel:
                     blk.attns.append(self._pack_transformer(sd, f"up_blocks.{i}.attentions.{j}"))
             if i < n - 1:
                 q = f"up_blocks.{i}.upsamplers.0.conv"
-                blk.up = (pack_conv_weight(sd[q + ".weight"], device=self.device), self._dev(sd[q + ".bias"]))
+                blk.up = (pack_conv_weight(sd[q + ".weight"], device=self.device), self._dev(sd[q + ".bias"]),
+                          pack_upsample_phase_weights(sd[q + ".weight"], device=self.device))
             self.up.append(blk)
         self.t_w_all = self._dev(torch.cat(temb_rows, 0))
         self.t_b_all = self._dev(torch.cat(temb_bias, 0))
@@ -212,11 +213,12 @@ class UNet2DConditionModel:
     # A "stream" value is (fp32 NHWC tensor, row-block channel statistics or None): every GEMM that
     # produces a residual-stream tensor also emits the sums GroupNorm needs, so the norm reads it once.
     def _resnet(self, r: _Resnet, hs, skip, temb, gnws):
-        h, h_st = hs
+        h, h_st = hs[0], hs[1]
+        h_ph = hs[2] if len(hs) > 2 else 0          # 4: statistics written by the four phased upsample GEMMs
         sk, sk_st = skip if skip is not None else (None, None)
         B, H, W = h.shape[0], h.shape[1], h.shape[2]
         n1, raw = ops.groupnorm(h, r.g1, r.b1, groups=self.groups, eps=self.eps, silu=True, x1=sk,
-                                want_raw=r.shortcut, partials=gnws, x0_stats=h_st, x1_stats=sk_st)
+                                want_raw=r.shortcut, partials=gnws, x0_stats=h_st, x1_stats=sk_st, x0_stats_phases=h_ph)
         t1, _, t1_st = self._gemm(n1, r.w1, mode=ops.A_3X3, bias=r.bias1, rowvec=temb[:, r.temb_off:],
                                   rowvec_ld=temb.shape[1], want_f32=True, want_stats=True)
         t1 = t1.view(B, H, W, r.cout)
@@ -336,9 +338,23 @@ class UNet2DConditionModel:
                 tap(f"up_blocks.{i}.{j}", h)
             if blk.up is not None:
                 ht = h[0]
-                hu = ops.upsample2x(ht)
-                o, _, o_st = self._gemm(hu, blk.up[0], mode=ops.A_3X3, bias=blk.up[1], want_f32=True, want_stats=True)
-                h = (o.view(B, hu.shape[1], hu.shape[2], ht.shape[3]), o_st)
+                Hl, Wl, Cu = ht.shape[1], ht.shape[2], ht.shape[3]
+                if B * Hl * Wl >= 2048 and (Hl * Wl) % 32 == 0:
+                    # Upsample2D as four 2x2 convolutions on the LOW-resolution tensor (one per output parity class,
+                    # 3x3 taps pre-summed): 4 x K = 4C instead of K = 9C on the upsampled tensor -> 2.25x fewer MACs,
+                    # and no upsampled operand is ever written
+                    xb = ops.cast_bf16(ht)
+                    o = torch.empty((B, 2 * Hl, 2 * Wl, Cu), dtype=f32, device=self.device)
+                    o_st = torch.empty((4, B * Hl * Wl // 32, Cu, 2), dtype=f32, device=self.device)
+                    for a in range(2):
+                        for c in range(2):
+                            self._gemm(xb, blk.up[2][a][c], mode=ops.A_2X2, bias=blk.up[1], out_f32=o, stats=o_st,
+                                       tap_off=(a - 1, c - 1), out_phase=(a, c))
+                    h = (o, o_st, 4)
+                else:
+                    hu = ops.upsample2x(ht)
+                    o, _, o_st = self._gemm(hu, blk.up[0], mode=ops.A_3X3, bias=blk.up[1], want_f32=True, want_stats=True)
+                    h = (o.view(B, hu.shape[1], hu.shape[2], Cu), o_st)
         n, _ = ops.groupnorm(h[0], self.out_g, self.out_b, groups=self.groups, eps=self.eps, silu=True, partials=gnws,
                              x0_stats=h[1])
         o, _ = self._gemm(n, self.w_conv_out, mode=ops.A_3X3, bias=self.b_conv_out, want_f32=True)

@@ -15,7 +15,7 @@ from typing import Dict, Optional
 import torch
 
 from . import ops
-from .packing import pack_conv_weight, pack_edge_conv_weight
+from .packing import pack_conv_weight, pack_edge_conv_weight, pack_upsample_phase_weights
 from .weights import VAE_CONFIG, random_state_dict, vae_decoder_manifest, vae_encoder_manifest
 
 bf16, f32 = torch.bfloat16, torch.float32
@@ -168,7 +168,8 @@ class AutoencoderKL:
                                            for j in range(self.cfg["layers_per_block"] + 1)], up=None)
             if i < n - 1:
                 q = f"decoder.up_blocks.{i}.upsamplers.0.conv"
-                blk.up = (pack_conv_weight(sd[q + ".weight"], device=self.device), self._dev(sd[q + ".bias"]))
+                blk.up = (pack_conv_weight(sd[q + ".weight"], device=self.device), self._dev(sd[q + ".bias"]),
+                          pack_upsample_phase_weights(sd[q + ".weight"], device=self.device))
             self.up.append(blk)
         self.out_g, self.out_b = self._dev(sd["decoder.conv_norm_out.weight"]), self._dev(sd["decoder.conv_norm_out.bias"])
         self.w_out = pack_edge_conv_weight(sd["decoder.conv_out.weight"], self.device)
@@ -184,10 +185,11 @@ class AutoencoderKL:
 
     # stream value = (fp32 NHWC tensor, row-block channel statistics or None), see unet.py
     def _resnet(self, r, hs, gnws):
-        h, h_st = hs
+        h, h_st = hs[0], hs[1]
+        h_ph = hs[2] if len(hs) > 2 else 0          # 4: statistics written by the four phased upsample GEMMs
         B, H, W = h.shape[:3]
         n1, raw = ops.groupnorm(h, r.g1, r.b1, groups=self.groups, eps=self.eps, silu=True, want_raw=r.shortcut,
-                                partials=gnws, x0_stats=h_st)
+                                partials=gnws, x0_stats=h_st, x0_stats_phases=h_ph)
         t1, _, t1_st = self._gemm(n1, r.w1, mode=ops.A_3X3, bias=r.bias1, want_f32=True, want_stats=True)
         n2, _ = ops.groupnorm(t1.view(B, H, W, r.cout), r.g2, r.b2, groups=self.groups, eps=self.eps, silu=True,
                               partials=gnws, x0_stats=t1_st)
@@ -241,9 +243,20 @@ class AutoencoderKL:
                 h = self._resnet(r, h, gnws)
             if blk.up is not None:
                 ht = h[0]
-                hu = ops.upsample2x(ht)
-                o, _, o_st = self._gemm(hu, blk.up[0], mode=ops.A_3X3, bias=blk.up[1], want_f32=True, want_stats=True)
-                h = (o.view(B, hu.shape[1], hu.shape[2], ht.shape[3]), o_st)
+                Hl, Wl, Cu = ht.shape[1], ht.shape[2], ht.shape[3]
+                if (Hl * Wl) % 32 == 0:   # Upsample2D as four 2x2 convs on the low-resolution tensor (see unet.py)
+                    xb = ops.cast_bf16(ht)
+                    o = torch.empty((B, 2 * Hl, 2 * Wl, Cu), dtype=f32, device=self.device)
+                    o_st = torch.empty((4, B * Hl * Wl // 32, Cu, 2), dtype=f32, device=self.device)
+                    for a in range(2):
+                        for c in range(2):
+                            self._gemm(xb, blk.up[2][a][c], mode=ops.A_2X2, bias=blk.up[1], out_f32=o, stats=o_st,
+                                       tap_off=(a - 1, c - 1), out_phase=(a, c))
+                    h = (o, o_st, 4)
+                else:
+                    hu = ops.upsample2x(ht)
+                    o, _, o_st = self._gemm(hu, blk.up[0], mode=ops.A_3X3, bias=blk.up[1], want_f32=True, want_stats=True)
+                    h = (o.view(B, hu.shape[1], hu.shape[2], Cu), o_st)
             if taps is not None:
                 taps[f"up{i}"] = h[0].permute(0, 3, 1, 2).clone()
         n, _ = ops.groupnorm(h[0], self.out_g, self.out_b, groups=self.groups, eps=self.eps, silu=True, partials=gnws,

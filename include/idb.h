@@ -61,7 +61,11 @@ int idb_num_sms(void);
  * N a multiple of 32.
  * ---------------------------------------------------------------------------------------- */
 enum { IDB_A_1X1 = 0, IDB_A_3X3 = 1, IDB_A_3X3_S2 = 2,
-       IDB_A_3X3_S2_ASYM = 3 /* stride 2 with the (0,1,0,1) right/bottom padding of the VAE encoder's Downsample2D: in(2y+dy, 2x+dx) */ };
+       IDB_A_3X3_S2_ASYM = 3, /* stride 2 with the (0,1,0,1) right/bottom padding of the VAE encoder's Downsample2D: in(2y+dy, 2x+dx) */
+       IDB_A_2X2 = 4          /* 2x2 taps at in(y + dy + tap_off_y, x + dx + tap_off_x), dy, dx in {0,1}, offsets in {-1,0}: one output
+                                 parity class of nearest-2x-upsample + conv3x3 (Upsample2D) evaluated on the LOW-resolution input
+                                 with the 3x3 taps that hit the same input pixel pre-summed (4 GEMMs with K = 4C instead of one
+                                 with K = 9C on the upsampled tensor) */ };
 enum {
   IDB_EPI_GEGLU = 1, /* W rows interleaved in 16-blocks [a(16) | g(16)]; out[:, j] = a_j * gelu_erf(g_j); N_out = N/2 */
   IDB_EPI_GELU = 4,  /* out = gelu_erf(acc + bias) (CLIP text MLP fc1); not combined with GEGLU */
@@ -114,6 +118,13 @@ typedef struct {
   /* optional: per-output-channel PReLU slopes [N], applied after bias / rowvec and before the residual
    * (ArcFace IResNet: bn2 folded into conv1, then nn.PReLU(planes)).  Not combined with GEGLU. */
   const float* prelu;
+  /* IDB_A_2X2 only */
+  int32_t tap_off_x, tap_off_y;
+  /* phased output: out_scale = 2 writes output pixel (y, x) of image b at (2y + out_phase_y, 2x + out_phase_x) of a
+   * [batch, 2*Ho, 2*Wo, N] tensor (and numbers its statistics row blocks per phase: stats_partials is then
+   * [4 phases][ceil(M/32)][N][2], this call filling phase 2*out_phase_y + out_phase_x).  0 / 1 = plain output.
+   * Not combined with residual, split-K or both outputs. */
+  int32_t out_scale, out_phase_x, out_phase_y;
 } idb_gemm_conv_args;
 
 int idb_gemm_conv(const idb_gemm_conv_args* args, void* stream);
@@ -162,6 +173,9 @@ typedef struct {
    * ([hw/32 * batch, C, 2] each).  When given for every source the statistics pass over x is skipped. */
   const float* x0_stats;
   const float* x1_stats;
+  /* 4 when x0 was written by four phased idb_gemm_conv calls (out_scale = 2): x0_stats is then
+   * [4 phases][batch * hw/128][C0][2]; 0 / 1 otherwise */
+  int32_t x0_stats_phases;
 } idb_groupnorm_args;
 int idb_groupnorm(const idb_groupnorm_args* args, void* stream);
 size_t idb_groupnorm_workspace_bytes(int32_t batch, int32_t groups);

@@ -210,6 +210,33 @@ def test_attention_causal_short(ops, cuda_dev):
     assert rel(out.float(), ref) < 6e-3
 
 
+@pytest.mark.parametrize("B,H,W,C", [(8, 32, 32, 640), (8, 16, 16, 1280), (2, 16, 16, 128)])
+def test_upsample_conv_four_phase(ops, cuda_dev, B, H, W, C):
+    """Upsample2D (nearest 2x + conv3x3) as four 2x2 convolutions on the low-resolution tensor, written phase by phase
+    into the full-resolution output; the GroupNorm that follows consumes the phased epilogue statistics."""
+    from faceposegenerator_b200.packing import pack_upsample_phase_weights
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    x = torch.randn(B, H, W, C, device=cuda_dev, generator=g)
+    w = torch.randn(C, C, 3, 3, device=cuda_dev, generator=g) / math.sqrt(9 * C)
+    bias = torch.randn(C, device=cuda_dev, generator=g)
+    wph = pack_upsample_phase_weights(w, device=cuda_dev)
+    xb = ops.cast_bf16(x)
+    out = torch.full((B, 2 * H, 2 * W, C), float("nan"), device=cuda_dev)
+    st = torch.empty((4, B * H * W // 32, C, 2), device=cuda_dev)
+    for a in range(2):
+        for c in range(2):
+            ops.gemm_conv(xb, wph[a][c], mode=ops.A_2X2, bias=bias, out_f32=out, stats=st, tap_off=(a - 1, c - 1), out_phase=(a, c))
+    up = F.interpolate(xb.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w, bias, padding=1).permute(0, 2, 3, 1)
+    assert not torch.isnan(out).any()
+    assert rel(out, ref) < 3e-3, rel(out, ref)          # the pre-summed taps are rounded to bf16 once more than the 3x3 weights
+    gamma = torch.randn(C, device=cuda_dev, generator=g)
+    beta = torch.randn(C, device=cuda_dev, generator=g)
+    y_ph, _ = ops.groupnorm(out, gamma, beta, groups=32, eps=1e-5, silu=True, x0_stats=st, x0_stats_phases=4)
+    y_pl, _ = ops.groupnorm(out, gamma, beta, groups=32, eps=1e-5, silu=True)
+    assert rel(y_ph.float(), y_pl.float()) < 2e-3
+
+
 def test_conv3x3_plus_shortcut_segment(ops, cuda_dev):
     """ResnetBlock2D tail: conv2(h) + conv_shortcut(x) + x-independent bias, as ONE GEMM
     whose K axis is [9*Cout | Cin]."""

@@ -15,8 +15,8 @@ for row in csv.DictReader(lines):
     u = row["Metric Unit"]
     v = v / 1e3 if u in ("ns", "nsecond") else (v * 1e3 if u in ("ms", "msecond") else v)
     launches.append((row["Kernel Name"], row["Grid Size"], v))
-# one forward = the launches from one conv_small_cin_kernel (conv_in) to the next; take the last complete one
-starts = [i for i, l in enumerate(launches) if "conv_small_cin_kernel" in l[0]]
+# one forward = the launches from one latent_operand_kernel (conv_in operand) to the next; take the last complete one
+starts = [i for i, l in enumerate(launches) if "latent_operand_kernel" in l[0]]
 if len(starts) >= 2:
     launches = launches[starts[-2]:starts[-1]]
 print(f"forward segment: {len(launches)} launches, {sum(l[2] for l in launches):.1f} us")
