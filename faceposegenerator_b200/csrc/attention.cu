@@ -258,302 +258,15 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
 }
 
 
-// ---------------------------------------------------------------------------------------- 256-query variant
-// One CTA per SM handles TWO 128-row query tiles (lanes a / b) that share every K_j / V_j tile: the
-// per-SM TMA load traffic per FLOP is half that of two independent 128-row CTAs, and while one
-// lane's warps run the softmax of tile j the tensor core works for the other lane.  S rows are held
-// in registers (ONE tcgen05.ld pass per tile: TMEM read bandwidth is a first-order cost at d = 64),
-// the O accumulator is rescaled lazily (only when a row max outgrows the reference by 2^8), and the
-// scale / subtract / row-sum arithmetic uses packed fp32x2 instructions.
-constexpr int AT2_THREADS = 320;   // warps 0-3: softmax lane a, 4-7: lane b, 8: TMA, 9: MMA
+// ---------------------------------------------------------------------------------------- shared constants of the 256-query kernels
 constexpr int AT2_RING = 4;
-constexpr int AT2_SMEM = 2 * ATT_TILE /*Q*/ + AT2_RING * ATT_TILE + 4 * ATT_TILE /*P a,b*/ + 1024 + 256;
 constexpr int AT2_TMEM_COLS = 512;
-constexpr float AT2_RESCALE_THRESHOLD = 8.0f;
-
-// exp2 on the FMA/ALU pipes (Cody-Waite range reduction + cubic), |rel err| < 5e-4 (P is rounded to
-// bf16 right after).  Optional share of the exponentials (template POLY_MASK); measured on B200 the
-// softmax is issue-bound rather than MUFU-bound, so the default uses the MUFU for all of them.
-__device__ __forceinline__ float exp2_poly(float x) {
-  x = fmaxf(x, -126.0f);
-  const float magic = 12582912.0f;   // 1.5 * 2^23: x + magic rounds x to an integer in the low mantissa bits
-  const float xf = x + magic;
-  const float n = xf - magic;
-  const float f = x - n;             // in [-0.5, 0.5]
-  float pl = fmaf(f, 0.05550410866f, 0.24022650696f);
-  pl = fmaf(pl, f, 0.69314718056f);
-  pl = fmaf(pl, f, 1.0f);
-  return __int_as_float(__float_as_int(pl) + (__float_as_int(xf) << 23));
-}
-
-template <int POLY_MASK, int PACKED>   // PACKED: 0 scalar, 1 ffma2+fadd2, 2 ffma2 only;  elements with (i & mask) == mask take the polynomial exp2: 1 -> 1/2, 3 -> 1/4, 7 -> 1/8, 32 -> none
-__global__ void __launch_bounds__(AT2_THREADS, 1) attention256_kernel(const __grid_constant__ AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                                   // [2][128 x 64]
-  uint8_t* sRing = sQ + 2 * ATT_TILE;
-  uint8_t* sP = sRing + AT2_RING * ATT_TILE;            // [2][128 x 128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATT_TILE);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + AT2_RING;
-  uint64_t* s_full = kv_empty + AT2_RING;   // [2]
-  uint64_t* p_full = s_full + 2;            // [2]
-  uint64_t* o_done = p_full + 2;            // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 2 * ATT_BM;
-  const int head = blockIdx.y;
-  const int b = blockIdx.z;
-  const int n_tiles = p.n_kv_tiles;
-
-  if (warp == 8 && lane == 0) {
-    tma_prefetch_desc(&p.tmQ);
-    tma_prefetch_desc(&p.tmK);
-    tma_prefetch_desc(&p.tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < AT2_RING; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
-    for (int x = 0; x < 2; ++x) {
-      mbar_init(&s_full[x], 1);
-      mbar_init(&p_full[x], 4);
-      mbar_init(&o_done[x], 1);
-    }
-    mbar_fence_init();
-  }
-  if (warp == 9) tmem_alloc<AT2_TMEM_COLS>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_trigger();
-  pdl_wait();   // q / k / v come from the preceding kernels
-  const uint32_t smem_base = smem_u32(smem);
-
-  if (warp == 8) {
-    // ================================================================ TMA producer
-    if (lane == 0) {
-      mbar_expect_tx(q_full, 2 * ATT_TILE);
-      tma_load_3d(sQ, &p.tmQ, q_full, p.col0_q + head * ATT_D, q0, b);
-      tma_load_3d(sQ + ATT_TILE, &p.tmQ, q_full, p.col0_q + head * ATT_D, q0 + ATT_BM, b);
-      for (int i = 0; i < 2 * n_tiles; ++i) {
-        const int slot = i % AT2_RING;
-        const uint32_t ph = (i / AT2_RING) & 1;
-        mbar_wait(&kv_empty[slot], ph ^ 1);
-        mbar_expect_tx(&kv_full[slot], ATT_TILE);
-        const int j = i >> 1;
-        if ((i & 1) == 0)
-          tma_load_3d(sRing + slot * ATT_TILE, &p.tmK, &kv_full[slot], p.col0_k + head * ATT_D, j * ATT_BN, b);
-        else
-          tma_load_3d(sRing + slot * ATT_TILE, &p.tmV, &kv_full[slot], p.col0_v + head * ATT_D, j * ATT_BN, b);
-      }
-    }
-  } else if (warp == 9) {
-    // ================================================================ MMA issuer (convergent loop, elected issue)
-    constexpr uint32_t IDESC_S = umma_idesc_bf16(ATT_BM, ATT_BN, 0, 0);
-    constexpr uint32_t IDESC_O = umma_idesc_bf16(ATT_BM, ATT_D, 0, 1);  // B (= V) is MN-major
-    const uint64_t desc_hi = umma_smem_desc_sw128(0);
-    const uint32_t bar0 = smem_base + 2 * ATT_TILE + AT2_RING * ATT_TILE + 4 * ATT_TILE;   // &bars[0]
-    auto bar_addr = [&](int idx) { return bar0 + idx * 8; };
-    const int I_KVE = 1 + AT2_RING, I_SF = 1 + 2 * AT2_RING, I_OD = I_SF + 4;
-    auto mk = [&](uint32_t addr) { return desc_hi | static_cast<uint64_t>((addr >> 4) & 0x3FFF); };
-
-    auto issue_qk = [&](int x, int j) {   // S_x = Q_x K_j^T
-      const int i = 2 * j, slot = i % AT2_RING;
-      if (x == 0) {
-        mbar_wait(&kv_full[slot], (i / AT2_RING) & 1);
-        tc_fence_after();
-      }
-      const uint64_t qd = mk(smem_base + x * ATT_TILE);
-      const uint64_t kd = mk(smem_base + 2 * ATT_TILE + slot * ATT_TILE);
-      const uint32_t tS = tmem_base + x * 128;
-      if (elect_one()) {
-        umma_bf16(tS, qd, kd, IDESC_S, 0u);
-        umma_bf16(tS, qd + 2, kd + 2, IDESC_S, 1u);
-        umma_bf16(tS, qd + 4, kd + 4, IDESC_S, 1u);
-        umma_bf16(tS, qd + 6, kd + 6, IDESC_S, 1u);
-        umma_commit_a(bar_addr(I_SF + x));
-        if (x == 1) umma_commit_a(bar_addr(I_KVE + slot));   // covers lane a's MMAs on this K tile too
-      }
-      __syncwarp();
-    };
-    auto issue_pv = [&](int x, int j) {   // O_x += P_x V_j
-      const int i = 2 * j + 1, slot = i % AT2_RING;
-      if (x == 0) {
-        mbar_wait(&kv_full[slot], (i / AT2_RING) & 1);
-        tc_fence_after();
-      }
-      const uint32_t pbase = smem_base + 2 * ATT_TILE + AT2_RING * ATT_TILE + x * 2 * ATT_TILE;
-      const uint32_t vbase = smem_base + 2 * ATT_TILE + slot * ATT_TILE;
-      const uint32_t tO = tmem_base + 256 + x * 64;
-      if (elect_one()) {
-#pragma unroll
-        for (int kk = 0; kk < ATT_BN / 16; ++kk) {
-          const uint64_t ad = mk(pbase + (kk >> 2) * ATT_TILE + (kk & 3) * 32);
-          const uint64_t bd = mk(vbase + kk * 2048);
-          umma_bf16(tO, ad, bd, IDESC_O, (j > 0 || kk > 0) ? 1u : 0u);
-        }
-        umma_commit_a(bar_addr(I_OD + x));
-        if (x == 1) umma_commit_a(bar_addr(I_KVE + slot));
-      }
-      __syncwarp();
-    };
-
-    mbar_wait(q_full, 0);
-    tc_fence_after();
-    issue_qk(0, 0);
-    issue_qk(1, 0);
-    for (int j = 0; j < n_tiles; ++j) {
-      for (int x = 0; x < 2; ++x) {
-        mbar_wait(&p_full[x], j & 1);  // P_x(j) staged, S_x consumed, O_x rescaled
-        tc_fence_after();
-        if (j + 1 < n_tiles) issue_qk(x, j + 1);
-        issue_pv(x, j);
-      }
-    }
-  } else {
-    // ================================================================ softmax warps (thread = query row of lane x)
-    const int x = warp >> 2;
-    const int wq = warp & 3;
-    const int r = wq * 32 + lane;
-    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t tS = tmem_base + lane_off + x * 128;
-    const uint32_t tO = tmem_base + lane_off + 256 + x * 64;
-    const float c = p.scale_log2;
-    float m_run = -INFINITY, l_run = 0.f;
-    uint8_t* prow = sP + x * 2 * ATT_TILE + r * 128;
-    const int sw = r & 7;
-
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(&s_full[x], j & 1);
-      tc_fence_after();
-      const int kv_valid = min(ATT_BN, p.Tkv - j * ATT_BN);
-      uint32_t s0[32], s1[32], s2[32], s3[32];
-      IDB_TMEM_LD_X32(tS, s0);
-      IDB_TMEM_LD_X32(tS + 32, s1);
-      IDB_TMEM_LD_X32(tS + 64, s2);
-      IDB_TMEM_LD_X32(tS + 96, s3);
-      tmem_ld_wait();
-      if (kv_valid < ATT_BN) {   // ragged last tile: mask keys >= Tkv (warp-uniform branch)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i >= kv_valid) s0[i] = 0xff800000u;
-          if (32 + i >= kv_valid) s1[i] = 0xff800000u;
-          if (64 + i >= kv_valid) s2[i] = 0xff800000u;
-          if (96 + i >= kv_valid) s3[i] = 0xff800000u;
-        }
-      }
-      float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        m0 = fmaxf(m0, __uint_as_float(s0[i]));
-        m1 = fmaxf(m1, __uint_as_float(s1[i]));
-        m2 = fmaxf(m2, __uint_as_float(s2[i]));
-        m3 = fmaxf(m3, __uint_as_float(s3[i]));
-      }
-      // lazy rescale: the exponent reference m_run only moves when some row of this warp would
-      // otherwise produce P > 2^8; until then O and l need no correction (alpha = 1)
-      const float m_tile = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * c;
-      const bool bump = __any_sync(0xffffffffu, m_tile > m_run + AT2_RESCALE_THRESHOLD);
-      float alpha = 1.0f;
-      if (bump) {
-        const float m_upd = fmaxf(m_run, m_tile);
-        alpha = ex2(m_run - m_upd);   // 0 on the first tile (m_run = -inf)
-        m_run = m_upd;
-        l_run *= alpha;
-      }
-      const float neg_m = -m_run;
-      if (j > 0) {
-        mbar_wait(&o_done[x], (j - 1) & 1);   // PV_x(j-1) retired: O readable, P buffer free
-        tc_fence_after();
-        if (bump) {
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            uint32_t v[32];
-            IDB_TMEM_LD_X32(tO + ch * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-            IDB_TMEM_ST_X32(tO + ch * 32, v);
-          }
-          tmem_st_wait();
-        }
-      }
-      float l0 = 0.f, l1 = 0.f;
-      auto emit = [&](const uint32_t (&sv)[32], int ch) {
-        float pv[32];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {   // masked keys: exp2(-inf) = 0 (MUFU) / 2^-126 (polynomial)
-          float x0, x1;
-          if (PACKED) {
-            ffma2(x0, x1, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]), c, c, neg_m, neg_m);   // one issue slot
-          } else {
-            x0 = fmaf(__uint_as_float(sv[i]), c, neg_m);
-            x1 = fmaf(__uint_as_float(sv[i + 1]), c, neg_m);
-          }
-          pv[i] = ((i & POLY_MASK) == POLY_MASK) ? exp2_poly(x0) : ex2(x0);
-          pv[i + 1] = (((i + 1) & POLY_MASK) == POLY_MASK) ? exp2_poly(x1) : ex2(x1);
-          if (PACKED == 1) fadd2(l0, l1, l0, l1, pv[i], pv[i + 1]);
-          else l0 += pv[i], l1 += pv[i + 1];
-        }
-        uint8_t* base = prow + (ch >> 1) * ATT_TILE;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (ch & 1) * 4 + q;
-          uint4 w = make_uint4(pack_bf16x2(pv[8 * q], pv[8 * q + 1]), pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]),
-                               pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]), pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]));
-          *reinterpret_cast<uint4*>(base + ((chunk ^ sw) << 4)) = w;
-        }
-      };
-      emit(s0, 0);
-      emit(s1, 1);
-      emit(s2, 2);
-      emit(s3, 3);
-      l_run += l0 + l1;
-      fence_proxy_async_smem();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[x]);
-    }
-    mbar_wait(&o_done[x], (n_tiles - 1) & 1);
-    tc_fence_after();
-    const float inv_l = 1.0f / l_run;
-    const int row = q0 + x * ATT_BM + r;
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Tq + row) * p.ld_out + head * ATT_D;
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      uint32_t v[32];
-      IDB_TMEM_LD_X32(tO + ch * 32, v);
-      tmem_ld_wait();
-      if (row < p.Tq) {
-        uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          dst[q] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * q]) * inv_l, __uint_as_float(v[8 * q + 1]) * inv_l),
-                              pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv_l, __uint_as_float(v[8 * q + 3]) * inv_l),
-                              pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv_l, __uint_as_float(v[8 * q + 5]) * inv_l),
-                              pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv_l, __uint_as_float(v[8 * q + 7]) * inv_l));
-      }
-      __syncwarp();
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 9) {
-    tc_fence_after();
-    tmem_dealloc<AT2_TMEM_COLS>(tmem_base);
-  }
-}
-
+constexpr float AT2_RESCALE_THRESHOLD = 8.0f;   // lazy rescale: the exponent reference moves only when P would exceed 2^8
 
 // ---------------------------------------------------------------------------------------- row-split 256-query variant
-// Same tiling as attention256_kernel (two 128-row query tiles x / "lanes" share every K_j / V_j tile), but each
-// query row's 128 scores are split between TWO threads (64 keys each, warps w and w + 4 of the same TMEM lane
+// One CTA per SM handles TWO 128-row query tiles ("lanes" a / b) that share every K_j / V_j tile: the TMA load traffic
+// per FLOP is half that of two independent 128-row CTAs, and while one lane's warps run the softmax of tile j the
+// tensor core works for the other lane.  Each query row's 128 scores are split between TWO threads (64 keys each, warps w and w + 4 of the same TMEM lane
 // quarter), i.e. 16 softmax warps = 4 per SM sub-partition.  With one row per thread the SM sub-partitions saw
 // ~1 runnable warp (the other lane waits for its MMAs) and the 128 live scores spilled; here every thread keeps
 // 64 scores in registers, the pair exchanges its partial row maxima through smem (one 64-thread named barrier
@@ -1129,7 +842,7 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
     configured = true;
   }
   static const int force_variant = getenv("IDB_ATTN_VARIANT") ? atoi(getenv("IDB_ATTN_VARIANT")) : 0;
-  const bool use256 = force_variant ? (force_variant == 256) : (a->t_q >= 1024 && a->t_kv >= 512);
+  const bool use256 = force_variant ? (force_variant == 256) : (a->t_q >= 1024 && a->t_kv >= 512);   // IDB_ATTN_VARIANT: 256 / 128 forces a kernel (profiling)
   if (a->t_kv <= 96 && (force_variant == 0 || p.causal)) {   // short context (cross-attention): K/V resident, chunks of query tiles per CTA
     static bool configured4 = false;
     if (!configured4) {
@@ -1149,7 +862,7 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
     return IDB_OK;
   }
   static const int rs_poly = getenv("IDB_ATTN_RSPOLY") ? atoi(getenv("IDB_ATTN_RSPOLY")) : 3;
-  if (use256 && force_variant != 256) {   // row-split 256-query kernel (16 softmax warps)
+  if (use256) {   // row-split 256-query kernel (16 softmax warps)
     void (*kern)(AttnParams, int, int) = attention_rs_kernel<3>;
     if (rs_poly == 1) kern = attention_rs_kernel<1>;
     else if (rs_poly == 7) kern = attention_rs_kernel<7>;
@@ -1175,30 +888,6 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
     launch_pdl(kern, dim3(static_cast<unsigned>(ctas)), dim3(AT3_THREADS), AT3_SMEM, stream, p, static_cast<int>(n_full), qblocks);
     cudaError_t e3 = cudaGetLastError();
     if (e3 != cudaSuccess) return fail(IDB_E_CUDA, std::string("attention_rs launch: ") + cudaGetErrorString(e3));
-    return IDB_OK;
-  }
-  if (use256) {   // two query tiles per CTA share the K/V stream (long sequences)
-    static const int poly = getenv("IDB_ATTN_POLY") ? atoi(getenv("IDB_ATTN_POLY")) : 7;
-    static const int packed = getenv("IDB_ATTN_PACKED") ? atoi(getenv("IDB_ATTN_PACKED")) : 1;
-    void (*kern)(AttnParams) = attention256_kernel<7, 1>;
-    if (poly == 32 && packed == 0) kern = attention256_kernel<32, 0>;
-    else if (poly == 32 && packed == 1) kern = attention256_kernel<32, 1>;
-    else if (poly == 32) kern = attention256_kernel<32, 2>;
-    else if (poly == 7 && packed == 0) kern = attention256_kernel<7, 0>;
-    else if (poly == 7 && packed == 2) kern = attention256_kernel<7, 2>;
-    else if (poly == 3 && packed == 0) kern = attention256_kernel<3, 0>;
-    else if (poly == 3 && packed == 1) kern = attention256_kernel<3, 1>;
-    else if (poly == 3) kern = attention256_kernel<3, 2>;
-    static bool configured2 = false;
-    if (!configured2) {
-      cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM);
-      if (e2 != cudaSuccess) return fail(IDB_E_CUDA, std::string("cudaFuncSetAttribute(attention256): ") + cudaGetErrorString(e2));
-      configured2 = true;
-    }
-    dim3 grid2((a->t_q + 2 * ATT_BM - 1) / (2 * ATT_BM), a->heads, a->batch);
-    launch_pdl(kern, dim3(grid2), dim3(AT2_THREADS), AT2_SMEM, stream, p);
-    cudaError_t e2 = cudaGetLastError();
-    if (e2 != cudaSuccess) return fail(IDB_E_CUDA, std::string("attention256 launch: ") + cudaGetErrorString(e2));
     return IDB_OK;
   }
   dim3 grid((a->t_q + ATT_BM - 1) / ATT_BM, a->heads, a->batch);
