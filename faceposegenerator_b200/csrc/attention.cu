@@ -294,7 +294,7 @@ __device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float
 }
 
 template <int POLY_MASK>   // pairs (i, i+1) with ((i >> 1) & POLY_MASK) == POLY_MASK take the polynomial exp2: 1 -> 1/2, 3 -> 1/4, 7 -> 1/8, 32 -> none
-__global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __grid_constant__ AttnParams p, int n_full, int qblocks) {
+__global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __grid_constant__ AttnParams p, int n_full, int qblocks, int n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                                   // [2][128 x 64]
@@ -308,23 +308,30 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
   uint64_t* p_full = s_full + 2;            // [2]
   uint64_t* o_done = p_full + 2;            // [2]
   uint64_t* s_free = o_done + 2;            // [2] every softmax warp of the lane has its last S values in registers
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_free + 2);
+  uint64_t* q_empty = s_free + 2;           // the item's last Q K^T has retired: the Q tiles may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
   float* xch_m = reinterpret_cast<float*>(sP + 4 * ATT_TILE + 1024 + 256);   // [parity][x][row][half]
   float* xch_l = xch_m + AT3_XCHG / 4;                                         // [x][row][half] (final row sums)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // 1-D grid: CTAs [0, n_full) take whole 256-query units; the units that would form a partial last wave are split
-  // into two single-lane CTAs each (128 queries, lane b idle), which finish in ~0.6 of a full CTA's time
-  const int lin = blockIdx.x;
-  const bool single = lin >= n_full;
-  const int unit = single ? n_full + ((lin - n_full) >> 1) : lin;
-  const int nl = single ? 1 : 2;                        // active lanes
-  const int qblk = unit % qblocks;
-  const int head = (unit / qblocks) % p.heads;
-  const int b = unit / (qblocks * p.heads);
-  const int q0 = qblk * 2 * ATT_BM + (single ? ((lin - n_full) & 1) * ATT_BM : 0);
+  // Persistent CTAs walk a list of work items (item = blockIdx.x, + gridDim.x, ...): items [0, n_full) are whole
+  // 256-query units; the units that would form a partial last round are split into two single-lane items each
+  // (128 queries, lane b idle), which take ~0.6 of a full item's time.  TMEM, barriers and the K/V ring live across
+  // items, so the launch / allocation / first-load latency is paid once per CTA instead of once per unit.
   const int n_tiles = p.n_kv_tiles;
+  struct Item { bool single; int nl, head, b, q0; };
+  auto decode = [&](int item) {
+    Item t;
+    t.single = item >= n_full;
+    const int unit = t.single ? n_full + ((item - n_full) >> 1) : item;
+    t.nl = t.single ? 1 : 2;
+    const int qblk = unit % qblocks;
+    t.head = (unit / qblocks) % p.heads;
+    t.b = unit / (qblocks * p.heads);
+    t.q0 = qblk * 2 * ATT_BM + (t.single ? ((item - n_full) & 1) * ATT_BM : 0);
+    return t;
+  };
 
   if (warp == 16 && lane == 0) {
     tma_prefetch_desc(&p.tmQ);
@@ -341,6 +348,7 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
       mbar_init(&o_done[x], 1);
       mbar_init(&s_free[x], 8);
     }
+    mbar_init(q_empty, 1);
     mbar_fence_init();
   }
   if (warp == 17) tmem_alloc<AT2_TMEM_COLS>(tmem_slot);
@@ -355,19 +363,24 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
   if (warp == 16) {
     // ================================================================ TMA producer
     if (lane == 0) {
-      mbar_expect_tx(q_full, nl * ATT_TILE);
-      tma_load_3d(sQ, &p.tmQ, q_full, p.col0_q + head * ATT_D, q0, b);
-      if (!single) tma_load_3d(sQ + ATT_TILE, &p.tmQ, q_full, p.col0_q + head * ATT_D, q0 + ATT_BM, b);
-      for (int i = 0; i < 2 * n_tiles; ++i) {
-        const int slot = i % AT2_RING;
-        const uint32_t ph = (i / AT2_RING) & 1;
-        mbar_wait(&kv_empty[slot], ph ^ 1);
-        mbar_expect_tx(&kv_full[slot], ATT_TILE);
-        const int j = i >> 1;
-        if ((i & 1) == 0)
-          tma_load_3d(sRing + slot * ATT_TILE, &p.tmK, &kv_full[slot], p.col0_k + head * ATT_D, j * ATT_BN, b);
-        else
-          tma_load_3d(sRing + slot * ATT_TILE, &p.tmV, &kv_full[slot], p.col0_v + head * ATT_D, j * ATT_BN, b);
+      int gi = 0;   // K / V tiles loaded so far (ring position and phase)
+      for (int item = blockIdx.x, it = 0; item < n_items; item += gridDim.x, ++it) {
+        const Item t = decode(item);
+        if (it > 0) mbar_wait(q_empty, (it - 1) & 1);
+        mbar_expect_tx(q_full, t.nl * ATT_TILE);
+        tma_load_3d(sQ, &p.tmQ, q_full, p.col0_q + t.head * ATT_D, t.q0, t.b);
+        if (!t.single) tma_load_3d(sQ + ATT_TILE, &p.tmQ, q_full, p.col0_q + t.head * ATT_D, t.q0 + ATT_BM, t.b);
+        for (int i = 0; i < 2 * n_tiles; ++i, ++gi) {
+          const int slot = gi % AT2_RING;
+          const uint32_t ph = (gi / AT2_RING) & 1;
+          mbar_wait(&kv_empty[slot], ph ^ 1);
+          mbar_expect_tx(&kv_full[slot], ATT_TILE);
+          const int j = i >> 1;
+          if ((i & 1) == 0)
+            tma_load_3d(sRing + slot * ATT_TILE, &p.tmK, &kv_full[slot], p.col0_k + t.head * ATT_D, j * ATT_BN, t.b);
+          else
+            tma_load_3d(sRing + slot * ATT_TILE, &p.tmV, &kv_full[slot], p.col0_v + t.head * ATT_D, j * ATT_BN, t.b);
+        }
       }
     }
   } else if (warp == 17) {
@@ -380,8 +393,11 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
     const int I_KVE = 1 + AT2_RING, I_SF = 1 + 2 * AT2_RING, I_OD = I_SF + 4;
     auto mk = [&](uint32_t addr) { return desc_hi | static_cast<uint64_t>((addr >> 4) & 0x3FFF); };
 
+    int gbase = 0;          // K / V tiles consumed by previous items
+    int nl = 2;             // active lanes of the current item
+    uint32_t gj[2] = {0, 0};   // tiles processed so far per lane (barrier phases)
     auto issue_qk = [&](int x, int j) {   // S_x = Q_x K_j^T
-      const int i = 2 * j, slot = i % AT2_RING;
+      const int i = gbase + 2 * j, slot = i % AT2_RING;
       if (x == 0) {
         mbar_wait(&kv_full[slot], (i / AT2_RING) & 1);
         tc_fence_after();
@@ -400,7 +416,7 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
       __syncwarp();
     };
     auto issue_pv = [&](int x, int j) {   // O_x += P_x V_j
-      const int i = 2 * j + 1, slot = i % AT2_RING;
+      const int i = gbase + 2 * j + 1, slot = i % AT2_RING;
       if (x == 0) {
         mbar_wait(&kv_full[slot], (i / AT2_RING) & 1);
         tc_fence_after();
@@ -421,24 +437,37 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
       __syncwarp();
     };
 
-    mbar_wait(q_full, 0);
-    tc_fence_after();
-    issue_qk(0, 0);
-    if (!single) issue_qk(1, 0);
-    for (int j = 0; j < n_tiles; ++j) {
+    for (int item = blockIdx.x, it = 0; item < n_items; item += gridDim.x, ++it) {
+      const Item t = decode(item);
+      nl = t.nl;
+      mbar_wait(q_full, it & 1);
+      tc_fence_after();
       for (int x = 0; x < nl; ++x) {
-        // S_x(j) is in the softmax warps' registers about half-way through their tile: the next Q K^T overlaps the rest
-        if (j + 1 < n_tiles) {
-          mbar_wait(&s_free[x], j & 1);
+        if (gj[x] > 0) {   // the lane's previous item: its last scores must be out of TMEM before S_x is overwritten
+          mbar_wait(&s_free[x], (gj[x] - 1) & 1);
           tc_fence_after();
-          issue_qk(x, j + 1);
         }
-        mbar_wait(&p_full[x], j & 1);  // P_x(j) staged, O_x rescaled
-        tc_fence_after();
-        issue_pv(x, j);
+        issue_qk(x, 0);
+        if (n_tiles == 1 && x == nl - 1 && elect_one()) umma_commit_a(bar_addr(I_SF + 8));   // q_empty
       }
+      for (int j = 0; j < n_tiles; ++j) {
+        for (int x = 0; x < nl; ++x) {
+          // S_x(j) is in the softmax warps' registers about half-way through their tile: the next Q K^T overlaps the rest
+          if (j + 1 < n_tiles) {
+            mbar_wait(&s_free[x], (gj[x] + j) & 1);
+            tc_fence_after();
+            issue_qk(x, j + 1);
+            if (j + 2 == n_tiles && x == nl - 1 && elect_one()) umma_commit_a(bar_addr(I_SF + 8));   // q_empty: last Q K^T of the item
+          }
+          mbar_wait(&p_full[x], (gj[x] + j) & 1);  // P_x(j) staged, O_x rescaled
+          tc_fence_after();
+          issue_pv(x, j);
+        }
+      }
+      for (int x = 0; x < nl; ++x) gj[x] += n_tiles;
+      gbase += 2 * n_tiles;
     }
-  } else if (!single || warp < 8) {
+  } else {
     // ================================================================ softmax warps (two threads per query row)
     const int x = warp >> 3;            // query tile ("lane") of the CTA
     const int wq = warp & 3;            // TMEM lane quarter (= warp % 4)
@@ -449,12 +478,15 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
     const uint32_t tO = tmem_base + lane_off + 256 + x * 64 + hs * 32;
     const float c = p.scale_log2;
     const int pair_id = 1 + x * 4 + wq;
-    float m_run = -INFINITY, l_run = 0.f;
     uint8_t* prow = sP + x * 2 * ATT_TILE + hs * ATT_TILE + r * 128;   // this thread's 64 keys = k-atom hs of row r
     const int sw = r & 7;
+    uint32_t gj = 0;   // tiles this lane has processed so far (barrier phases)
 
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(&s_full[x], j & 1);
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    if (item >= n_full && x == 1) continue;   // lane b idles through single-lane items
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j, ++gj) {
+      mbar_wait(&s_full[x], gj & 1);
       tc_fence_after();
       const int kv_valid = min(ATT_BN, p.Tkv - j * ATT_BN) - hs * 64;   // my keys < kv_valid are real
       // pass 1: row maximum of my 64 scores (they are re-read from TMEM for pass 2: keeping them would spill)
@@ -478,7 +510,7 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
         }
       }
       // exchange the partial row maxima with the thread that owns the row's other 64 keys
-      float* xm = xch_m + (((j & 1) * 2 + x) * 128 + r) * 2;
+      float* xm = xch_m + (((gj & 1) * 2 + x) * 128 + r) * 2;
       const float m_loc = fmaxf(m0, m1);
       xm[hs] = m_loc;
       pair_barrier(pair_id);
@@ -495,7 +527,7 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
       }
       const float neg_m = -m_run;
       if (j > 0) {
-        mbar_wait(&o_done[x], (j - 1) & 1);   // PV_x(j-1) retired: O readable, P buffer free
+        mbar_wait(&o_done[x], (gj - 1) & 1);   // PV_x(j-1) retired: O readable, P buffer free
         tc_fence_after();
         if (bump) {   // my 32 of the row's 64 O columns
           uint32_t v[32];
@@ -556,10 +588,11 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
     xl[hs] = l_run;
     pair_barrier(pair_id);
     const float inv_l = 1.0f / (l_run + xl[hs ^ 1]);
-    mbar_wait(&o_done[x], (n_tiles - 1) & 1);
+    mbar_wait(&o_done[x], (gj - 1) & 1);
     tc_fence_after();
-    const int row = q0 + x * ATT_BM + r;
-    __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Tq + row) * p.ld_out + head * ATT_D + hs * 32;
+    const Item t = decode(item);   // decoded here, not before the tile loop: nothing item-specific is live across it
+    const int row = t.q0 + x * ATT_BM + r;
+    __nv_bfloat16* orow = p.out + (static_cast<long long>(t.b) * p.Tq + row) * p.ld_out + t.head * ATT_D + hs * 32;
     {
       uint32_t v[32];
       IDB_TMEM_LD_X32(tO, v);
@@ -574,6 +607,8 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
                               pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv_l, __uint_as_float(v[8 * q + 7]) * inv_l));
       }
     }
+    tc_fence_before();   // the O reads above precede the next item's first P V (ordered through p_full)
+    }   // items
   }
 
   tc_fence_before();
@@ -863,13 +898,13 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
   }
   static const int rs_poly = getenv("IDB_ATTN_RSPOLY") ? atoi(getenv("IDB_ATTN_RSPOLY")) : 3;
   if (use256) {   // row-split 256-query kernel (16 softmax warps)
-    void (*kern)(AttnParams, int, int) = attention_rs_kernel<3>;
+    void (*kern)(AttnParams, int, int, int) = attention_rs_kernel<3>;
     if (rs_poly == 1) kern = attention_rs_kernel<1>;
     else if (rs_poly == 7) kern = attention_rs_kernel<7>;
     else if (rs_poly == 32) kern = attention_rs_kernel<32>;
     static bool configured3 = false;
     if (!configured3) {
-      void (*all[4])(AttnParams, int, int) = {attention_rs_kernel<1>, attention_rs_kernel<3>, attention_rs_kernel<7>, attention_rs_kernel<32>};
+      void (*all[4])(AttnParams, int, int, int) = {attention_rs_kernel<1>, attention_rs_kernel<3>, attention_rs_kernel<7>, attention_rs_kernel<32>};
       for (int i = 0; i < 4; ++i) {
         cudaError_t e3 = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM);
         if (e3 != cudaSuccess) return fail(IDB_E_CUDA, std::string("cudaFuncSetAttribute(attention_rs): ") + cudaGetErrorString(e3));
@@ -884,8 +919,11 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
     static const int split_tail = getenv("IDB_ATTN_TAILSPLIT") ? atoi(getenv("IDB_ATTN_TAILSPLIT")) : 1;
     const long long rem = units % sms;
     if (split_tail && units > sms && rem != 0 && 2 * rem <= sms && a->t_q % (2 * ATT_BM) == 0) n_full = units - rem;
-    const long long ctas = n_full + 2 * (units - n_full);
-    launch_pdl(kern, dim3(static_cast<unsigned>(ctas)), dim3(AT3_THREADS), AT3_SMEM, stream, p, static_cast<int>(n_full), qblocks);
+    const long long items = n_full + 2 * (units - n_full);
+    static const int persistent = getenv("IDB_ATTN_PERSISTENT") ? atoi(getenv("IDB_ATTN_PERSISTENT")) : 1;
+    const long long ctas = (persistent && items > sms) ? sms : items;   // persistent CTAs walk the item list
+    launch_pdl(kern, dim3(static_cast<unsigned>(ctas)), dim3(AT3_THREADS), AT3_SMEM, stream, p, static_cast<int>(n_full), qblocks,
+               static_cast<int>(items));
     cudaError_t e3 = cudaGetLastError();
     if (e3 != cudaSuccess) return fail(IDB_E_CUDA, std::string("attention_rs launch: ") + cudaGetErrorString(e3));
     return IDB_OK;

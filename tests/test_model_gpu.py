@@ -3,11 +3,13 @@
 Tolerances are the north-star ones: per-step latent rel-L2 <= 1e-2 (bf16 operands),
 decoded-image PSNR >= 35 dB."""
 import math
+import os
 
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def rel(a, b):
@@ -136,6 +138,20 @@ def test_pipeline_teacher_forced_and_free_running(world):
     drift = [rel(free[i], ref_l[i + 1]) for i in range(30)]
     print("free-running latent rel-L2: final %.3e max %.3e" % (drift[-1], max(drift)))
     assert drift[-1] < 5e-2
+
+
+def test_clip_text_encoder_vs_transformers_golden(cuda_dev):
+    """The CLIP-H text tower on the sm_100a kernels against outputs of transformers' own `CLIPTextModel`
+    (tests/golden/clip_text_golden.pt, made by tests/golden/make_clip_text_golden.py) on the same keyed weights and ids."""
+    from faceposegenerator_b200.text import CLIPTextEncoder, text_manifest
+    from faceposegenerator_b200.weights import random_state_dict
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "clip_text_golden.pt"))
+    enc = CLIPTextEncoder(random_state_dict(text_manifest(), 0), cuda_dev)
+    assert torch.equal(enc.tokenizer(gold["prompts"]), gold["ids"])
+    out = enc.forward_ids(gold["ids"]).float().cpu()
+    e = rel(out, gold["last_hidden_state"])
+    print(f"clip text vs transformers rel-L2 {e:.3e}")
+    assert e < 1e-2   # bf16 operands, fp32 residual stream (north_star tolerance for bf16)
 
 
 def test_clip_text_encoder_vs_torch_fp32(cuda_dev):

@@ -258,7 +258,9 @@ def test_conv3x3_plus_shortcut_segment(ops, cuda_dev):
 # ------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,heads,Tq,Tkv", [(2, 5, 4096, 4096), (2, 10, 1024, 1024), (2, 20, 256, 256), (3, 20, 64, 64),
                                             (2, 5, 4096, 77), (1, 20, 64, 77), (1, 2, 200, 333), (8, 10, 1024, 77),
-                                            (8, 20, 256, 77), (2, 3, 300, 50), (2, 3, 700, 96), (1, 2, 130, 16)])
+                                            (8, 20, 256, 77), (2, 3, 300, 50), (2, 3, 700, 96), (1, 2, 130, 16),
+                                            # more work items than SMs: the persistent row-split kernel walks several items per CTA
+                                            (8, 10, 1024, 1024), (4, 5, 2304, 1000), (6, 5, 1100, 1024)])
 def test_attention(ops, cuda_dev, B, heads, Tq, Tkv):
     C = heads * 64
     g = torch.Generator(device="cuda").manual_seed(Tq + Tkv)

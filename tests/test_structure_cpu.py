@@ -150,6 +150,22 @@ def test_iresnet_oracle_vs_reference_golden():
     assert torch.allclose(y, gold["embedding"], rtol=1e-4, atol=1e-3 * float(gold["embedding"].abs().mean()))
 
 
+def test_clip_text_oracle_vs_transformers_golden():
+    """PINNED: oracle/clip_text.py against outputs of transformers' own `CLIPTextModel` with the SD2.1-base text config
+    (fixture made by tests/golden/make_clip_text_golden.py; weights regenerated from key names, ids from the fixture)."""
+    from faceposegenerator_b200.text import text_manifest
+    from faceposegenerator_b200.weights import random_state_dict
+    from oracle.clip_text import clip_text_forward
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "clip_text_golden.pt"))
+    sd = random_state_dict(text_manifest(), 0)
+    assert sum(v.numel() for v in sd.values()) == gold["n_params"] == 340_387_840
+    y = clip_text_forward(sd, gold["ids"])
+    ref = gold["last_hidden_state"]
+    e = float((y - ref).norm() / ref.norm())
+    assert e < 2e-5, e
+    assert torch.allclose(y, ref, atol=2e-4)
+
+
 def test_lora_file_round_trip(tmp_path):
     from faceposegenerator_b200 import weights as w
     lora = w.random_lora(seed=5)
