@@ -2,6 +2,7 @@
 // time embedding, edge convolutions (tiny Cin / tiny Cout), nearest-2x upsample, casts and the
 // fused CFG + DDPMScheduler.step.  All vectorised (16 B per thread per access where the layout
 // allows), coalesced along the NHWC channel axis, fp32 math.
+#include <cstdlib>
 #include <string>
 
 #include "../../include/idb.h"
@@ -18,6 +19,8 @@ namespace idb {
 
 constexpr int GN_MAX_CHUNKS = 256;
 constexpr int GN_MAX_GROUPS = 64;
+constexpr int GN_FUSE_MAX_RB = 8;     // fused finalize: at most 8 row blocks (256 pixels) per image ...
+constexpr int GN_FUSE_MAX_CQ = 640;   // ... and at most 2560 channels (one thread per channel quad)
 
 // ---------------------------------------------------------------------------------------- GroupNorm
 struct GnParams {
@@ -34,6 +37,10 @@ struct GnParams {
   float* partials;  // [B, nchunks, groups, 2]
   float* stats;     // [B, groups, 2] = (mean, rstd), written by the last stats CTA of each image
   unsigned int* counters;  // [B] arrival tickets (zero on entry, reset to zero by the last CTA)
+  // fused finalize (small rasters): the apply CTAs reduce the producers' row-block channel sums themselves
+  const float2* rb0;   // non-null selects the fused path; [row block][c0] (sum, sum of squares) of source 0
+  const float2* rb1;   // same for source 1
+  int rbpi, phases0;   // row blocks per image (<= GN_FUSE_MAX_RB), phased layout of source 0 (see gn_finalize_kernel)
 };
 
 __device__ __forceinline__ float4 gn_load(const GnParams& p, int b, int pix, int cq) {
@@ -195,12 +202,67 @@ __device__ __forceinline__ void gn_emit(const GnParams& p, int b, int pix, int c
   if (p.out_raw) *reinterpret_cast<uint2*>(p.out_raw + o) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
 }
 
-__global__ void gn_apply_kernel(const GnParams p) {
+__global__ void __launch_bounds__(1024) gn_apply_kernel(const GnParams p) {
   pdl_trigger();
   pdl_wait();
   __shared__ float g_mean[GN_MAX_GROUPS], g_rstd[GN_MAX_GROUPS];
+  __shared__ double f_s[GN_FUSE_MAX_CQ], f_ss[GN_FUSE_MAX_CQ];
   const int chunk = blockIdx.x, b = blockIdx.y;
-  if (threadIdx.x < p.groups) {
+  if (p.rb0 != nullptr) {
+    // Fused finalize (rasters of <= 256 pixels: the row-block sums of an image are a few KB, so every CTA reduces
+    // them itself instead of waiting for a separate tiny kernel).  Thread t owns channels 4t .. 4t+3 (one group,
+    // cpg % 4 == 0); all its loads are issued before the first use; fixed summation order -> deterministic.
+    const int t = threadIdx.x;
+    if (t < p.CQ) {
+      const int c = 4 * t;
+      const long long row0 = static_cast<long long>(b) * p.rbpi;
+      const int rbl = p.phases0 > 1 ? p.rbpi / p.phases0 : p.rbpi;
+      auto src_of = [&](int rb) -> const float4* {
+        const float2* src;
+        if (c >= p.c0) {
+          src = p.rb1 + (row0 + rb) * p.c1 + (c - p.c0);
+        } else if (p.phases0 <= 1) {
+          src = p.rb0 + (row0 + rb) * p.c0 + c;
+        } else {   // [phase][image][row block of the low-resolution raster]
+          const int ph = rb / rbl, r2 = rb - ph * rbl;
+          src = p.rb0 + ((static_cast<long long>(ph) * gridDim.y + b) * rbl + r2) * p.c0 + c;
+        }
+        return reinterpret_cast<const float4*>(src);   // [0] = (s, ss) of channels c, c + 1; [1] = c + 2, c + 3
+      };
+      double s = 0.0, ss = 0.0;
+      for (int rb0 = 0; rb0 < p.rbpi; rb0 += 4) {   // four row blocks = eight 16-byte loads in flight
+        float4 va[4], vb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          va[i] = vb[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rb0 + i < p.rbpi) {
+            const float4* src = src_of(rb0 + i);
+            va[i] = src[0];
+            vb[i] = src[1];
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          s += (static_cast<double>(va[i].x) + va[i].z) + (static_cast<double>(vb[i].x) + vb[i].z);
+          ss += (static_cast<double>(va[i].y) + va[i].w) + (static_cast<double>(vb[i].y) + vb[i].w);
+        }
+      }
+      f_s[t] = s;
+      f_ss[t] = ss;
+    }
+    __syncthreads();
+    if (t < p.groups) {
+      const int nq = p.cpg >> 2, q0 = t * nq;
+      double ts = 0.0, tss = 0.0;
+      for (int q = 0; q < nq; ++q) ts += f_s[q0 + q], tss += f_ss[q0 + q];
+      const double n = static_cast<double>(p.hw) * p.cpg;
+      const double mean = ts / n;
+      double var = tss / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      g_mean[t] = static_cast<float>(mean);
+      g_rstd[t] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+    }
+  } else if (threadIdx.x < p.groups) {
     const float2 st = *reinterpret_cast<const float2*>(p.stats + (static_cast<long long>(b) * p.groups + threadIdx.x) * 2);
     g_mean[threadIdx.x] = st.x;
     g_rstd[threadIdx.x] = st.y;
@@ -688,9 +750,19 @@ extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
   p.x0 = a->x0, p.x1 = a->x1, p.c0 = a->c0, p.c1 = a->x1 ? a->c1 : 0, p.C = C, p.CQ = C / 4;
   p.PY = p.CQ >= 256 ? 1 : 256 / p.CQ;
   p.hw = a->hw, p.groups = a->groups, p.cpg = C / a->groups, p.eps = a->eps;
+  const bool have_stats = a->x0_stats != nullptr && (a->x1 == nullptr || a->x1_stats != nullptr) && a->hw % 32 == 0 &&
+                          (a->x0_stats_phases <= 1 || (a->x0_stats_phases == 4 && a->hw % 128 == 0));
+  // small rasters: the apply CTAs finalize the statistics themselves (one launch instead of two).  Measured on the UNet
+  // step (B = 8, same box): 8x8 rasters only (2 row blocks) 8.851 -> 8.745 ms; extending it to 16x16 (8 row blocks,
+  // 164 KB of sums re-read per CTA at 2560 channels) gives the gain back, so the default stops at 2.
+  // IDB_GN_FUSE_RB = 0 disables, up to GN_FUSE_MAX_RB widens.
+  static const int fuse_rb = getenv("IDB_GN_FUSE_RB") ? atoi(getenv("IDB_GN_FUSE_RB")) : 2;
+  const bool fused = have_stats && p.PY == 1 && p.cpg % 4 == 0 && p.CQ <= GN_FUSE_MAX_CQ && p.CQ >= a->groups &&
+                     a->hw / 32 <= fuse_rb && a->hw / 32 <= GN_FUSE_MAX_RB;
   // pixels per CTA: enough for >= 4 unrolled rounds of PY rows, while keeping >= ~4 CTAs per SM in flight
   int ppc = 16 * p.PY;
   while (ppc > 4 * p.PY && static_cast<long long>(a->batch) * ((a->hw + ppc - 1) / ppc) < 4LL * num_sms()) ppc /= 2;
+  if (fused && ppc < 2 * (a->hw / 32)) ppc = 2 * (a->hw / 32);   // every CTA re-reads the image's row-block sums: keep that below its own pixel traffic
   int nchunks = (a->hw + ppc - 1) / ppc;
   if (nchunks > GN_MAX_CHUNKS) nchunks = GN_MAX_CHUNKS;
   p.pix_per_chunk = (a->hw + nchunks - 1) / nchunks;
@@ -705,9 +777,11 @@ extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
   threads = (threads + 31) / 32 * 32;
   if (threads < 64) threads = 64;  // the apply kernel's first `groups` threads publish mean / rstd
   dim3 grid(p.nchunks, a->batch);
-  const bool have_stats = a->x0_stats != nullptr && (a->x1 == nullptr || a->x1_stats != nullptr) && a->hw % 32 == 0 &&
-                          (a->x0_stats_phases <= 1 || (a->x0_stats_phases == 4 && a->hw % 128 == 0));
-  if (have_stats) {   // statistics already produced by the GEMM epilogues of the sources
+  p.rb0 = p.rb1 = nullptr, p.rbpi = a->hw / 32, p.phases0 = a->x0_stats_phases;
+  if (fused) {
+    p.rb0 = reinterpret_cast<const float2*>(a->x0_stats);
+    p.rb1 = reinterpret_cast<const float2*>(a->x1_stats);
+  } else if (have_stats) {   // statistics already produced by the GEMM epilogues of the sources
     launch_pdl(gn_finalize_kernel, dim3(dim3(a->groups, a->batch)), dim3(256), 0, stream, 
         reinterpret_cast<const float2*>(a->x0_stats), p.c0, reinterpret_cast<const float2*>(a->x1_stats), p.c1,
         a->hw / 32, p.cpg, a->hw, a->eps, p.stats, a->x0_stats_phases);

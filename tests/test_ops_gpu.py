@@ -210,7 +210,8 @@ def test_attention_causal_short(ops, cuda_dev):
     assert rel(out.float(), ref) < 6e-3
 
 
-@pytest.mark.parametrize("B,H,W,C", [(8, 32, 32, 640), (8, 16, 16, 1280), (2, 16, 16, 128)])
+@pytest.mark.parametrize("B,H,W,C", [(8, 32, 32, 640), (8, 16, 16, 1280), (2, 16, 16, 128),
+                                     (4, 8, 8, 1280)])   # 16x16 output: the GroupNorm finalizes the phased statistics inside its apply kernel
 def test_upsample_conv_four_phase(ops, cuda_dev, B, H, W, C):
     """Upsample2D (nearest 2x + conv3x3) as four 2x2 convolutions on the low-resolution tensor, written phase by phase
     into the full-resolution output; the GroupNorm that follows consumes the phased epilogue statistics."""
@@ -409,7 +410,9 @@ def test_cfg_ddpm_step_vs_oracle(ops, cuda_dev, use_cfg, vpred):
 
 
 @pytest.mark.parametrize("B,H,W,C0,C1,N", [(2, 64, 64, 320, 0, 320), (3, 8, 8, 1280, 1280, 1280), (2, 32, 32, 640, 320, 640),
-                                           (1, 256, 256, 128, 0, 128)])
+                                           (1, 256, 256, 128, 0, 128),
+                                           # rasters of <= 256 pixels: statistics finalized inside the apply kernel
+                                           (2, 16, 16, 1280, 640, 1280), (8, 16, 16, 1280, 0, 1280), (2, 8, 8, 1280, 0, 1280)])
 def test_groupnorm_from_epilogue_statistics(ops, cuda_dev, B, H, W, C0, C1, N):
     """GroupNorm fed by the row-block channel sums that the producing conv GEMM wrote in its epilogue
     (no statistics pass over the tensor) == GroupNorm that reads the tensor itself."""
