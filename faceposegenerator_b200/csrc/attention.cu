@@ -753,12 +753,20 @@ __global__ void __launch_bounds__(ATX_THREADS, 2) attention_x_kernel(const __gri
       float m = -INFINITY;
       // keys this query row may see: [0, kmax) -- the context length, or the row's own position under a causal mask
       const int kmax = p.causal ? min(p.Tkv, (qt0 + i) * ATT_BM + r + 1) : p.Tkv;
+      if (!p.causal && p.Tkv > 64) {   // the UNet's cross-attention (77 keys): only the third chunk has masked columns
 #pragma unroll
-      for (int k = 0; k < 32; ++k) {
-        if (k >= kmax) s0[k] = 0xff800000u;
-        if (32 + k >= kmax) s1[k] = 0xff800000u;
-        if (nkv <= 64 || 64 + k >= kmax) s2[k] = 0xff800000u;
-        m = fmaxf(m, fmaxf(__uint_as_float(s0[k]), fmaxf(__uint_as_float(s1[k]), __uint_as_float(s2[k]))));
+        for (int k = 0; k < 32; ++k) {
+          if (64 + k >= kmax) s2[k] = 0xff800000u;
+          m = fmaxf(m, fmaxf(__uint_as_float(s0[k]), fmaxf(__uint_as_float(s1[k]), __uint_as_float(s2[k]))));
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          if (k >= kmax) s0[k] = 0xff800000u;
+          if (32 + k >= kmax) s1[k] = 0xff800000u;
+          if (nkv <= 64 || 64 + k >= kmax) s2[k] = 0xff800000u;
+          m = fmaxf(m, fmaxf(__uint_as_float(s0[k]), fmaxf(__uint_as_float(s1[k]), __uint_as_float(s2[k]))));
+        }
       }
       const float neg_m = -m * c;
       float l = 0.f;
@@ -781,7 +789,23 @@ __global__ void __launch_bounds__(ATX_THREADS, 2) attention_x_kernel(const __gri
       };
       emit(s0, 0);
       emit(s1, 1);
-      if (nkv > 64) emit(s2, 2);
+      if (nkv == 80) {   // 77 keys: the P V product reads 80 columns, so only 16 more exponentials (2 of the 4 smem chunks)
+        float pv[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          pv[k] = ex2(fmaf(__uint_as_float(s2[k]), c, neg_m));
+          l += pv[k];
+        }
+        uint8_t* base = prow + ATT_TILE;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          uint4 w = make_uint4(pack_bf16x2(pv[8 * q], pv[8 * q + 1]), pack_bf16x2(pv[8 * q + 2], pv[8 * q + 3]),
+                               pack_bf16x2(pv[8 * q + 4], pv[8 * q + 5]), pack_bf16x2(pv[8 * q + 6], pv[8 * q + 7]));
+          *reinterpret_cast<uint4*>(base + ((q ^ sw) << 4)) = w;
+        }
+      } else if (nkv > 64) {
+        emit(s2, 2);
+      }
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();

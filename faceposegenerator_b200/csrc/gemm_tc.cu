@@ -1057,7 +1057,8 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
       // tiny-M layers (8x8 latents) run split-K anyway: with dual-N tiles each split streams the weights once per
       // 256 rows instead of once per 128-column tile
       const bool splitk_regime = !phased && a->k_splits == 0 && a->workspace && tiles1 * 2 <= units && p.nkb0 + p.nkb1 >= 64;   // (split anyway)
-      if (force_dual == 1 || (p.nkb0 + p.nkb1 >= 32 && cost < cost1) || splitk_regime) dual = true, block_n = 160;
+      static const int dual_min_kb = env_int("IDB_GEMM_DUAL_MINKB", 32);   // smallest K (in 64-wide blocks) that takes dual-N tiles
+      if (force_dual == 1 || (p.nkb0 + p.nkb1 >= dual_min_kb && cost < cost1) || splitk_regime) dual = true, block_n = 160;
     }
   }
   p.n_tiles_n = (a->n + block_n * (dual ? 2 : 1) - 1) / (block_n * (dual ? 2 : 1));
