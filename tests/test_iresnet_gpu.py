@@ -80,6 +80,24 @@ def test_crop_resize_norm_vs_torch(ops, cuda_dev):
         assert rel(got, ref) < 4e-3
 
 
+def test_crop_resize_norm_vs_reference_golden(ops, cuda_dev):
+    """`idb_crop_resize_norm` against outputs of the reference's own glue functions (train_ID-Booth.py:433-455,1090;
+    tests/golden/arcface_glue_golden.pt): decoded image -> [0, 1] NHWC (the VAE's fused post-process) -> crop + bilinear
+    112 x 112 + normalise in one kernel."""
+    import os
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "arcface_glue_golden.pt"))
+    for k, (seed, size, bbox) in enumerate(gold["cases"]):
+        dec = torch.rand(1, 3, size, size, generator=torch.Generator().manual_seed(seed)) * 2.4 - 1.2
+        img01 = (dec / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1).contiguous()
+        out = ops.crop_resize_norm(img01.to(cuda_dev), torch.tensor([bbox], dtype=torch.int32, device=cuda_dev),
+                                   size=112, c_pad=64).float().cpu()
+        got = out[0, :, :, :3].permute(2, 0, 1)
+        want = gold["arcface_inputs"][k]
+        if want.shape[-1] != 112:
+            got = got[:, ::4, ::4]
+        assert float((got - want).abs().max()) < 1e-2 and rel(got, want) < 4e-3   # bf16 output rounding on [-1, 1]
+
+
 def test_channel_affine(ops, cuda_dev):
     g = torch.Generator(device="cuda").manual_seed(5)
     x = torch.randn(3, 14, 14, 256, device=cuda_dev, generator=g)

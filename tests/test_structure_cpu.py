@@ -166,6 +166,24 @@ def test_clip_text_oracle_vs_transformers_golden():
     assert torch.allclose(y, ref, atol=2e-4)
 
 
+def _decoded_image(seed, size):   # same seeded stand-in for `vae.decode(z).sample` as tests/golden/make_arcface_glue_golden.py
+    return torch.rand(1, 3, size, size, generator=torch.Generator().manual_seed(seed)) * 2.4 - 1.2
+
+
+def test_arcface_glue_oracle_vs_reference_golden():
+    """PINNED: oracle/arcface_glue.py against outputs of the reference's own `latents_to_image_for_mtcnn` /
+    `cropped_image_to_arcface_input` (train_ID-Booth.py:433-455) and its bbox crop (`:1090`)."""
+    from oracle.arcface_glue import crop_to_arcface_input, decoded_to_mtcnn_image
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "arcface_glue_golden.pt"))
+    for k, (seed, size, bbox) in enumerate(gold["cases"]):
+        img = decoded_to_mtcnn_image(_decoded_image(seed, size))
+        assert torch.equal(img[::16, ::16], gold["mtcnn_image_slices"][k])
+        x = crop_to_arcface_input(img, bbox)[0]
+        want = gold["arcface_inputs"][k]
+        got = x if want.shape[-1] == 112 else x[:, ::4, ::4]
+        assert torch.allclose(got, want, atol=1e-6), float((got - want).abs().max())
+
+
 def test_lora_file_round_trip(tmp_path):
     from faceposegenerator_b200 import weights as w
     lora = w.random_lora(seed=5)
