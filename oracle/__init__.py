@@ -12,9 +12,13 @@ tests or golden vectors.  The restatement follows the
 published diffusers 0.32.2 semantics and is pinned only by
 self-made anchors: exact parameter counts (865,910,724 / 49,490,199), the
 closed-form scheduler known answers (App. C), metamorphic identities (merged
-LoRA == unmerged LoRA in fp64, ...), and -- for the one model that *is* in the
-reference tree -- IResNet-100 outputs generated by importing
-`/root/reference/ArcFace_files/backbones/iresnet.py` (tests/golden/).
+LoRA == unmerged LoRA in fp64, ...).  That statement covers oracle/sd21.py (UNet, VAE,
+scheduler, pipeline loop).  The pieces that CAN be checked against reference code run in
+this container are PINNED by golden vectors under tests/golden/ (each with its generating
+script): oracle/iresnet.py against `/root/reference/ArcFace_files/backbones/iresnet.py`,
+oracle/arcface_glue.py against the glue functions of `/root/reference/train_ID-Booth.py:433-455`,
+oracle/clip_text.py against transformers' own `CLIPTextModel`, and the caller-side host logic
+(faceposegenerator_b200/sweep.py) against a log of `/root/reference/inference_ID-Booth.py` itself.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this package, and there only as the checker / the

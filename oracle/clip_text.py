@@ -1,8 +1,9 @@
 """TEST INFRASTRUCTURE ONLY -- fp32 restatement of the CLIP text tower of SD2.1 (OpenCLIP ViT-H text encoder as exposed by
 transformers `CLIPTextModel`: pre-LN blocks, causal self-attention, erf-GELU MLP, final LayerNorm; SURVEY App. A.0;
 reference call site `encode_prompt` behind `inference_ID-Booth.py:138`, in-tree twin `train_ID-Booth.py:457-491`).
-PARITY UNPINNED: transformers 4.34 / the SD2.1 text weights are not available offline; this is the plain-torch
-formulation of the published architecture that tests compare the CUDA path against on the same random-init weights."""
+PINNED: checked against outputs of transformers' own `CLIPTextModel` (5.5.0 installed here; the reference pins 4.34.1) with
+the SD2.1-base text config on the repo's keyed random-init weights (tests/golden/clip_text_golden.pt, made by
+tests/golden/make_clip_text_golden.py; the SD2.1 text weights themselves are not available offline)."""
 import torch
 import torch.nn.functional as F
 
