@@ -22,7 +22,7 @@ import torch
 
 from . import ops
 from .scheduler import DDPMScheduler, randn_tensor
-from .text import CLIPTextEncoder, text_manifest
+from .text import CLIPTextEncoder, load_tokenizer, text_manifest
 from .unet import UNet2DConditionModel
 from .vae import AutoencoderKL
 from .weights import (LORA_FILE, UNET_CONFIG, VAE_CONFIG, load_lora_state, random_state_dict, unet_manifest,
@@ -43,7 +43,8 @@ class StableDiffusionPipelineOutput:
 
 def _load_component_state(root: str, sub: str):
     from safetensors.torch import load_file
-    for fn in ("diffusion_pytorch_model.safetensors", "model.safetensors"):
+    for fn in ("diffusion_pytorch_model.safetensors", "model.safetensors",
+               "diffusion_pytorch_model.fp16.safetensors", "model.fp16.safetensors"):
         p = os.path.join(root, sub, fn)
         if os.path.isfile(p):
             return load_file(p)
@@ -101,7 +102,8 @@ class StableDiffusionPipeline:
                                             UNET_CONFIG, device)
                 vae = AutoencoderKL(vsd or random_state_dict(vae_decoder_manifest(VAE_CONFIG), self.weight_seed),
                                     VAE_CONFIG, device)
-                text = CLIPTextEncoder(tsd or random_state_dict(text_manifest(), self.weight_seed), device)
+                text = CLIPTextEncoder(tsd or random_state_dict(text_manifest(), self.weight_seed), device,
+                                       tokenizer=load_tokenizer(local))
             _COMPONENT_CACHE[key] = (unet, vae, text)
         self.unet, self.vae, self.text_encoder = _COMPONENT_CACHE[key]
         self.unet.set_lora(self._lora)   # a fresh pipeline starts without (or with its own) adapters

@@ -37,6 +37,33 @@ class HashTokenizer:
         return torch.tensor(rows, dtype=torch.long)
 
 
+class SnapshotTokenizer:
+    """The snapshot's own CLIP BPE tokenizer (`<dir>/tokenizer/{vocab.json, merges.txt, ...}`) through transformers'
+    `CLIPTokenizer`, called the way diffusers' `encode_prompt` / `train_ID-Booth.py:463-469` call it:
+    `padding="max_length"`, `max_length=model_max_length` (77), `truncation=True`."""
+
+    def __init__(self, tokenizer_dir: str):
+        from transformers import CLIPTokenizer
+        self.tok = CLIPTokenizer.from_pretrained(tokenizer_dir, local_files_only=True)
+        self.model_max_length = min(int(self.tok.model_max_length), TEXT_CONFIG["max_pos"])
+
+    def __call__(self, texts: List[str]) -> torch.Tensor:
+        out = self.tok(list(texts), padding="max_length", max_length=self.model_max_length, truncation=True,
+                       return_tensors="pt")
+        return out.input_ids.to(torch.long)
+
+
+def load_tokenizer(snapshot_dir=None):
+    """`SnapshotTokenizer` when a local model snapshot ships its tokenizer files, else the hashed stand-in (there is no
+    CLIP vocabulary offline, and with random-init weights the token ids only need to be deterministic)."""
+    if snapshot_dir:
+        import os
+        tok_dir = os.path.join(str(snapshot_dir), "tokenizer")
+        if os.path.isfile(os.path.join(tok_dir, "vocab.json")) and os.path.isfile(os.path.join(tok_dir, "merges.txt")):
+            return SnapshotTokenizer(tok_dir)
+    return HashTokenizer()
+
+
 def text_manifest(cfg: dict = TEXT_CONFIG):
     h, inter = cfg["hidden"], cfg["intermediate"]
     m = [("text_model.embeddings.token_embedding.weight", (cfg["vocab"], h)),
@@ -54,11 +81,12 @@ def text_manifest(cfg: dict = TEXT_CONFIG):
 
 
 class CLIPTextEncoder:
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device, dtype=torch.bfloat16, cfg: dict = TEXT_CONFIG):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, dtype=torch.bfloat16, cfg: dict = TEXT_CONFIG,
+                 tokenizer=None):
         self.cfg, self.device, self.dtype = cfg, torch.device(device), dtype
         if self.device.type != "cuda":
             raise RuntimeError("CLIPTextEncoder runs on CUDA (sm_100a) only; there is no CPU fallback")
-        self.tokenizer = HashTokenizer()
+        self.tokenizer = tokenizer if tokenizer is not None else HashTokenizer()
         self._cache: Dict[str, torch.Tensor] = {}
         bf, f32 = torch.bfloat16, torch.float32
         dev = self.device

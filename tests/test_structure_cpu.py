@@ -184,6 +184,33 @@ def test_arcface_glue_oracle_vs_reference_golden():
         assert torch.allclose(got, want, atol=1e-6), float((got - want).abs().max())
 
 
+def test_snapshot_tokenizer_is_used_when_the_model_directory_ships_one(tmp_path):
+    """A local SD2.1 snapshot brings `tokenizer/{vocab.json, merges.txt}`: prompts are then tokenized by transformers'
+    CLIPTokenizer the way `encode_prompt` / train_ID-Booth.py:463-469 do (max_length padding to 77, truncation); without a
+    snapshot the hashed stand-in is used."""
+    import json
+    from faceposegenerator_b200.text import HashTokenizer, SnapshotTokenizer, load_tokenizer
+    assert isinstance(load_tokenizer(None), HashTokenizer) and isinstance(load_tokenizer(str(tmp_path)), HashTokenizer)
+    bs = list(range(ord("!"), ord("~") + 1)) + list(range(0xA1, 0xAD)) + list(range(0xAE, 0x100))
+    cs = [chr(b) for b in bs] + [chr(256 + k) for k in range(256 - len(bs))]     # CLIP's byte-level alphabet
+    merges = [("f", "a"), ("fa", "c"), ("fac", "e</w>"), ("p", "h"), ("ph", "o"), ("pho", "t"), ("phot", "o</w>")]
+    vocab = cs + [c + "</w>" for c in cs] + [a + b for a, b in merges] + ["<|startoftext|>", "<|endoftext|>"]
+    tok_dir = tmp_path / "tokenizer"
+    tok_dir.mkdir()
+    (tok_dir / "vocab.json").write_text(json.dumps({t: i for i, t in enumerate(vocab)}))
+    (tok_dir / "merges.txt").write_text("#version: 0.2\n" + "\n".join(f"{a} {b}" for a, b in merges) + "\n")
+    (tok_dir / "tokenizer_config.json").write_text(json.dumps({
+        "model_max_length": 77, "pad_token": "!", "bos_token": "<|startoftext|>", "eos_token": "<|endoftext|>",
+        "unk_token": "<|endoftext|>", "tokenizer_class": "CLIPTokenizer"}))
+    tok = load_tokenizer(str(tmp_path))
+    assert isinstance(tok, SnapshotTokenizer) and tok.model_max_length == 77
+    ids = tok(["face photo", "photo face " * 60])
+    bos, eos, face, photo = vocab.index("<|startoftext|>"), vocab.index("<|endoftext|>"), vocab.index("face</w>"), vocab.index("photo</w>")
+    assert ids.shape == (2, 77) and ids.dtype == torch.long
+    assert ids[0].tolist() == [bos, face, photo, eos] + [0] * 73           # SD2.1 pads with "!" (id 0), not with EOS
+    assert ids[1, 0] == bos and ids[1, -1] == eos and ids[1, 1:5].tolist() == [photo, face, photo, face]   # truncated to 77
+
+
 def test_lora_file_round_trip(tmp_path):
     from faceposegenerator_b200 import weights as w
     lora = w.random_lora(seed=5)
