@@ -1058,7 +1058,14 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
       // 256 rows instead of once per 128-column tile
       const bool splitk_regime = !phased && a->k_splits == 0 && a->workspace && tiles1 * 2 <= units && p.nkb0 + p.nkb1 >= 64;   // (split anyway)
       static const int dual_min_kb = env_int("IDB_GEMM_DUAL_MINKB", 32);   // smallest K (in 64-wide blocks) that takes dual-N tiles
-      if (force_dual == 1 || (p.nkb0 + p.nkb1 >= dual_min_kb && cost < cost1) || splitk_regime) dual = true, block_n = 160;
+      // experiment (off by default): one-wave layers whose dual-N tile grid would leave half the machine idle (16x16 latents,
+      // N = 1280) take dual-N tiles AND two K splits -- the same number of work units, 31 % fewer operand bytes per MAC,
+      // at the price of the fp32 workspace round trip.  IDB_GEMM_DUAL_SPLIT = smallest K (in 64-wide blocks) that qualifies.
+      static const int dual_split_kb = env_int("IDB_GEMM_DUAL_SPLIT", 0);
+      const bool dual_split = dual_split_kb > 0 && !phased && a->k_splits == 0 && a->workspace && tiles * 2 <= units &&
+                              tiles1 * 2 > units && p.nkb0 + p.nkb1 >= dual_split_kb &&
+                              static_cast<size_t>(p.M) * a->n * sizeof(float) * 2 <= a->workspace_bytes;
+      if (force_dual == 1 || (p.nkb0 + p.nkb1 >= dual_min_kb && cost < cost1) || splitk_regime || dual_split) dual = true, block_n = 160;
     }
   }
   p.n_tiles_n = (a->n + block_n * (dual ? 2 : 1) - 1) / (block_n * (dual ? 2 : 1));
