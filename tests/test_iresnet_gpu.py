@@ -163,3 +163,39 @@ def test_config5_training_forward_identity(model, golden_sd, cuda_dev):
     assert rel(eps.cpu(), eps_r) < 1e-2
     assert rel(x0.cpu(), x0_r) < 1e-2
     assert float(F.cosine_similarity(emb.cpu(), emb_r, dim=-1).min()) > 0.995
+
+
+def test_extract_embeds_on_cuda(model, golden_sd, cuda_dev, tmp_path, monkeypatch):
+    """`extract_embeds.run` (the reference's extract_ArcFace_embeds.py) with the CUDA backbone: per-folder embeddings of
+    every detected face against the pinned CPU oracle on the same preprocessed crops; host logic is pinned on the CPU
+    side (tests/test_extract_embeds_cpu.py)."""
+    import json
+    import numpy as np
+    from PIL import Image
+    from faceposegenerator_b200.extract_embeds import crop_to_bbox, prepare_for_arcface, run
+    from oracle.iresnet import iresnet_forward
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.RandomState(0)
+    boxes = {}
+    for folder, sizes in (("p1", (160, 144)), ("p2", (128,))):
+        os.makedirs(os.path.join("FACE_DATASET", "images", folder))
+        for k, size in enumerate(sizes):
+            arr = np.kron(rng.randint(0, 256, size=(size // 8, size // 8, 3)).astype(np.uint8), np.ones((8, 8, 1), np.uint8))
+            Image.fromarray(arr).save(os.path.join("FACE_DATASET", "images", folder, f"{k}.png"))
+            boxes[os.path.join("images", folder, f"{k}.png")] = [12, 9, size - 17, size - 6]
+    with open("boxes.json", "w") as f:
+        json.dump(boxes, f)
+    without = run("FACE_DATASET", device="cuda:0", model=model, bbox_file="boxes.json", embed="all",
+                  listdir=lambda p: sorted(os.listdir(p)))
+    assert without == {"files_without_faces": []}
+    for folder, n in (("p1", 2), ("p2", 1)):
+        emb = torch.load(os.path.join("FACE_DATASET", "ArcFace_embeds", folder, folder + ".pt")).float().cpu()
+        assert emb.shape == (n, 512)
+        crops = []
+        for k in range(n):
+            rel_path = os.path.join("images", folder, f"{k}.png")
+            img = torch.from_numpy(np.array(Image.open(os.path.join("FACE_DATASET", rel_path))))
+            crops.append(prepare_for_arcface(crop_to_bbox(img, boxes[rel_path])))
+        with torch.no_grad():
+            ref = iresnet_forward(golden_sd, torch.cat(crops, 0))
+        assert rel(emb, ref) < 1.5e-2, rel(emb, ref)
