@@ -177,12 +177,12 @@ def test_extract_embeds_on_cuda(model, golden_sd, cuda_dev, tmp_path, monkeypatc
     monkeypatch.chdir(tmp_path)
     rng = np.random.RandomState(0)
     boxes = {}
-    for folder, sizes in (("p1", (160, 144)), ("p2", (128,))):
+    for folder, sizes in (("p1", (160, 160)), ("p2", (128,))):   # the images of a folder are stacked (`:46`): one size per folder
         os.makedirs(os.path.join("FACE_DATASET", "images", folder))
         for k, size in enumerate(sizes):
             arr = np.kron(rng.randint(0, 256, size=(size // 8, size // 8, 3)).astype(np.uint8), np.ones((8, 8, 1), np.uint8))
             Image.fromarray(arr).save(os.path.join("FACE_DATASET", "images", folder, f"{k}.png"))
-            boxes[os.path.join("images", folder, f"{k}.png")] = [12, 9, size - 17, size - 6]
+            boxes[os.path.join("images", folder, f"{k}.png")] = [12 + 9 * k, 9, size - 17, size - 6 - 11 * k]
     with open("boxes.json", "w") as f:
         json.dump(boxes, f)
     without = run("FACE_DATASET", device="cuda:0", model=model, bbox_file="boxes.json", embed="all",
