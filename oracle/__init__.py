@@ -18,7 +18,8 @@ this container are PINNED by golden vectors under tests/golden/ (each with its g
 script): oracle/iresnet.py against `/root/reference/ArcFace_files/backbones/iresnet.py`,
 oracle/arcface_glue.py against the glue functions of `/root/reference/train_ID-Booth.py:433-455`,
 oracle/clip_text.py against transformers' own `CLIPTextModel`, and the caller-side host logic
-(faceposegenerator_b200/sweep.py) against a log of `/root/reference/inference_ID-Booth.py` itself.
+(faceposegenerator_b200/sweep.py, extract_embeds.py) against logs of `/root/reference/inference_ID-Booth.py` and
+`/root/reference/extract_ArcFace_embeds.py` themselves, executed under recording stubs.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this package, and there only as the checker / the
