@@ -1,8 +1,9 @@
 """Generates tests/golden/arcface_glue_golden.pt by running the reference's OWN glue functions between the decoded x0 image
 and the ArcFace backbone -- `latents_to_image_for_mtcnn` and `cropped_image_to_arcface_input`
-(/root/reference/train_ID-Booth.py:433-455) plus the bbox crop expression of its call sites (`:1090,1123`) -- in this
+(/root/reference/train_ID-Booth.py:433-455), and its in-tree twin of the pipeline's image post-process,
+`latents_to_pil_images` (`:408-417`), plus the bbox crop expression of its call sites (`:1090,1123`) -- in this
 container.  `train_ID-Booth.py` cannot be imported (it imports diffusers / accelerate / facenet_pytorch at the top), so
-the two function definitions are taken from its syntax tree and executed as they are, with `torch` and
+the function definitions are taken from its syntax tree and executed as they are, with `torch` and
 `torchvision.transforms` in scope; nothing of them is stored in this repo.  Inputs are regenerated from seeds.
     python tests/golden/make_arcface_glue_golden.py
 """
@@ -14,14 +15,15 @@ from torchvision import transforms
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = "/root/reference/train_ID-Booth.py"
-WANTED = ("latents_to_image_for_mtcnn", "cropped_image_to_arcface_input")
+WANTED = ("latents_to_image_for_mtcnn", "cropped_image_to_arcface_input", "latents_to_pil_images")
 # (seed, image size, bbox x0 y0 x1 y1) -- the fixed cfg-5 box, a box hanging over two edges, a small off-centre box
 CASES = [(0, 512, (96, 96, 416, 416)), (1, 512, (-20, 30, 540, 470)), (2, 256, (100, 90, 171, 200))]
 
 
 def reference_functions():
     tree = ast.parse(open(SRC).read())
-    ns = {"torch": torch, "transforms": transforms}
+    from PIL import Image
+    ns = {"torch": torch, "transforms": transforms, "Image": Image}
     for node in tree.body:
         if isinstance(node, ast.FunctionDef) and node.name in WANTED:
             exec(compile(ast.Module([node], []), SRC, "exec"), ns)
@@ -42,8 +44,13 @@ class _Vae:   # `vae.decode(z).sample`: the decoder itself is pinned elsewhere; 
 
 
 if __name__ == "__main__":
-    to_mtcnn, to_arcface = reference_functions()
+    to_mtcnn, to_arcface, to_pil = reference_functions()
     gold = {"cases": CASES, "mtcnn_image_slices": [], "arcface_inputs": []}
+    # row a14: `latents_to_pil_images` (:408-417) = decode, /2 + 0.5, clamp, NHWC, * 255, round, uint8 -- two images, subsampled
+    import numpy as np
+    batch = torch.cat([decoded_image(10, 256), decoded_image(11, 256)])
+    pils = to_pil(torch.zeros(2, 4, 32, 32), _Vae(batch))
+    gold["pil_uint8_slices"] = torch.from_numpy(np.stack([np.asarray(im) for im in pils]))[:, ::4, ::4].clone()
     for seed, size, bbox in CASES:
         img = to_mtcnn(torch.zeros(1, 4, size // 8, size // 8), _Vae(decoded_image(seed, size)))     # [H, W, 3] in 0..255
         assert img.shape == (size, size, 3)

@@ -211,6 +211,18 @@ def test_snapshot_tokenizer_is_used_when_the_model_directory_ships_one(tmp_path)
     assert ids[1, 0] == bos and ids[1, -1] == eos and ids[1, 1:5].tolist() == [photo, face, photo, face]   # truncated to 77
 
 
+def test_postprocess_oracle_vs_reference_golden():
+    """PINNED (row a14): oracle `postprocess_np` + the uint8 conversion of `output_type="pil"` against the reference's own
+    `latents_to_pil_images` (train_ID-Booth.py:408-417) run on the same seeded decoder outputs."""
+    from oracle.sd21 import postprocess_np
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "arcface_glue_golden.pt"))
+    batch = torch.cat([_decoded_image(10, 256), _decoded_image(11, 256)])
+    img = postprocess_np(batch)                                  # float32 [2, 256, 256, 3] in [0, 1]
+    assert img.shape == (2, 256, 256, 3) and img.min() >= 0.0 and img.max() <= 1.0
+    u8 = torch.from_numpy((img * 255).round().astype("uint8"))
+    assert torch.equal(u8[:, ::4, ::4], gold["pil_uint8_slices"])
+
+
 def test_lora_file_round_trip(tmp_path):
     from faceposegenerator_b200 import weights as w
     lora = w.random_lora(seed=5)
