@@ -2,7 +2,8 @@
 `pipe.text_encoder` / `encode_prompt` at `inference_ID-Booth.py:138`, in-tree twin `train_ID-Booth.py:457-491`) in this
 container: SD2.1-base text config (hidden 1024, 23 layers, 16 heads, intermediate 4096, 77 positions,
 vocab 49408, gelu), weights regenerated deterministically from key names (`weights.random_state_dict(text_manifest())`),
-token ids from the repo's hashed tokenizer.  Only outputs are stored.  The installed transformers is 5.5.0 (the
+token ids from the repo's hashed tokenizer, the encoder driven through the reference's OWN in-tree `encode_prompt`
+(`train_ID-Booth.py:476-491`).  Only outputs are stored.  The installed transformers is 5.5.0 (the
 reference pins 4.34.1, `requirements.txt`): same module, same state-dict keys for everything the manifest names.
     python tests/golden/make_clip_text_golden.py
 """
@@ -44,9 +45,19 @@ if __name__ == "__main__":
     ids = HashTokenizer()(PROMPTS)
     with torch.no_grad():
         out = model(input_ids=ids, output_hidden_states=True)
+        # the reference's own in-tree `encode_prompt` (train_ID-Booth.py:476-491, taken from its syntax tree because the
+        # module imports diffusers at the top) driving the same text encoder: this is the tensor the UNet receives
+        import ast
+        src = "/root/reference/train_ID-Booth.py"
+        ns = {"torch": torch}
+        for node in ast.parse(open(src).read()).body:
+            if isinstance(node, ast.FunctionDef) and node.name == "encode_prompt":
+                exec(compile(ast.Module([node], []), src, "exec"), ns)
+        via_reference = ns["encode_prompt"](model, ids, None)
+        assert torch.equal(via_reference, out.last_hidden_state)
     hs = out.hidden_states   # embeddings + one per layer (before the final LayerNorm)
     gold = {"transformers_version": transformers.__version__, "ids": ids, "prompts": PROMPTS,
-            "last_hidden_state": out.last_hidden_state.clone(),
+            "last_hidden_state": via_reference.clone(),   # == out.last_hidden_state (asserted above)
             "hidden_1_slice": hs[1][:, :, :16].clone(), "hidden_12_slice": hs[12][:, :, :16].clone(),
             "hidden_23_slice": hs[23][:, :, :16].clone(),
             "n_params": sum(p.numel() for p in model.parameters())}
