@@ -154,6 +154,21 @@ def identity_loss(pred: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
     return 1.0 - torch.nn.functional.cosine_similarity(pred.float(), gt.float(), dim=-1)
 
 
+def triplet_identity_loss(pred: torch.Tensor, positive: torch.Tensor, negative: torch.Tensor, margin: float = 1.0) -> torch.Tensor:
+    """The `triplet_prior` identity loss of config 5: `TripletMarginWithDistanceLoss(distance_function=1 - cosine)` as built at
+    train_ID-Booth.py:974-979 and applied at `:1133` to (predicted-x0 embedding, gt_embed[0], gt_embed[1]):
+    mean(max(d(a, p) - d(a, n) + margin, 0)).  A few hundred floats: plain tensor arithmetic, no kernel."""
+    cos = torch.nn.functional.cosine_similarity
+    d_ap = 1.0 - cos(pred.float(), positive.float())
+    d_an = 1.0 - cos(pred.float(), negative.float())
+    return torch.clamp_min(margin + d_ap - d_an, 0.0).mean()
+
+
+def identity_noise_level_weight(timestep, num_train_timesteps: int = 1000, timestep_loss_weighting: bool = True):
+    """`(1 - t / T) ** 2` (train_ID-Booth.py:1100-1101,1129-1130): the identity term counts less at high noise levels."""
+    return (1.0 - timestep / num_train_timesteps) ** 2 if timestep_loss_weighting else 1
+
+
 def training_forward_identity(unet, vae, scheduler, arcface: IResNet, noisy_latents: torch.Tensor, timesteps,
                               encoder_hidden_states: torch.Tensor, bbox: torch.Tensor, context=None):
     """The forward half of the reference's identity-loss branch (config 5; train_ID-Booth.py:1040-1046, :1081,

@@ -223,6 +223,26 @@ def test_postprocess_oracle_vs_reference_golden():
     assert torch.equal(u8[:, ::4, ::4], gold["pil_uint8_slices"])
 
 
+def test_triplet_identity_loss_is_the_reference_loss_object():
+    """`triplet_identity_loss` == the loss object the reference builds at train_ID-Booth.py:974-979
+    (`TripletMarginWithDistanceLoss` over 1 - cosine) on the shapes of its call site (`:1133`)."""
+    import torch.nn.functional as F
+    from faceposegenerator_b200.iresnet import identity_loss, identity_noise_level_weight, triplet_identity_loss
+
+    def cosine_distance(x, y):
+        return 1 - F.cosine_similarity(x, y)
+    ref = torch.nn.TripletMarginWithDistanceLoss(distance_function=cosine_distance)
+    g = torch.Generator().manual_seed(4)
+    for n in (1, 4):
+        a, gt = torch.randn(n, 512, generator=g), torch.randn(2, 512, generator=g)
+        assert torch.allclose(triplet_identity_loss(a, gt[0][None, :], gt[1][None, :]), ref(a, gt[0][None, :], gt[1][None, :]), atol=1e-7)
+        close = a + 0.05 * torch.randn(n, 512, generator=g)       # a positive near the anchor: the hinge is active
+        assert torch.allclose(triplet_identity_loss(a, close, gt[1][None, :]), ref(a, close, gt[1][None, :]), atol=1e-7)
+        cos = torch.nn.CosineSimilarity(dim=1, eps=1e-6)
+        assert torch.allclose(identity_loss(a, gt[0]), 1 - cos(a, gt[0][None]), atol=1e-6)      # `:1096-1098`
+    assert identity_noise_level_weight(250) == (1 - 250 / 1000) ** 2 and identity_noise_level_weight(250, 1000, False) == 1
+
+
 def test_lora_file_round_trip(tmp_path):
     from faceposegenerator_b200 import weights as w
     lora = w.random_lora(seed=5)
