@@ -81,7 +81,10 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
     _chk(out_f32, f32, "out_f32", allow_none=True); _chk(out_bf16, t16, "out_bf16", allow_none=True)
     if k_splits > 1 and workspace is None:
         workspace = torch.empty((k_splits, M, N), dtype=f32, device=a0.device)
-    if stats is None and want_stats:   # row-block channel statistics of the fp32 output (consumed by groupnorm)
+    # row-block channel statistics of the fp32 output (consumed by groupnorm); geometries whose 128-pixel tiles are not
+    # raster runs of one image (e.g. the 96 / 48 / 24 / 12-wide rasters of 768 x 768 images) return stats = None and the
+    # GroupNorm that follows computes its own statistics (`gn_stats_kernel`)
+    if stats is None and want_stats and epilogue_stats_supported(B, Ho, Wo):
         stats = torch.empty(((M + 31) // 32, n_out, 2), dtype=f32, device=a0.device)
     _chk(stats, f32, "stats", allow_none=True)
     args = _lib.GemmConvArgs(
@@ -102,6 +105,27 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
     if want_stats or stats is not None:
         return out_f32, out_bf16, stats
     return out_f32, out_bf16
+
+
+def _pow2_divisor(v: int, cap: int) -> int:
+    d = 1
+    while d * 2 <= cap and v % (d * 2) == 0:
+        d *= 2
+    return d
+
+
+def epilogue_stats_supported(batch: int, ho: int, wo: int) -> bool:
+    """Mirror of the `stats_partials` precondition of `idb_gemm_conv` (gemm_tc.cu): the 32-row blocks of a 128-pixel output
+    tile (BW x BH x BB pixels) must be raster-contiguous runs of one image, and an image must hold whole blocks.
+    A Linear ([M, K] operand) arrives here as batch = 1, ho = 1, wo = M."""
+    if (ho * wo) % 32:
+        return False
+    if ho == 1 and batch == 1:
+        return True
+    bw = _pow2_divisor(wo, 128)
+    bh = _pow2_divisor(ho, 128 // bw)
+    bb = 128 // (bw * bh)
+    return bw == wo or (bh == 1 and bb == 1)
 
 
 def attention(q, k, v, out=None, *, batch: int, heads: int, t_q: int, t_kv: int, scale: float,

@@ -339,7 +339,7 @@ class UNet2DConditionModel:
             if blk.up is not None:
                 ht = h[0]
                 Hl, Wl, Cu = ht.shape[1], ht.shape[2], ht.shape[3]
-                if B * Hl * Wl >= 2048 and (Hl * Wl) % 32 == 0:
+                if B * Hl * Wl >= 2048 and ops.epilogue_stats_supported(B, Hl, Wl):
                     # Upsample2D as four 2x2 convolutions on the LOW-resolution tensor (one per output parity class,
                     # 3x3 taps pre-summed): 4 x K = 4C instead of K = 9C on the upsampled tensor -> 2.25x fewer MACs,
                     # and no upsampled operand is ever written

@@ -244,7 +244,7 @@ class AutoencoderKL:
             if blk.up is not None:
                 ht = h[0]
                 Hl, Wl, Cu = ht.shape[1], ht.shape[2], ht.shape[3]
-                if (Hl * Wl) % 32 == 0:   # Upsample2D as four 2x2 convs on the low-resolution tensor (see unet.py)
+                if ops.epilogue_stats_supported(B, Hl, Wl):   # Upsample2D as four 2x2 convs on the low-resolution tensor (see unet.py)
                     xb = ops.cast_bf16(ht)
                     o = torch.empty((B, 2 * Hl, 2 * Wl, Cu), dtype=f32, device=self.device)
                     o_st = torch.empty((4, B * Hl * Wl // 32, Cu, 2), dtype=f32, device=self.device)

@@ -243,6 +243,17 @@ def test_triplet_identity_loss_is_the_reference_loss_object():
     assert identity_noise_level_weight(250) == (1 - 250 / 1000) ** 2 and identity_noise_level_weight(250, 1000, False) == 1
 
 
+def test_epilogue_statistics_gate_mirrors_the_kernel_precondition():
+    """`ops.epilogue_stats_supported` (host mirror of the `stats_partials` check in gemm_tc.cu): every raster of the 512 x 512
+    path keeps the fused GroupNorm statistics; the 96 / 48 / 24 / 12-wide rasters of config 4 (768 x 768) and the
+    VAE's 192-wide level fall back to GroupNorm's own statistics kernel instead of raising IDB_E_UNSUPPORTED."""
+    from faceposegenerator_b200.ops import epilogue_stats_supported as ok
+    for b in (1, 2, 4, 8, 16):
+        assert all(ok(b, w, w) for w in (8, 16, 32, 64, 128, 256, 512, 384, 768))
+        assert not any(ok(b, w, w) for w in (12, 24, 48, 96, 192, 112, 56))
+    assert ok(1, 1, 8 * 4096) and ok(1, 1, 16 * 9216) and not ok(1, 1, 154)      # Linear layers: rows in whole 32-row blocks
+
+
 def test_lora_file_round_trip(tmp_path):
     from faceposegenerator_b200 import weights as w
     lora = w.random_lora(seed=5)
