@@ -254,6 +254,49 @@ def test_epilogue_statistics_gate_mirrors_the_kernel_precondition():
     assert ok(1, 1, 8 * 4096) and ok(1, 1, 16 * 9216) and not ok(1, 1, 154)      # Linear layers: rows in whole 32-row blocks
 
 
+def test_upsample_four_phase_weights_are_the_upsampled_conv():
+    """Host packing of the Upsample2D rewrite: four 2x2 convolutions on the low-resolution tensor (tap offsets (a-1, c-1),
+    `pack_upsample_phase_weights`) == conv3x3(pad 1) on the nearest-2x upsampled tensor.  Checked here with power-of-two
+    valued weights / inputs so that the bf16 rounding of the pre-summed taps is exact (the GPU test covers real values)."""
+    import torch.nn.functional as F
+    from faceposegenerator_b200.packing import pack_upsample_phase_weights
+    g = torch.Generator().manual_seed(2)
+    cin, cout, H, W = 8, 5, 6, 7
+    w = torch.randint(-3, 4, (cout, cin, 3, 3), generator=g).float() / 4          # sums of <= 4 taps stay exact in bf16
+    x = torch.randint(-8, 9, (2, cin, H, W), generator=g).float() / 8
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, padding=1)
+    wph = pack_upsample_phase_weights(w)
+    out = torch.empty_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))                                                   # zero padding == TMA out-of-bounds fill
+    for a in range(2):
+        for c in range(2):
+            k = wph[a][c].float().view(cout, 2, 2, cin).permute(0, 3, 1, 2)       # [Cout, 4*Cin] tap-major -> [Cout, Cin, 2, 2]
+            # tap (u, v) reads low-resolution pixel (i + a - 1 + u, j + c - 1 + v)
+            y = F.conv2d(xp[:, :, a:a + H + 1, c:c + W + 1], k)
+            out[:, :, a::2, c::2] = y
+    assert torch.equal(out, ref)
+
+
+def test_iresnet_batchnorm_folding_is_exact_in_eval_mode():
+    """Host-side weight preparation of the ArcFace backbone (iresnet.py): a conv followed by an eval-mode BatchNorm ==
+    the conv with scaled weights + a bias (`_bn_affine` / `_fold_conv`), in the tap-major / channel-minor operand layout."""
+    import torch.nn.functional as F
+    from faceposegenerator_b200.iresnet import _bn_affine, _fold_conv
+    g = torch.Generator().manual_seed(9)
+    cin, cout = 6, 10
+    w = torch.randn(cout, cin, 3, 3, generator=g, dtype=torch.float64)
+    sd = {"bn.weight": torch.rand(cout, generator=g, dtype=torch.float64) + 0.5, "bn.bias": torch.randn(cout, generator=g, dtype=torch.float64),
+          "bn.running_mean": torch.randn(cout, generator=g, dtype=torch.float64), "bn.running_var": torch.rand(cout, generator=g, dtype=torch.float64) + 0.1}
+    x = torch.randn(2, cin, 9, 9, generator=g, dtype=torch.float64)
+    ref = F.batch_norm(F.conv2d(x, w, padding=1), sd["bn.running_mean"], sd["bn.running_var"], sd["bn.weight"], sd["bn.bias"],
+                       training=False, eps=1e-5)
+    scale, shift = _bn_affine(sd, "bn")
+    wk, bias = _fold_conv(w, scale, shift)                                    # [Cout, 9 * Cin], tap-major
+    w_back = wk.view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    got = F.conv2d(x, w_back, bias, padding=1)
+    assert torch.allclose(got, ref, atol=1e-10)
+
+
 def test_lora_file_round_trip(tmp_path):
     from faceposegenerator_b200 import weights as w
     lora = w.random_lora(seed=5)
