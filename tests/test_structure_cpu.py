@@ -118,6 +118,41 @@ def test_oracle_lora_metamorphic_fp64():
     assert (row0 - un[:1]).abs().max() < 1e-10
 
 
+def test_oracle_lora_gradients_fp64_finite_differences():
+    """Checker for SURVEY 8(f)-4 (LoRA-only backward, not built yet): autograd gradients of the reference's denoising loss
+    with respect to the adapters (oracle/lora_grad.py) against central finite differences in fp64, and the structure of
+    the up-projection gradient (d loss / d B = sum dY (x A^T): zero wherever x A^T is zero)."""
+    from oracle import lora_grad
+    sd, lora, x, ctx = _tiny()
+    g = torch.Generator().manual_seed(5)
+    noise = torch.randn(x.shape, generator=g, dtype=torch.float64)
+    t = torch.tensor([700, 40])
+    loss, grads = lora_grad.lora_gradients(sd, lora, x, noise, t, ctx, TINY)
+    assert set(grads) == set(lora) and float(loss) > 0
+    keys = sorted(lora)
+    picks = [keys[0], keys[len(keys) // 2], keys[-1]]          # adapters in different blocks / on different projections
+    h = 1e-6
+    for k in picks:
+        for which, idx in ((0, (1, 3)), (1, (2, 1))):
+            def loss_at(delta):
+                d, u, s = lora[k]
+                d, u = d.clone(), u.clone()
+                (d if which == 0 else u)[idx] += delta
+                with torch.no_grad():
+                    return float(lora_grad.denoising_loss(sd, {**lora, k: (d, u, s)}, x, noise, t, ctx, TINY))
+            fd = (loss_at(h) - loss_at(-h)) / (2 * h)
+            an = float(grads[k][which][idx])
+            assert abs(fd - an) <= 1e-6 * max(1.0, abs(an)) + 1e-9, (k, which, fd, an)
+    # an adapter whose down-projection is zero has a zero up-projection gradient (and a non-zero down gradient)
+    k = picks[1]
+    zeroed = {**lora, k: (torch.zeros_like(lora[k][0]), lora[k][1], lora[k][2])}
+    _, gz = lora_grad.lora_gradients(sd, zeroed, x, noise, t, ctx, TINY)
+    assert float(gz[k][1].abs().max()) == 0.0 and float(gz[k][0].abs().max()) > 0.0
+    # v-prediction target (train_ID-Booth.py:1057-1058) gives a different loss on the same prediction
+    lv = lora_grad.denoising_loss(sd, lora, x, noise, t, ctx, TINY, prediction_type="v_prediction")
+    assert abs(float(lv) - float(loss)) > 1e-6
+
+
 def test_oracle_cfg_scale_one_is_conditional_branch():
     from oracle import sd21
     sd, lora, _, _ = _tiny()
