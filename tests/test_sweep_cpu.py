@@ -196,3 +196,44 @@ def test_async_writer_writes_everything_and_reports_errors(tmp_path):
     w.save(torch.zeros(1, 3, 4, 4), str(tmp_path / "b.png"))
     with pytest.raises(OSError):
         w.close()
+
+
+# ---------------------------------------------------------------------------------------------- N > 1 over gloo
+def _gloo_worker(rank, world, port, cwd, q):
+    import torch.distributed as dist
+    os.chdir(cwd)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        log = {"pipelines": [], "calls": [], "kwargs": []}
+        totals = _run(log, rank=rank, world_size=world)
+        dist.barrier()                                   # the sweep's only synchronisation point (sweep.main)
+        files = [None] * world
+        dist.all_gather_object(files, [s[0] for s in log["saved"]])
+        q.put((rank, totals["identities"], totals["generated"], files))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_process_gloo_sweep_writes_the_single_process_tree(tree, gold):
+    """World-size-2 run of the sweep over real processes (gloo): every rank replays the plan, takes its identities, writes its
+    own files; together they are exactly the files of the reference script's single-process run."""
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, str(tree), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [(r, n_id, n_img) for r, n_id, n_img, _ in results] == [(0, 2, 126), (1, 2, 126)]
+    gathered = results[0][3]
+    assert results[1][3] == gathered                     # both ranks see the same gathered lists
+    assert sorted(f for part in gathered for f in part) == sorted(s[0] for s in gold["saved"])
+    assert all(os.path.isfile(f) for part in gathered for f in part)
