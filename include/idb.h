@@ -134,7 +134,9 @@ size_t idb_gemm_conv_workspace_bytes(int64_t m, int64_t n, int32_t k_splits);
 /* ------------------------------------------------------------------------------------------
  * idb_attention: O = softmax(Q K^T * scale) V per (batch, head), flash-style on tcgen05
  * (S and O accumulators in TMEM, online softmax in fp32).  Replaces AttnProcessor2_0 ->
- * F.scaled_dot_product_attention (diffusers Attention, self- and cross-; head_dim 64).
+ * F.scaled_dot_product_attention (diffusers Attention, self- and cross-; head_dim 64) inside the UNet call of
+ * inference_ID-Booth.py:138 / train_ID-Booth.py:1040-1046 (the attention projections are the LoRA targets named at
+ * train_ID-Booth.py:676); with causal = 1 the CLIPAttention behind encode_prompt (train_ID-Booth.py:476-491).
  * q/k/v: bf16 row-major token matrices; row (b, t) at ptr + ((b*T + t)*ld + col0 + head*64).
  * out: bf16 [B*Tq, heads*64] (ld_out).
  * ---------------------------------------------------------------------------------------- */
@@ -151,7 +153,8 @@ int idb_attention(const idb_attention_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU) over NHWC, fp32 statistics.  Replaces F.group_norm + F.silu in
- * ResnetBlock2D.norm1/norm2, Transformer2DModel.norm, conv_norm_out.  Reads the logical
+ * ResnetBlock2D.norm1/norm2, Transformer2DModel.norm, conv_norm_out (UNet call of inference_ID-Booth.py:138 /
+ * train_ID-Booth.py:1040-1046; VAE decode of train_ID-Booth.py:412,437).  Reads the logical
  * channel-concatenation [x0 | x1] (UpBlock skip `torch.cat([h, skip], 1)`) without
  * materialising it.  Inputs fp32 (stream) ; outputs bf16 [B,H,W,C0+C1]:
  *   out_norm = act(GN(x))        out_raw (optional) = bf16(x)   (operand of conv_shortcut)
@@ -181,11 +184,13 @@ int idb_groupnorm(const idb_groupnorm_args* args, void* stream);
 size_t idb_groupnorm_workspace_bytes(int32_t batch, int32_t groups);
 
 /* LayerNorm over the last dim (eps 1e-5, affine): fp32 [rows, C] -> bf16 [rows, C].
- * Replaces BasicTransformerBlock.norm1/2/3. C % 4 == 0, C <= 2048. */
+ * Replaces BasicTransformerBlock.norm1/2/3 (UNet call of inference_ID-Booth.py:138 / train_ID-Booth.py:1040-1046) and the
+ * LayerNorms of the CLIP text tower (encode_prompt, train_ID-Booth.py:476-491). C % 4 == 0, C <= 2048. */
 int idb_layernorm(const float* x, const float* gamma, const float* beta, void* out_bf16,
                   int64_t rows, int32_t c, float eps, void* stream);
 
-/* Row softmax for the VAE mid-block attention (1 head, d = 512): fp32 [rows, cols] * scale ->
+/* Row softmax for the VAE mid-block attention (1 head, d = 512; vae.decode at train_ID-Booth.py:412,437 and the pipeline
+ * tail of inference_ID-Booth.py:138): fp32 [rows, cols] * scale ->
  * bf16 probabilities [rows, cols]. */
 int idb_softmax_rows(const float* s, void* p_bf16, int64_t rows, int32_t cols, float scale, void* stream);
 
@@ -195,7 +200,9 @@ int idb_softmax_rows(const float* s, void* p_bf16, int64_t rows, int32_t cols, f
 /* Timesteps(320, flip_sin_to_cos, shift 0) -> linear_1 -> SiLU -> linear_2 -> SiLU (the SiLU
  * that every ResnetBlock2D applies before time_emb_proj), then ALL time_emb_proj layers at
  * once: proj_out[b, :] = W_all . silu(emb[b]) + b_all  with W_all = row-concat of the 22
- * time_emb_proj weights.  fp32 weights.  scratch: fp32 [batch, 2*dim_emb + dim_sin]. */
+ * time_emb_proj weights.  fp32 weights.  scratch: fp32 [batch, 2*dim_emb + dim_sin].
+ * Reference: the `timesteps` argument of the UNet call, train_ID-Booth.py:1040-1046 / the pipeline loop of
+ * inference_ID-Booth.py:138. */
 typedef struct {
   const float* timesteps;            /* [batch] */
   int32_t batch, dim_sin, dim_emb;   /* 320, 1280 */
@@ -215,7 +222,8 @@ int idb_conv3x3_small_cin(const float* x, int32_t x_nchw, const float* w, const 
                           int32_t batch, int32_t h, int32_t wd, int32_t cin, int32_t cout, void* stream);
 /* 3x3 pad-1 conv with tiny Cout (<= 4): conv_out of the UNet (320->4) and VAE (128->3).
  * x bf16 NHWC (already GroupNorm+SiLU'd); w fp32 [Cout, 3, 3, Cin]; out fp32 NCHW, or when
- * postprocess != 0 NHWC with (v*0.5+0.5).clamp(0,1) (VaeImageProcessor.postprocess "np"). */
+ * postprocess != 0 NHWC with (v*0.5+0.5).clamp(0,1) (VaeImageProcessor.postprocess "np"; in-tree twin
+ * train_ID-Booth.py:413-415, output_type="np" at inference_ID-Booth.py:138). */
 int idb_conv3x3_small_cout(const void* x_bf16, const float* w, const float* bias, float* out,
                            int32_t postprocess, int32_t batch, int32_t h, int32_t wd,
                            int32_t cin, int32_t cout, void* stream);
@@ -223,7 +231,8 @@ int idb_conv3x3_small_cout(const void* x_bf16, const float* w, const float* bias
 int idb_upsample2x(const float* x, void* out_bf16, int32_t batch, int32_t h, int32_t wd, int32_t c, void* stream);
 /* fp32 -> bf16 cast (operand staging for Downsample2D). */
 int idb_cast_bf16(const float* x, void* out_bf16, int64_t n, void* stream);
-/* VAE front: z/scaling_factor -> post_quant_conv 1x1 (4->4): NCHW fp32 -> NHWC fp32. */
+/* VAE front: z/scaling_factor -> post_quant_conv 1x1 (4->4): NCHW fp32 -> NHWC fp32
+ * (`latents = (1 / 0.18215) * latents; vae.decode(latents)`, train_ID-Booth.py:410-412,435-437). */
 int idb_vae_latent_prep(const float* z_nchw, const float* w, const float* bias, float inv_scaling,
                         float* out_nhwc, int32_t batch, int32_t hw, void* stream);
 
