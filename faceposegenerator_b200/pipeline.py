@@ -30,6 +30,48 @@ from .weights import (LORA_FILE, UNET_CONFIG, VAE_CONFIG, load_lora_state, rando
 
 f32 = torch.float32
 _COMPONENT_CACHE = {}   # (model id, device) -> components with packed base weights (LoRA hot-swaps on top)
+MAX_STEP_STATES = 4     # CUDA-graph step states kept per UNet (each owns its activations' private pool)
+# keyword arguments of diffusers' `StableDiffusionPipeline.__call__` that are accepted and have no effect on this path
+_IGNORED_CALL_KWARGS = {"callback_on_step_end_tensor_inputs": None, "callback_steps": None, "eta": 0.0,
+                        "guidance_rescale": 0.0, "clip_skip": None, "cross_attention_kwargs": None, "callback": None,
+                        "callback_on_step_end": None, "ip_adapter_image": None, "ip_adapter_image_embeds": None,
+                        "timesteps": None, "sigmas": None}
+# parity hooks of this implementation (tests / bench): shared noise tape, teacher forcing, per-step latent collection
+_PARITY_KWARGS = ("noise_tape", "teacher_latents", "collect_latents")
+
+
+def random_weights_allowed(flag=None) -> bool:
+    """Random-init stand-ins for missing checkpoints are an explicit opt-in (bench, tests, the offline replay of the
+    reference script): `allow_random_weights=True` / `weight_seed=` on `from_pretrained`, or IDB_ALLOW_RANDOM_WEIGHTS=1."""
+    if flag is not None:
+        return bool(flag)
+    return os.environ.get("IDB_ALLOW_RANDOM_WEIGHTS", "0") == "1"
+
+
+def resolve_snapshot(model_id: str) -> Optional[str]:
+    """A local directory, or the newest snapshot of a hub id in the local Hugging Face cache (HF_HUB_CACHE / HF_HOME);
+    None when neither exists (there is no network: nothing is ever downloaded)."""
+    if os.path.isdir(model_id):
+        return model_id
+    roots = [os.environ.get("HF_HUB_CACHE"), os.environ.get("HUGGINGFACE_HUB_CACHE")]
+    roots.append(os.path.join(os.environ.get("HF_HOME", os.path.join(os.path.expanduser("~"), ".cache", "huggingface")), "hub"))
+    for root in roots:
+        if not root:
+            continue
+        repo = os.path.join(root, "models--" + model_id.replace("/", "--"))
+        snaps = os.path.join(repo, "snapshots")
+        if not os.path.isdir(snaps):
+            continue
+        ref = os.path.join(repo, "refs", "main")
+        if os.path.isfile(ref):
+            with open(ref) as f:
+                cand = os.path.join(snaps, f.read().strip())
+            if os.path.isdir(cand):
+                return cand
+        dirs = sorted((os.path.join(snaps, d) for d in os.listdir(snaps)), key=os.path.getmtime)
+        if dirs:
+            return dirs[-1]
+    return None
 
 
 class StableDiffusionPipelineOutput:
@@ -41,21 +83,30 @@ class StableDiffusionPipelineOutput:
         return (self.images, self.nsfw_content_detected)[i]
 
 
-def _load_component_state(root: str, sub: str):
+def _load_component_state(root: Optional[str], sub: str):
+    """State dict of `<root>/<sub>/` from safetensors or a torch `.bin` checkpoint; None if the component has neither."""
+    if root is None:
+        return None
     from safetensors.torch import load_file
     for fn in ("diffusion_pytorch_model.safetensors", "model.safetensors",
                "diffusion_pytorch_model.fp16.safetensors", "model.fp16.safetensors"):
         p = os.path.join(root, sub, fn)
         if os.path.isfile(p):
             return load_file(p)
+    for fn in ("diffusion_pytorch_model.bin", "pytorch_model.bin", "diffusion_pytorch_model.fp16.bin", "pytorch_model.fp16.bin"):
+        p = os.path.join(root, sub, fn)
+        if os.path.isfile(p):
+            return torch.load(p, map_location="cpu", weights_only=True)
     return None
 
 
 class StableDiffusionPipeline:
-    def __init__(self, model_id: str, torch_dtype=None, seed: int = 0):
+    def __init__(self, model_id: str, torch_dtype=None, seed: int = 0, allow_random_weights=None):
         self.model_id = model_id
         self.torch_dtype = torch_dtype or torch.float32
         self.weight_seed = seed
+        self.allow_random_weights = allow_random_weights
+        self._lora_token = object()      # identity of the adapter set this pipeline wants installed on the (shared) UNet
         self.device = torch.device("cpu")
         self.scheduler = DDPMScheduler.from_pretrained(model_id, subfolder="scheduler")
         self.unet: Optional[UNet2DConditionModel] = None
@@ -64,17 +115,23 @@ class StableDiffusionPipeline:
         self.safety_checker = None
         self._lora = None
         self._progress = {}
-        self._graphs = {}
+        self._last_state = None          # step state (CUDA graphs + static buffers) used by the last call
         self.use_cuda_graph = os.environ.get("IDB_CUDA_GRAPH", "1") != "0"
         self.step_events = None    # set to a list to collect (start, end) CUDA events around every denoise step
 
     # ------------------------------------------------------------------ construction
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, torch_dtype=None, **kwargs):
-        """Loads `<dir>/{unet,vae,text_encoder}/*.safetensors` when given a local snapshot;
-        otherwise (offline, HF_HUB_OFFLINE=1) falls back to the built-in SD2.1-base configs with
-        deterministic random-init weights (weights.random_state_dict)."""
-        return cls(str(pretrained_model_name_or_path), torch_dtype=torch_dtype, seed=int(kwargs.get("weight_seed", 0)))
+        """Loads `<dir>/{unet,vae,text_encoder}/` (safetensors or .bin) from a local directory or from the local Hugging
+        Face cache of a hub id.  A component that cannot be found RAISES at `.to(device)`, unless random-init stand-ins
+        were asked for explicitly (`allow_random_weights=True` / `weight_seed=` / IDB_ALLOW_RANDOM_WEIGHTS=1: bench, tests
+        and the offline replay of `inference_ID-Booth.py`), in which case the built-in SD2.1-base configs get deterministic
+        random weights (weights.random_state_dict) and a warning is logged."""
+        allow = kwargs.get("allow_random_weights")
+        if allow is None and "weight_seed" in kwargs:
+            allow = True
+        return cls(str(pretrained_model_name_or_path), torch_dtype=torch_dtype, seed=int(kwargs.get("weight_seed", 0)),
+                   allow_random_weights=allow)
 
     def to(self, device=None, dtype=None):
         if device is None:
@@ -93,39 +150,48 @@ class StableDiffusionPipeline:
         self.device = device
         key = (self.model_id, str(device), self.weight_seed)
         if key not in _COMPONENT_CACHE or os.environ.get("IDB_NO_WEIGHT_CACHE") == "1":
+            local = resolve_snapshot(self.model_id)
+            allow = random_weights_allowed(self.allow_random_weights)
+            states = {sub: _load_component_state(local, sub) for sub in ("unet", "vae", "text_encoder")}
+            missing = [sub for sub, sd in states.items() if sd is None]
+            if missing and not allow:
+                raise FileNotFoundError(
+                    f"no weights for {missing} of {self.model_id!r} (looked in {local or 'no local snapshot / HF cache entry'}); "
+                    "pass a local snapshot directory, or opt in to random-init stand-ins with allow_random_weights=True / "
+                    "IDB_ALLOW_RANDOM_WEIGHTS=1 (benchmarks and tests only: the images are noise)")
+            if missing:
+                import warnings
+                warnings.warn(f"{self.model_id!r}: RANDOM-INIT weights for {missing} (seed {self.weight_seed}); "
+                              "generated images are noise -- benchmarking / testing only", stacklevel=2)
             with torch.cuda.device(device):
-                local = self.model_id if os.path.isdir(self.model_id) else None
-                usd = _load_component_state(local, "unet") if local else None
-                vsd = _load_component_state(local, "vae") if local else None
-                tsd = _load_component_state(local, "text_encoder") if local else None
-                unet = UNet2DConditionModel(usd or random_state_dict(unet_manifest(UNET_CONFIG), self.weight_seed),
+                unet = UNet2DConditionModel(states["unet"] or random_state_dict(unet_manifest(UNET_CONFIG), self.weight_seed),
                                             UNET_CONFIG, device)
-                vae = AutoencoderKL(vsd or random_state_dict(vae_decoder_manifest(VAE_CONFIG), self.weight_seed),
+                vae = AutoencoderKL(states["vae"] or random_state_dict(vae_decoder_manifest(VAE_CONFIG), self.weight_seed),
                                     VAE_CONFIG, device)
-                text = CLIPTextEncoder(tsd or random_state_dict(text_manifest(), self.weight_seed), device,
-                                       tokenizer=load_tokenizer(local))
+                text = CLIPTextEncoder(states["text_encoder"] or random_state_dict(text_manifest(), self.weight_seed), device,
+                                       tokenizer=load_tokenizer(local, allow_hash=allow))
             _COMPONENT_CACHE[key] = (unet, vae, text)
         self.unet, self.vae, self.text_encoder = _COMPONENT_CACHE[key]
-        self.unet.set_lora(self._lora)   # a fresh pipeline starts without (or with its own) adapters
-        self._graphs = {}
         return self
 
     # ------------------------------------------------------------------ LoRA lifecycle
     def load_lora_weights(self, pretrained_model_name_or_path_or_dict, weight_name: str = LORA_FILE, **kwargs):
+        """Adapters are per PIPELINE; they are installed on the (possibly shared) UNet at the next call, in place in its
+        persistent packed buffers, so captured step graphs survive the swap."""
         if isinstance(pretrained_model_name_or_path_or_dict, dict):
             lora = pretrained_model_name_or_path_or_dict
         else:
             lora = load_lora_state(str(pretrained_model_name_or_path_or_dict), weight_name)
         self._lora = lora
-        if self.unet is not None:
-            self.unet.set_lora(lora)
-        self._graphs = {}
+        self._lora_token = object()
 
     def unload_lora_weights(self):
         self._lora = None
-        if self.unet is not None:
-            self.unet.set_lora(None)
-        self._graphs = {}
+        self._lora_token = object()
+
+    def _install_lora(self):
+        if self.unet._lora_token is not self._lora_token:
+            self.unet.set_lora(self._lora, token=self._lora_token)
 
     def set_progress_bar_config(self, **kwargs):
         self._progress = dict(kwargs)
@@ -171,19 +237,57 @@ class StableDiffusionPipeline:
                           use_cfg=st.do_cfg, v_prediction=st.vpred, x_prev=st.lat_next)
         st.latents.copy_(st.lat_next)
 
-    def _make_step_state(self, n, h, w, do_cfg, guidance_scale, context):
+    def _step_state(self, n, h, w, do_cfg, guidance_scale, n_ctx, ctx_dim):
+        """Static buffers + CUDA graphs of one call geometry.  States live on the UNet (`unet.step_cache`), not on the
+        pipeline: the reference script builds a new pipeline object per (identity, model)
+        (`/root/reference/inference_ID-Booth.py:103-107`) on the same cached components, and must not re-capture."""
         dev = self.device
+        vpred = self.scheduler.config.prediction_type == "v_prediction"
+        key = (n, h, w, do_cfg, float(guidance_scale), vpred, n_ctx, ctx_dim, self.unet.lora_topology, id(self.vae))
+        cache = self.unet.step_cache
+        st = cache.get(key) if self.use_cuda_graph else None
+        if st is not None:
+            cache[key] = cache.pop(key)      # most recently used last
+            return st
         rows = 2 * n if do_cfg else n
-        return SimpleNamespace(
-            n=n, do_cfg=do_cfg, guidance_scale=float(guidance_scale), context=context,
-            vpred=self.scheduler.config.prediction_type == "v_prediction",
+        st = SimpleNamespace(
+            key=key, n=n, do_cfg=do_cfg, guidance_scale=float(guidance_scale), context=None, vpred=vpred,
+            ctx_in=torch.zeros((rows, n_ctx, ctx_dim), dtype=f32, device=dev),
             latents=torch.zeros((n, 4, h, w), dtype=f32, device=dev),
             lat_next=torch.zeros((n, 4, h, w), dtype=f32, device=dev),
             noise=torch.zeros((n, 4, h, w), dtype=f32, device=dev),
             x2=torch.zeros((rows, 4, h, w), dtype=f32, device=dev),
             t_dev=torch.zeros((rows,), dtype=f32, device=dev),
             temb=torch.zeros((rows, self.unet.t_w_all.shape[0]), dtype=f32, device=dev),
-            coef=torch.zeros((5,), dtype=f32, device=dev), graph=None, launches_per_step=0)
+            coef=torch.zeros((5,), dtype=f32, device=dev), graph=None, ctx_graph=None, vae_graph=None, image=None,
+            launches_per_step=0, launches_ctx=0, launches_vae=0)
+        if self.use_cuda_graph:
+            cache[key] = st
+            while len(cache) > MAX_STEP_STATES:
+                cache.pop(next(iter(cache)))
+        return st
+
+    def _capture(self, fn):
+        """Warm-up run (lazy kernel-attribute setup must happen outside capture), then capture `fn` into a CUDA graph.
+        Returns (graph, result of the captured run, launches of this library inside the graph)."""
+        from . import _lib
+        fn()
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count
+        with torch.cuda.graph(g):
+            out = fn()
+        return g, out, _lib.launch_count - n0
+
+    def _time_embedding_table(self, timesteps):
+        """[steps, n_time_proj] for the call's timesteps: depends on the schedule only, so it is cached on the UNet."""
+        cache = self.unet.__dict__.setdefault("_temb_tables", {})
+        key = tuple(timesteps)
+        if key not in cache:
+            if len(cache) >= 8:
+                cache.pop(next(iter(cache)))
+            cache[key] = self.unet.time_embedding(torch.tensor(timesteps, dtype=f32, device=self.device))
+        return cache[key]
 
     # ------------------------------------------------------------------ __call__
     @torch.no_grad()
@@ -194,8 +298,16 @@ class StableDiffusionPipeline:
                  **kwargs):
         if self.unet is None:
             raise RuntimeError("call .to('cuda:N') first: the pipeline runs on a B200 only (no CPU path)")
+        for k, v in kwargs.items():
+            if k in _PARITY_KWARGS:
+                continue
+            if k in _IGNORED_CALL_KWARGS and (v is None or v == _IGNORED_CALL_KWARGS[k]):
+                continue     # a diffusers argument at its no-op value
+            raise TypeError(f"StableDiffusionPipeline.__call__: argument {k}={v!r} is not supported on this path "
+                            "(it would be silently ignored)")
         dev = self.device
         with torch.cuda.device(dev):
+            self._install_lora()
             height = height or self.unet.config.sample_size * 8
             width = width or self.unet.config.sample_size * 8
             if height % 64 or width % 64:
@@ -206,7 +318,6 @@ class StableDiffusionPipeline:
                 pe = pe.repeat_interleave(num_images_per_prompt, dim=0)
                 ne = ne.repeat_interleave(num_images_per_prompt, dim=0) if ne is not None else None
             n = pe.shape[0]
-            ctx = torch.cat([ne, pe], dim=0) if do_cfg else pe       # uncond first (A.1 step 2)
             self.scheduler.set_timesteps(num_inference_steps, device=dev)
             timesteps = self.scheduler._timesteps_list
             h, w = height // 8, width // 8
@@ -222,26 +333,28 @@ class StableDiffusionPipeline:
                 latents = noise_tape[0]
             latents = latents.to(device=dev, dtype=f32) * self.scheduler.init_noise_sigma
 
-            context = self.unet.encode_context(ctx)
-            key = (n, h, w, do_cfg, float(guidance_scale), self.unet._lora_version)
-            st = self._graphs.get(key) if self.use_cuda_graph else None
-            if st is None:
-                st = self._make_step_state(n, h, w, do_cfg, guidance_scale, context)
-                if self.use_cuda_graph:
-                    self._graphs = {key: st}     # keep one graph (its private pool holds all activations)
-            # refresh the step-invariant context projections in place (graph reads these buffers)
-            if st.context is not context:
-                for dst, src in zip(st.context.kv, context.kv):
-                    dst.copy_(src)
+            st = self._step_state(n, h, w, do_cfg, guidance_scale, pe.shape[1], pe.shape[2])
+            self._last_state = st
+            graphs = self.use_cuda_graph
+            # ---- step-invariant context projections (cross-attention K/V incl. LoRA): one graph launch per call
+            if do_cfg:                                                    # uncond first (A.1 step 2)
+                st.ctx_in[:n].copy_(ne, non_blocking=True)
+                st.ctx_in[n:].copy_(pe, non_blocking=True)
+            else:
+                st.ctx_in.copy_(pe, non_blocking=True)
+            if not graphs:
+                st.context = self.unet.encode_context(st.ctx_in)
+            else:
+                if st.ctx_graph is None:
+                    st.ctx_graph, st.context, st.launches_ctx = self._capture(lambda: self.unet.encode_context(st.ctx_in))
+                st.ctx_graph.replay()
             st.latents.copy_(latents)
-            t_table = torch.tensor(timesteps, dtype=f32, device=dev)
             # the time embedding + all 22 time_emb_proj layers depend on the timestep only: one batched call for
-            # every step of this image batch instead of one per step
-            temb_table = self.unet.time_embedding(t_table)
+            # every step, cached per schedule
+            temb_table = self._time_embedding_table(timesteps)
 
             for i in self.progress_bar(range(len(timesteps))):
                 t = timesteps[i]
-                st.t_dev.copy_(t_table[i].expand_as(st.t_dev))
                 st.temb.copy_(temb_table[i].expand_as(st.temb))
                 st.coef.copy_(self.scheduler.coef_row(i, t, dev))
                 if teacher is not None:
@@ -252,19 +365,10 @@ class StableDiffusionPipeline:
                     st.noise.copy_(randn_tensor((n, 4, h, w), generator=generator, device=dev, dtype=draw_dtype))
                 else:
                     st.noise.zero_()
-                if self.use_cuda_graph:
+                if graphs:
                     if st.graph is None:
                         saved = st.latents.clone()
-                        self._step_eager(st)               # warm-up (lazy kernel attribute setup)
-                        st.latents.copy_(saved)
-                        torch.cuda.synchronize(dev)
-                        g = torch.cuda.CUDAGraph()
-                        from . import _lib
-                        n0 = _lib.launch_count
-                        with torch.cuda.graph(g):
-                            self._step_eager(st)
-                        st.launches_per_step = _lib.launch_count - n0
-                        st.graph = g
+                        st.graph, _, st.launches_per_step = self._capture(lambda: self._step_eager(st))
                         st.latents.copy_(saved)
                     if self.step_events is not None:
                         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -277,16 +381,28 @@ class StableDiffusionPipeline:
                     self._step_eager(st)
                 if collected is not None:
                     collected.append(st.latents.clone())
-            latents = st.latents.clone()
 
             if output_type == "latent":
-                images = latents
+                images = st.latents.clone()
             else:
-                img = self.vae.decode(latents / self.vae.config.scaling_factor, output_image=True)[0]   # NHWC [0,1]
+                sf = self.vae.config.scaling_factor
+
+                def decode():
+                    return self.vae.decode(st.latents / sf, output_image=True)[0]   # NHWC [0,1]
+                if not graphs:
+                    img = decode()
+                else:
+                    if st.vae_graph is None:
+                        st.vae_graph, st.image, st.launches_vae = self._capture(decode)
+                    st.vae_graph.replay()
+                    img = st.image                       # static buffer: overwritten by the next call of this geometry
                 if output_type == "np":
-                    images = img.cpu().numpy()
+                    host = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
+                    host.copy_(img, non_blocking=True)
+                    torch.cuda.current_stream(dev).synchronize()
+                    images = host.numpy()
                 elif output_type == "pt":
-                    images = img.permute(0, 3, 1, 2)
+                    images = img.permute(0, 3, 1, 2).clone() if graphs else img.permute(0, 3, 1, 2)
                 elif output_type == "pil":
                     from PIL import Image
                     arr = (img * 255).round().to(torch.uint8).cpu().numpy()
@@ -299,6 +415,13 @@ class StableDiffusionPipeline:
         if collected is not None:
             out.step_latents = torch.stack(collected)
         return out
+
+    def launches_per_call(self, num_inference_steps: int, decode: bool = True) -> int:
+        """Kernels of this library launched by one call of the last geometry (graph replays counted by their content)."""
+        st = self._last_state
+        if st is None:
+            return 0
+        return st.launches_ctx + num_inference_steps * st.launches_per_step + (st.launches_vae if decode else 0)
 
 
 class AutoPipelineForText2Image:

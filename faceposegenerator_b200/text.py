@@ -53,14 +53,18 @@ class SnapshotTokenizer:
         return out.input_ids.to(torch.long)
 
 
-def load_tokenizer(snapshot_dir=None):
+def load_tokenizer(snapshot_dir=None, allow_hash: bool = True):
     """`SnapshotTokenizer` when a local model snapshot ships its tokenizer files, else the hashed stand-in (there is no
-    CLIP vocabulary offline, and with random-init weights the token ids only need to be deterministic)."""
+    CLIP vocabulary offline, and with random-init weights the token ids only need to be deterministic).  With real
+    weights (`allow_hash=False`) a missing tokenizer is an error: hashed ids would silently produce wrong embeddings."""
     if snapshot_dir:
         import os
         tok_dir = os.path.join(str(snapshot_dir), "tokenizer")
         if os.path.isfile(os.path.join(tok_dir, "vocab.json")) and os.path.isfile(os.path.join(tok_dir, "merges.txt")):
             return SnapshotTokenizer(tok_dir)
+    if not allow_hash:
+        raise FileNotFoundError(f"no tokenizer/vocab.json + merges.txt under {snapshot_dir!r}: the CLIP BPE vocabulary is "
+                                "required with real weights (the hashed stand-in is for random-init benchmarking only)")
     return HashTokenizer()
 
 

@@ -53,7 +53,8 @@ class UNet2DConditionModel:
         self.groups = self.cfg["norm_num_groups"]
         self.eps = self.cfg["norm_eps"]
         self._lora_version = 0
-        self._kv_cache = None
+        self._lora_token = None
+        self.step_cache = {}          # CUDA-graph step states of the pipelines that share this UNet (pipeline.py)
         self._workspace = None
         self._pack(state_dict)
         self.set_lora(None)
@@ -172,28 +173,53 @@ class UNet2DConditionModel:
         self.cross_dim = cfg["cross_attention_dim"]
 
     # ------------------------------------------------------------------ LoRA (peft lora.Linear, unmerged)
-    def set_lora(self, lora: Optional[dict]) -> None:
+    def set_lora(self, lora: Optional[dict], token=None) -> None:
         """lora: {module_path: (down [r,in], up [out,r], scale)} or None.  Only the small packed
-        adapter tensors change; base weights stay bit-identical (adapter hot-swap)."""
+        adapter tensors change; base weights stay bit-identical (adapter hot-swap).
+
+        The packed adapter buffers are PERSISTENT: a second adapter set of the same layout is copied into the same
+        device buffers, so CUDA graphs captured with adapters installed stay valid across `load_lora_weights`
+        (`/root/reference/inference_ID-Booth.py:103-107` swaps adapters every 21 images).  `lora_topology` (which fused
+        projections carry adapters) is what a captured graph depends on; `token` identifies the owner of the installed
+        set (several pipelines may share this UNet)."""
         known = set()
+        topo = []
         for t in self.transformers:
             tb = t.path + ".transformer_blocks.0"
             get = (lambda k: lora.get(k)) if lora else (lambda k: None)
             a1, a2 = tb + ".attn1", tb + ".attn2"
             known.update(f"{a}.{m}" for a in (a1, a2) for m in ("to_q", "to_k", "to_v", "to_out.0"))
-            t.lora = {
+            packed = {
                 "qkv": pack_lora([get(a1 + ".to_q"), get(a1 + ".to_k"), get(a1 + ".to_v")], self.device, seg_n=t.c, k=t.c),
                 "o1": pack_lora([get(a1 + ".to_out.0")], self.device, seg_n=t.c, k=t.c),
                 "q2": pack_lora([get(a2 + ".to_q")], self.device, seg_n=t.c, k=t.c),
                 "kv2": pack_lora([get(a2 + ".to_k"), get(a2 + ".to_v")], self.device, seg_n=t.c, k=self.cross_dim),
                 "o2": pack_lora([get(a2 + ".to_out.0")], self.device, seg_n=t.c, k=t.c),
             }
+            bufs = t.__dict__.setdefault("lora_buf", {})
+            active = {}
+            for name, (ld, lu) in packed.items():
+                if ld is None:
+                    active[name] = (None, None)       # the buffers (if any) stay alive for graphs captured with them
+                else:
+                    old = bufs.get(name)
+                    if old is not None and old[0].shape == ld.shape and old[1].shape == lu.shape:
+                        old[0].copy_(ld)
+                        old[1].copy_(lu)
+                    else:
+                        if old is not None:
+                            self.step_cache.clear()   # captured graphs hold the old buffers' addresses
+                        bufs[name] = (ld, lu)
+                    active[name] = bufs[name]
+                topo.append(ld is not None)
+            t.lora = active
         if lora:
             unknown = set(lora) - known
             if unknown:
                 raise KeyError(f"LoRA targets not present in this UNet: {sorted(unknown)[:4]} ...")
+        self.lora_topology = tuple(topo)
+        self._lora_token = token
         self._lora_version += 1
-        self._kv_cache = None
 
     # ------------------------------------------------------------------ helpers
     def _ws(self):

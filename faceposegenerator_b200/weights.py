@@ -236,15 +236,17 @@ def load_lora_state(path_or_dir: str, weight_name: str = LORA_FILE) -> dict:
     """Reads a LoRA checkpoint into {module_path: (down, up, scale)}.  Accepts the
     diffusers spelling (`.lora.down/up`), the peft spelling (`.lora_A/.lora_B[.adapter]`),
     the legacy attn-processor spelling (`.processor.to_q_lora.down`), optional
-    `.alpha` scalars (scale = alpha / r; absent => 1.0), and ignores `text_encoder.*`."""
+    `.alpha` scalars (scale = alpha / r; absent => 1.0); `text_encoder.*` tensors are skipped with a warning."""
     from safetensors.torch import load_file
     fn = path_or_dir if os.path.isfile(path_or_dir) else os.path.join(path_or_dir, weight_name)
     if not os.path.isfile(fn):
         raise FileNotFoundError(f"LoRA weights not found: {fn}")
     raw = load_file(fn)
     downs, ups, alphas = {}, {}, {}
+    skipped = 0
     for key, t in raw.items():
         if key.startswith("text_encoder."):
+            skipped += 1     # `train_text_encoder=True` checkpoints (train_ID-Booth.py:700-707): not applied on this path
             continue
         if key.endswith(".alpha"):
             p = key[:-len(".alpha")]
@@ -258,6 +260,10 @@ def load_lora_state(path_or_dir: str, weight_name: str = LORA_FILE) -> dict:
         mod = f"{m.group('path')}.{proj}"
         which = m.group("legacy") or m.group("dd") or {"A": "down", "B": "up"}[m.group("peft")]
         (downs if which == "down" else ups)[mod] = t.float()
+    if skipped:
+        import warnings
+        warnings.warn(f"{fn}: {skipped} text_encoder.* LoRA tensors are NOT applied (the CLIP tower runs without adapters "
+                      "on this path); images will differ from a diffusers run that loads them", stacklevel=2)
     if set(downs) != set(ups):
         raise KeyError("LoRA checkpoint has unpaired down/up tensors")
     out = {}

@@ -297,13 +297,14 @@ class DDPMSchedulerRef:
 # ----------------------------------------------------------------------------- pipeline loop (App. A.1)
 def denoise_loop(unet_sd, lora, prompt_embeds: Tensor, negative_embeds: Tensor, noise_tape: Tensor,
                  num_steps: int = 30, guidance_scale: float = 5.0, cfg: dict = UNET_SD21,
-                 teacher: Optional[Tensor] = None, max_steps: Optional[int] = None):
+                 teacher: Optional[Tensor] = None, max_steps: Optional[int] = None,
+                 prediction_type: str = "epsilon"):
     """Steps 3-6 of `StableDiffusionPipeline.__call__` (a1; `inference_ID-Booth.py:138`).
     noise_tape[0] = initial latents draw, noise_tape[1+i] = draw of step i.
     Returns the per-step latents [steps+1, n, 4, h, w] (index 0 = initial) and the
     per-step CFG-combined eps.  `teacher`: if given (same shape as the returned
     latents), step i starts from teacher[i] instead of the free-running latent."""
-    sch = DDPMSchedulerRef()
+    sch = DDPMSchedulerRef(prediction_type=prediction_type)   # "v_prediction": the 768-v checkpoints (App. A.0)
     sch.set_timesteps(num_steps)
     ctx = torch.cat([negative_embeds, prompt_embeds], dim=0)  # uncond first
     lat = noise_tape[0] * sch.init_noise_sigma

@@ -4,6 +4,9 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# no SD2.1 checkpoint exists offline: the suites run on deterministic random-init weights (an explicit opt-in, see
+# faceposegenerator_b200.pipeline.random_weights_allowed)
+os.environ.setdefault("IDB_ALLOW_RANDOM_WEIGHTS", "1")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

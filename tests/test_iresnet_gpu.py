@@ -127,8 +127,8 @@ def test_identity_loss_end_to_end(model, golden_sd, cuda_dev):
 
 
 def test_config5_training_forward_identity(model, golden_sd, cuda_dev):
-    """Config 5 slice (B = 2 here to keep the CPU oracle to seconds): UNet(noisy, t, ctx) -> pred_original_sample ->
-    VAE decode -> crop -> 112x112 -> IResNet, against the same chain in the fp32 oracles."""
+    """Config 5 at its stated batch (B = 4, no CFG, `train_ID-Booth.py:1040-1046,1109-1133`): UNet(noisy, t, ctx) ->
+    pred_original_sample -> VAE decode -> crop -> 112x112 -> IResNet, against the same chain in the fp32 oracles."""
     from faceposegenerator_b200 import DDPMScheduler
     from faceposegenerator_b200.iresnet import training_forward_identity
     from faceposegenerator_b200.unet import UNet2DConditionModel
@@ -143,17 +143,18 @@ def test_config5_training_forward_identity(model, golden_sd, cuda_dev):
     vae = AutoencoderKL(vsd, device=cuda_dev)
     sched = DDPMScheduler.from_pretrained("stabilityai/stable-diffusion-2-1-base", subfolder="scheduler")
     g = torch.Generator().manual_seed(0)
-    x0_true = torch.randn(2, 4, 64, 64, generator=g)
-    noise = torch.randn(2, 4, 64, 64, generator=g)
-    ctx = torch.randn(2, 77, 1024, generator=g)
-    ts = [437, 112]
+    nb = 4
+    x0_true = torch.randn(nb, 4, 64, 64, generator=g)
+    noise = torch.randn(nb, 4, 64, 64, generator=g)
+    ctx = torch.randn(nb, 77, 1024, generator=g)
+    ts = [437, 112, 871, 3]
     ref_s = sd21.DDPMSchedulerRef()
     noisy = ref_s.add_noise(x0_true, noise, torch.tensor(ts))
-    bbox = torch.tensor([[96, 96, 416, 416]] * 2, dtype=torch.int32)
+    bbox = torch.tensor([[96, 96, 416, 416]] * nb, dtype=torch.int32)
     eps, x0, emb = training_forward_identity(unet, vae, sched, model, noisy.to(cuda_dev), ts, ctx.to(cuda_dev), bbox.to(cuda_dev))
     with torch.no_grad():
-        eps_r = torch.cat([sd21.unet_forward(usd, noisy[i:i + 1], ts[i], ctx[i:i + 1], lora) for i in range(2)])
-        x0_r = torch.cat([ref_s.step(eps_r[i:i + 1], ts[i], noisy[i:i + 1], torch.zeros(1, 4, 64, 64))[1] for i in range(2)])
+        eps_r = torch.cat([sd21.unet_forward(usd, noisy[i:i + 1], ts[i], ctx[i:i + 1], lora) for i in range(nb)])
+        x0_r = torch.cat([ref_s.step(eps_r[i:i + 1], ts[i], noisy[i:i + 1], torch.zeros(1, 4, 64, 64))[1] for i in range(nb)])
         img_r = (sd21.vae_decode(vsd, x0_r / 0.18215) * 0.5 + 0.5).clamp(0, 1)                 # NCHW
         crop = (img_r * 255)[:, :, 96:416, 96:416]
         xin = ((F.interpolate(crop, size=(112, 112), mode="bilinear", align_corners=False) / 255) - 0.5) / 0.5

@@ -137,7 +137,10 @@ def test_pipeline_teacher_forced_and_free_running(world):
     free = pipe(**kw).step_latents
     drift = [rel(free[i], ref_l[i + 1]) for i in range(30)]
     print("free-running latent rel-L2: final %.3e max %.3e" % (drift[-1], max(drift)))
-    assert drift[-1] < 5e-2
+    # north_star gate on the free-running trajectory too (measured 8.9e-3 final / 9.1e-3 max in round 1): every step of the
+    # loop, not only the teacher-forced one, stays within the bf16 tolerance of the fp32 oracle
+    assert drift[-1] <= 1e-2
+    assert max(drift) <= 1e-2
 
 
 def test_clip_text_encoder_vs_transformers_golden(cuda_dev):
