@@ -1,5 +1,6 @@
 // C-ABI plumbing: version, error reporting, device checks, tensor-map encoding.
 #include <mutex>
+#include <unordered_map>
 
 #include "../../include/idb.h"
 #include <cstdlib>
@@ -77,11 +78,46 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return make_tmap(out, base, 2, 128, rank, dims, strides_bytes, box);
 }
 
+// Encoded tensor maps are cached per (pointer, element size, swizzle, shape, strides, box) -- SURVEY 8(b): an eager caller
+// that re-issues the same layer on the same buffers (the allocator hands a loop the same blocks again) pays a hash lookup
+// instead of up to nine cuTensorMapEncodeTiled calls per GEMM.  A map is a pure function of the key, so a stale entry can
+// never be wrong, only unused; the table is dropped wholesale when it fills up.
+struct TmapKey {
+  uint64_t v[16];   // base, (elem | swizzle << 8 | rank << 16), dims[5], strides[4], box[5]
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (int i = 0; i < 16; ++i) h = (h ^ k.v[i]) * 0x100000001b3ull;
+    return static_cast<size_t>(h ^ (h >> 29));
+  }
+};
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmaps;
+static std::mutex g_tmap_mu;
+static const bool g_tmap_cache_on = !(getenv("IDB_TMAP_CACHE") && atoi(getenv("IDB_TMAP_CACHE")) == 0);
+constexpr size_t TMAP_CACHE_MAX = 1 << 15;
+
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(IDB_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(IDB_E_BADARG, "TMA operand must be 16-byte aligned");
+  if (rank < 1 || rank > 5) return fail(IDB_E_BADARG, "TMA rank must be 1..5");
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.v[0] = reinterpret_cast<uintptr_t>(base);
+  key.v[1] = static_cast<uint64_t>(elem_bytes) | (static_cast<uint64_t>(swizzle_bytes) << 8) | (static_cast<uint64_t>(rank) << 16);
+  for (int i = 0; i < rank; ++i) key.v[2 + i] = dims[i], key.v[11 + i] = box[i];
+  for (int i = 0; i + 1 < rank; ++i) key.v[7 + i] = strides_bytes[i];
+  if (g_tmap_cache_on) {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) {
+      *out = it->second;
+      return IDB_OK;
+    }
+  }
   cuuint64_t gdims[5];
   cuuint64_t gstr[4];
   cuuint32_t gbox[5];
@@ -110,6 +146,11 @@ int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_by
     d += " box";
     for (int i = 0; i < rank; ++i) d += " " + std::to_string(box[i]);
     return fail(IDB_E_CUDA, d);
+  }
+  if (g_tmap_cache_on) {
+    std::lock_guard<std::mutex> lk(g_tmap_mu);
+    if (g_tmaps.size() >= TMAP_CACHE_MAX) g_tmaps.clear();
+    g_tmaps.emplace(key, *out);
   }
   return IDB_OK;
 }

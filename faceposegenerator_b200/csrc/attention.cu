@@ -894,20 +894,18 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
   p.causal = a->causal ? 1 : 0;
   if (p.causal && a->t_kv > 96) return fail(IDB_E_UNSUPPORTED, "idb_attention: causal masking is implemented for t_kv <= 96 (short-context kernel)");
 
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+  static PerDeviceOnce configured;
+  {
+    cudaError_t e = ensure_dynamic_smem(attention_kernel, ATT_SMEM, configured);
     if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("cudaFuncSetAttribute(attention): ") + cudaGetErrorString(e));
-    configured = true;
   }
   static const int force_variant = getenv("IDB_ATTN_VARIANT") ? atoi(getenv("IDB_ATTN_VARIANT")) : 0;
   const bool use256 = force_variant ? (force_variant == 256) : (a->t_q >= 1024 && a->t_kv >= 512);   // IDB_ATTN_VARIANT: 256 / 128 forces a kernel (profiling)
   if (a->t_kv <= 96 && (force_variant == 0 || p.causal)) {   // short context (cross-attention): K/V resident, chunks of query tiles per CTA
-    static bool configured4 = false;
-    if (!configured4) {
-      cudaError_t e4 = cudaFuncSetAttribute(attention_x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATX_SMEM);
+    static PerDeviceOnce configured4;
+    {
+      cudaError_t e4 = ensure_dynamic_smem(attention_x_kernel, ATX_SMEM, configured4);
       if (e4 != cudaSuccess) return fail(IDB_E_CUDA, std::string("cudaFuncSetAttribute(attention_x): ") + cudaGetErrorString(e4));
-      configured4 = true;
     }
     const int n_qtiles = (a->t_q + ATT_BM - 1) / ATT_BM;
     const long long units = static_cast<long long>(n_qtiles) * a->heads * a->batch;
@@ -926,14 +924,13 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
     if (rs_poly == 1) kern = attention_rs_kernel<1>;
     else if (rs_poly == 7) kern = attention_rs_kernel<7>;
     else if (rs_poly == 32) kern = attention_rs_kernel<32>;
-    static bool configured3 = false;
-    if (!configured3) {
+    static PerDeviceOnce configured3[4];
+    {
       void (*all[4])(AttnParams, int, int, int) = {attention_rs_kernel<1>, attention_rs_kernel<3>, attention_rs_kernel<7>, attention_rs_kernel<32>};
       for (int i = 0; i < 4; ++i) {
-        cudaError_t e3 = cudaFuncSetAttribute(all[i], cudaFuncAttributeMaxDynamicSharedMemorySize, AT3_SMEM);
+        cudaError_t e3 = ensure_dynamic_smem(all[i], AT3_SMEM, configured3[i]);
         if (e3 != cudaSuccess) return fail(IDB_E_CUDA, std::string("cudaFuncSetAttribute(attention_rs): ") + cudaGetErrorString(e3));
       }
-      configured3 = true;
     }
     // 256-query units; the ones that would form a partial last wave run as two single-lane CTAs each
     const int qblocks = (a->t_q + 2 * ATT_BM - 1) / (2 * ATT_BM);

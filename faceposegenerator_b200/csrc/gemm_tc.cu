@@ -2,17 +2,17 @@
 //
 //   D[M, N] = epilogue( sum_k im2col(A)[M, k] * W[N, k] )          bf16 x bf16 -> fp32 (TMEM)
 //
-// One CTA per SM, 320 threads:
-//   warps 0-7 : epilogue   (TMEM -> registers -> bias / time-emb / LoRA-up / GEGLU / residual -> global)
-//   warp  8   : TMA producer (im2col by signed TMA coordinates over the NHWC image; halo = OOB zero fill)
-//   warp  9   : tcgen05.mma issuer (one elected lane), owns the TMEM allocation
-// Pipelines: STAGES-deep smem ring (full/empty mbarriers) and a double-buffered TMEM
-// accumulator (tmem_full/tmem_empty) so the epilogue of tile i overlaps the mainloop of tile i+1.
+// One CTA per SM, 576 threads:
+//   warps 0-15 : epilogue   (TMEM -> registers -> bias / time-emb / GEGLU / residual -> smem staging -> TMA store)
+//   warp  16   : TMA producer (im2col by signed TMA coordinates over the NHWC image; halo = OOB zero fill)
+//   warp  17   : tcgen05.mma issuer (one elected lane), owns the TMEM allocation
+// Pipelines: STAGES-deep smem ring (full/empty mbarriers) and a ring of 2-4 TMEM accumulator buffers
+// (tmem_full/tmem_empty) so the epilogue of tile i overlaps the mainloop of tiles i+1...
 // A tile is 128 output pixels laid out as a (BW x BH x BB) rectangle of the (x, y, image) space,
 // so a 3x3 tap is one 4-D TMA box shifted by (dx-1, dy-1); a stride-2 conv uses a 5-D view
 // [B, H/2, 2, W/2, 2*C] of the same tensor.  A Linear is the 1x1 "image" [1, 1, M, K].
-// A fused rank-r LoRA rides along as 16 extra UMMA N-columns (x A^T kept in TMEM) and is
-// applied as 4-16 FMAs per output in the epilogue -- base weights are never touched.
+// A fused rank-r LoRA rides along as 16 extra UMMA N-columns (T = x A^T in TMEM); the epilogue warps round T to a
+// bf16 operand tile and the MMA warp adds T U^T with one more K=16 UMMA -- base weights are never touched.
 //
 // CG = 2 (`cta_group::2`): two CTAs of a cluster (an SM pair) share one 256 x BLOCK_N tile.  Each CTA
 // TMA-loads its own 128 A rows and HALF of the B tile; the leader issues tcgen05.mma.cta_group::2
@@ -895,11 +895,10 @@ static int launch_gemm_e(const GemmParams& p, int grid, cudaStream_t stream) {
                              epi_bias_bytes(BLOCK_N * NSUB) + (LORA ? 1024 + A_TILE_BYTES + 2 * (BLOCK_N / CG) * BLOCK_K * 2 : 0);   // ring + slack + barriers + staging + bias (+ LoRA T / U tiles)
   static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
   auto kern = gemm_tc_kernel<BLOCK_N, STAGES, LORA, CG, EPI, NSUB>;
-  static bool configured = false;  // per instantiation
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  static PerDeviceOnce configured;  // per instantiation (and per device inside)
+  {
+    cudaError_t e = ensure_dynamic_smem(kern, smem_bytes, configured);
     if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    configured = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <cstring>
 #include <string>
 
@@ -22,6 +23,23 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // general form: elem_bytes in {2 (bf16), 4 (fp32)}, swizzle_bytes in {0, 32, 64, 128}
 int make_tmap(CUtensorMap* out, const void* base, int elem_bytes, int swizzle_bytes, int rank, const uint64_t* dims,
               const uint64_t* strides_bytes, const uint32_t* box);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: one flag per (kernel instantiation, device),
+// so a second GPU used by the same process gets its own opt-in.  Racing threads at worst set the attribute twice.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+};
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K kern, int bytes, PerDeviceOnce& once) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (once.done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) once.done.fetch_or(bit, std::memory_order_release);
+  return e;
+}
 
 // kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-dependent-launch attribute (IDB_PDL=0 disables)
 bool pdl_enabled();

@@ -23,6 +23,10 @@ def _chk(t: Optional[torch.Tensor], dtype, name: str, allow_none: bool = False):
         raise ValueError(f"{name} is required")
     if not t.is_cuda:
         raise RuntimeError(f"{name} must be a CUDA tensor (no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        # launches go to the CURRENT device's current stream: a tensor of another GPU would be read by the wrong device
+        raise RuntimeError(f"{name} lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                           "wrap the call in `with torch.cuda.device(tensor.device):`")
     if t.dtype != dtype:
         raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
     if not t.is_contiguous():

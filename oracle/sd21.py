@@ -32,6 +32,12 @@ VAE_SD21 = dict(latent_channels=4, out_channels=3, block_out_channels=(128, 256,
                 layers_per_block=2, norm_num_groups=32, norm_eps=1e-6, scaling_factor=0.18215)
 
 
+# Attention as an explicit softmax(q k^T / sqrt(d)) v (default: the oracle's arithmetic is spelled out), or through
+# `F.scaled_dot_product_attention` -- the call diffusers' AttnProcessor2_0 makes -- when bench.py times this module graph
+# on the GPU as the "library" comparator.  Same mathematics either way.
+USE_SDPA = False
+
+
 # ----------------------------------------------------------------------------- primitives
 def _linear(sd, name: str, x: Tensor, lora: Optional[Lora] = None) -> Tensor:
     """nn.Linear, optionally wrapped by an unmerged peft LoRA adapter (a8)."""
@@ -87,8 +93,11 @@ def attention(sd, p: str, x: Tensor, ctx: Tensor, heads: int, lora: Optional[Lor
     q = q.view(B, T, heads, d).transpose(1, 2)
     k = k.view(B, -1, heads, d).transpose(1, 2)
     v = v.view(B, -1, heads, d).transpose(1, 2)
-    s = torch.softmax((q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(d)), dim=-1)
-    o = (s @ v).transpose(1, 2).reshape(B, T, C)
+    if USE_SDPA:
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, T, C)
+    else:
+        s = torch.softmax((q @ k.transpose(-1, -2)) * (1.0 / math.sqrt(d)), dim=-1)
+        o = (s @ v).transpose(1, 2).reshape(B, T, C)
     return _linear(sd, p + ".to_out.0", o, lora)
 
 

@@ -22,7 +22,16 @@ def _worker(rank, world, port, n_units, q):
         mine = shard_units(n_units, rank, world)
         local = torch.stack([_fake_image(u) for u in mine]) if mine else torch.zeros((0, 8, 8, 3), dtype=torch.uint8)
         full = gather_images(local, n_units, rank, world)
-        q.put((rank, mine, full.clone()))
+        # the asynchronous double-buffered gather of bench.py: three submissions, each result read one call later
+        from faceposegenerator_b200.parallel import ImageGather, unit_index
+        ig = ImageGather(n_units, rank, world, (8, 8, 3), "cpu")
+        rounds = []
+        for k in range(3):
+            ig.submit((local.int() + k).clamp(max=255).to(torch.uint8))
+            if k > 0:
+                assert ig.last is not None
+        buf = ig.wait()
+        q.put((rank, mine, full.clone(), buf[unit_index(n_units, world)].clone()))
     finally:
         dist.destroy_process_group()
 
@@ -59,8 +68,9 @@ def test_two_rank_gloo_sweep_matches_single_process():
     for n_units in (6, 7):   # even and ragged
         ref = torch.stack([_fake_image(u) for u in range(n_units)])
         res = _run(n_units)
-        ranks = sorted(r for r, _, _ in res)
+        ranks = sorted(r[0] for r in res)
         assert ranks == [0, 1]
-        for rank, mine, full in res:
+        for rank, mine, full, last_async in res:
             assert mine == list(range(rank, n_units, 2))
             assert full.shape == ref.shape and torch.equal(full, ref)
+            assert torch.equal(last_async, (ref.int() + 2).clamp(max=255).to(torch.uint8))   # third submission, unit order

@@ -95,12 +95,18 @@ class _RecordingPipeline:
 
     def __call__(self, **kwargs):
         gen = kwargs.pop("generator")
+        tape = kwargs.pop("noise_tape", None)
         self.log["calls"].append([len(self.log["pipelines"]) - 1, gen.initial_seed(), kwargs["prompt"]])
         self.log["kwargs"].append({k: v for k, v in kwargs.items() if k != "prompt"})
-        acc = 0.0
-        for _ in range(31):
-            acc += float(torch.randn((1, 4, 64, 64), generator=gen, device="cpu", dtype=torch.float16).float().mean())
-        img = np.full((1, 8, 8, 3), 0.5 + 0.4 * np.tanh(acc * 10), dtype=np.float32)
+        if tape is not None:     # batched mode: the caller pre-drew every image's 31 tensors ([31, n, 4, 64, 64])
+            assert tape.shape[0] == 31 and tape.shape[1] == len(kwargs["prompt"]) and tape.dtype == torch.float16
+            accs = [sum(float(tape[d, k].float().mean()) for d in range(31)) for k in range(tape.shape[1])]
+        else:
+            acc = 0.0
+            for _ in range(31):
+                acc += float(torch.randn((1, 4, 64, 64), generator=gen, device="cpu", dtype=torch.float16).float().mean())
+            accs = [acc]
+        img = np.stack([np.full((8, 8, 3), 0.5 + 0.4 * np.tanh(a * 10), dtype=np.float32) for a in accs])
         return type("Out", (), {"images": img})()
 
 
@@ -120,7 +126,9 @@ def _run(log, **kw):
     saved = log.setdefault("saved", [])
 
     def save_fn(tensor, fp, **kwargs):
-        saved.append([fp, list(tensor.shape), kwargs])
+        base, ext = os.path.splitext(fp)                 # the writer saves to <name>.tmp<ext> and renames into place
+        assert base.endswith(".tmp"), "images must be written atomically"
+        saved.append([base[:-4] + ext, list(tensor.shape), kwargs])
         from torchvision.utils import save_image
         save_image(tensor, fp=fp, **kwargs)
     return run_sweep(SweepConfig(), device="cpu", writer=_SyncWriter(save_fn), pipeline_cls=_RecordingPipeline,
@@ -182,6 +190,37 @@ def test_skip_existing_resumes_with_identical_images(tree):
     assert totals["generated"] == 0 and idle["pipelines"] == [] and idle["saved"] == []
 
 
+def test_batched_sweep_feeds_every_image_the_scripts_own_generator_draws(tree):
+    """`batch_prompts=4`: prompts go through the pipeline four at a time (last call of a run padded to four rows), and
+    every image still gets exactly the 31 generator draws the one-prompt-per-call script gives it -- the fake image is
+    a function of those draws, so the files must be byte-identical to the unbatched sweep, also after a resume."""
+    def read(path):
+        with open(path, "rb") as f:
+            return f.read()
+    first = {"pipelines": [], "calls": [], "kwargs": []}
+    _run(first, max_identities=1)
+    files = [s[0] for s in first["saved"]]
+    before = {p: read(p) for p in files}
+    for p in files:
+        os.remove(p)
+    b = {"pipelines": [], "calls": [], "kwargs": []}
+    totals = _run(b, max_identities=1, batch_prompts=4)
+    assert totals["generated"] == 63
+    assert [s[0] for s in b["saved"]] == files                      # same files, same order
+    assert {p: read(p) for p in files} == before
+    assert len(b["calls"]) == 3 * 6 and all(len(c[2]) == 4 for c in b["calls"])      # 21 prompts = 5 x 4 + 1 (padded)
+    flat = [p for c in b["calls"][:6] for p in c[2]]
+    assert flat[:21] == [c[2] for c in first["calls"][:21]] and flat[21:] == [flat[20]] * 3
+    # resume in batched mode: images 3..9 of the second model's run are lost
+    pngs = [p for p in files if p.endswith(".png")]
+    lost = pngs[21 + 3:21 + 10]
+    for p in lost:
+        os.remove(p)
+    again = {"pipelines": [], "calls": [], "kwargs": []}
+    totals = _run(again, max_identities=1, batch_prompts=4, skip_existing=True)
+    assert totals["generated"] == 7 and {p: read(p) for p in files} == before
+
+
 def test_async_writer_writes_everything_and_reports_errors(tmp_path):
     from faceposegenerator_b200.sweep import AsyncImageWriter
     w = AsyncImageWriter(workers=3, max_pending=4)
@@ -196,6 +235,26 @@ def test_async_writer_writes_everything_and_reports_errors(tmp_path):
     w.save(torch.zeros(1, 3, 4, 4), str(tmp_path / "b.png"))
     with pytest.raises(OSError):
         w.close()
+    # an error surfaces at the NEXT save, not only at the end of the sweep; nothing is left under the final name
+    w = AsyncImageWriter(workers=1, save_fn=boom)
+    w.save(torch.zeros(1, 3, 4, 4), str(tmp_path / "c.png"))
+    import time
+    time.sleep(0.3)
+    with pytest.raises(OSError):
+        w.save(torch.zeros(1, 3, 4, 4), str(tmp_path / "d.png"))
+    assert not os.path.exists(tmp_path / "c.png") and not os.path.exists(tmp_path / "c.tmp.png")
+
+    def half(tensor, fp, **kw):          # a writer that dies mid-file
+        with open(fp, "wb") as f:
+            f.write(b"\x89PNG truncated")
+        raise KeyboardInterrupt
+    from faceposegenerator_b200.sweep import _atomic_save, _existing_image
+    with pytest.raises(KeyboardInterrupt):
+        _atomic_save(half, torch.zeros(1), str(tmp_path / "e.png"), {})
+    assert not os.path.exists(tmp_path / "e.png")
+    with open(tmp_path / "f.png", "wb") as f:
+        f.write(b"\x89PNG truncated")
+    assert not _existing_image(str(tmp_path / "f.png"))      # skip_existing regenerates an undecodable file
 
 
 # ---------------------------------------------------------------------------------------------- N > 1 over gloo
