@@ -322,15 +322,18 @@ class StableDiffusionPipeline:
             timesteps = self.scheduler._timesteps_list
             h, w = height // 8, width // 8
             draw_dtype = self.torch_dtype
-            if latents is None:
-                latents = randn_tensor((n, 4, h, w), generator=generator, device=dev, dtype=draw_dtype)
-            # parity hooks (not part of the diffusers surface): a pre-drawn noise tape shared with the
-            # oracle, teacher forcing of each step's input latent, and per-step latent collection
+            # extensions of the diffusers surface: `noise_tape` [1 + steps, n, 4, h, w] = every generator draw of the call,
+            # pre-drawn by the caller (the batched sweep, the parity tests: shared with the oracle) -- the generator is then
+            # not touched at all; teacher forcing of each step's input latent; per-step latent collection
             noise_tape = kwargs.get("noise_tape")
             teacher = kwargs.get("teacher_latents")
             collected = [] if kwargs.get("collect_latents") else None
             if noise_tape is not None:
+                if tuple(noise_tape.shape) != (1 + len(timesteps), n, 4, h, w):
+                    raise ValueError(f"noise_tape must be [{1 + len(timesteps)}, {n}, 4, {h}, {w}], got {tuple(noise_tape.shape)}")
                 latents = noise_tape[0]
+            elif latents is None:
+                latents = randn_tensor((n, 4, h, w), generator=generator, device=dev, dtype=draw_dtype)
             latents = latents.to(device=dev, dtype=f32) * self.scheduler.init_noise_sigma
 
             st = self._step_state(n, h, w, do_cfg, guidance_scale, pe.shape[1], pe.shape[2])

@@ -345,7 +345,7 @@ def run_identity(unit: IdentityUnit, cfg: SweepConfig, device: str, writer: Asyn
             m = len(pending)
             prompts = [j.prompt for j, _, _ in pending] + [pending[-1][0].prompt] * (batch_prompts - m)
             tapes = [t for _, _, t in pending] + [torch.zeros_like(pending[0][2])] * (batch_prompts - m)
-            out = pipe(prompt=prompts, generator=generator, noise_tape=torch.cat(tapes, dim=1), **call_kw)
+            out = pipe(prompt=prompts, generator=generator, noise_tape=torch.cat(tapes, dim=1), **call_kw)   # (the tape replaces every draw)
             images = torch.Tensor(out.images)
             for k, (job, slot, _) in enumerate(pending):
                 comparison[slot] = images[k:k + 1]
