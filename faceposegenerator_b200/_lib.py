@@ -34,6 +34,7 @@ class GemmConvArgs(C.Structure):
         ("out_f32", c_void_p), ("out_bf16", c_void_p),
         ("k_splits", c_int32), ("workspace", c_void_p), ("workspace_bytes", c_size_t),
         ("stats_partials", c_void_p),
+        ("stats_image_sums", c_void_p), ("stats_hw", c_int32), ("stats_gran", c_int32),
         ("prelu", c_void_p),
         ("tap_off_x", c_int32), ("tap_off_y", c_int32),
         ("out_scale", c_int32), ("out_phase_x", c_int32), ("out_phase_y", c_int32),
@@ -62,6 +63,7 @@ class GroupNormArgs(C.Structure):
         ("out_norm", c_void_p), ("out_raw", c_void_p),
         ("partials", c_void_p),
         ("x0_stats", c_void_p), ("x1_stats", c_void_p), ("x0_stats_phases", c_int32),
+        ("x0_sums", c_void_p), ("x1_sums", c_void_p), ("sums_gran", c_int32),
     ]
 
 
@@ -85,6 +87,7 @@ EXPORTS = {
     "idb_num_sms": (c_int32, []),
     "idb_gemm_conv": (c_int32, [C.POINTER(GemmConvArgs), c_void_p]),
     "idb_gemm_conv_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
+    "idb_sizeof_args": (c_size_t, [c_int32]),
     "idb_attention": (c_int32, [C.POINTER(AttentionArgs), c_void_p]),
     "idb_groupnorm": (c_int32, [C.POINTER(GroupNormArgs), c_void_p]),
     "idb_groupnorm_workspace_bytes": (c_size_t, [c_int32, c_int32]),
@@ -110,7 +113,7 @@ EXPORTS = {
 _lib: Optional[C.CDLL] = None
 trace = None      # profiling only: set to a list to record (entry point, description) per call
 launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"idb_groupnorm": 2, "idb_time_embed": 4}   # (a lower bound for split-K GEMMs)
+_LAUNCHES_PER_CALL = {"idb_time_embed": 4}   # entry points that always launch more than one kernel
 
 
 def load() -> C.CDLL:
@@ -126,6 +129,10 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
+        for which, struct in enumerate((GemmConvArgs, AttentionArgs, GroupNormArgs, TimeEmbedArgs)):
+            if lib.idb_sizeof_args(which) != C.sizeof(struct):   # a stale binding would make the library read past the struct
+                raise RuntimeError(f"{struct.__name__}: ctypes layout ({C.sizeof(struct)} B) does not match include/idb.h "
+                                   f"({lib.idb_sizeof_args(which)} B); rebuild the library / update _lib.py")
         _lib = lib
     return _lib
 
@@ -149,11 +156,12 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def call(name: str, *args, desc=None) -> None:
+def call(name: str, *args, desc=None, launches: int = 0) -> None:
+    """`launches`: kernels this call enqueues when the caller knows (idb_groupnorm: 1 with producer sums, else 2)."""
     global launch_count
     if trace is not None:
         trace.append((name, desc))
     rc = getattr(load(), name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (code {rc}): {last_error()}")
-    launch_count += _LAUNCHES_PER_CALL.get(name, 1)
+    launch_count += launches or _LAUNCHES_PER_CALL.get(name, 1)

@@ -168,5 +168,15 @@ extern "C" int idb_last_error(char* buf, size_t n) {
   return IDB_OK;
 }
 
+extern "C" size_t idb_sizeof_args(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(idb_gemm_conv_args);
+    case 1: return sizeof(idb_attention_args);
+    case 2: return sizeof(idb_groupnorm_args);
+    case 3: return sizeof(idb_time_embed_args);
+    default: return 0;
+  }
+}
+
 extern "C" int idb_device_check(void) { return idb::require_sm100(); }
 extern "C" int idb_num_sms(void) { return idb::num_sms(); }

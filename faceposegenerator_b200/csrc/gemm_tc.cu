@@ -88,7 +88,19 @@ struct GemmParams {
   float* workspace;
   long long stats_rowblock0;   // first row block of this call inside stats (phased output)
   float2* stats;   // optional [ceil(M/32)][N] (sum, sum of squares) over each 32-row block of the fp32 output
+  // optional per-IMAGE sums of the fp32 output over GRANULES of `gran` consecutive channels (gran divides the group size
+  // of every GroupNorm that will consume the tensor), in 64-bit FIXED POINT, accumulated with integer atomics straight
+  // from the epilogue: integer addition commutes, so the result is bit-identical whatever the arrival order (no
+  // counters, no fences, no finalize pass).  [n_img][N_out / gran][2] = (sum * 2^32, sum of squares * 2^24); zero on entry.
+  unsigned long long* isums;
+  FastDiv fd_rbpi;             // row blocks per image of THIS call's raster
+  FastDiv fd_gran;             // channels per granule
+  int n_gran;                  // N_out / gran
+  long long n_rowblocks;       // row blocks of this call (M / 32)
 };
+
+constexpr float ISUM_SCALE_S = 4294967296.0f;    // 2^32: |sum of an (image, channel)| < 2^31
+constexpr float ISUM_SCALE_SS = 16777216.0f;     // 2^24: sum of squares < 2^39 (rms 11,000 over 4096 pixels)
 
 template <int CG>
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, int rank) {
@@ -471,7 +483,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
     const int dbg = EPI ? 0 : p.debug;
     const bool has_rowvec = (EPI == 1 || EPI == 2) ? false : (p.rowvec != nullptr);
     const bool has_prelu = (EPI == 2) ? false : (p.prelu != nullptr);
-    const bool has_stats = (EPI == 1 || EPI == 2) ? false : (p.stats != nullptr);
+    const bool has_stats = (EPI == 1 || EPI == 2) ? false : (p.stats != nullptr || p.isums != nullptr);
     const bool f16 = (p.flags & IDB_EPI_F16) != 0;
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t sbuf = smem_base + STG_OFFSET + warp * EPI_BUF_BYTES;
@@ -734,8 +746,27 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               cs += v;
               cs2 = fmaf(v, v, cs2);
             }
-            const long long rowblock = p.stats_rowblock0 + static_cast<long long>(m_blk) * 4 + quarter;
-            if (ocol + lane < p.N_out) p.stats[rowblock * p.N_out + ocol + lane] = make_float2(cs, cs2);
+            const long long rb_local = static_cast<long long>(m_blk) * 4 + quarter;   // (padding row blocks of a ragged batch tile write nothing)
+            if (p.stats != nullptr && rb_local < p.n_rowblocks && ocol + lane < p.N_out)
+              p.stats[(p.stats_rowblock0 + rb_local) * p.N_out + ocol + lane] = make_float2(cs, cs2);
+            if (p.isums != nullptr) {
+              // column sums -> granule sums: segmented warp reduction (lanes of one granule are contiguous; fixed tree, so
+              // deterministic), then ONE pair of fire-and-forget integer reductions (RED.ADD.64) per granule segment
+              const int gid = p.fd_gran.div(ocol + lane);
+#pragma unroll
+              for (int o = 1; o < 32; o <<= 1) {
+                const float t = __shfl_down_sync(0xffffffffu, cs, o), t2 = __shfl_down_sync(0xffffffffu, cs2, o);
+                const int g2 = __shfl_down_sync(0xffffffffu, gid, o);
+                if (lane + o < 32 && g2 == gid) cs += t, cs2 += t2;
+              }
+              const int gprev = __shfl_up_sync(0xffffffffu, gid, 1);
+              if ((lane == 0 || gprev != gid) && rb_local < p.n_rowblocks && ocol + lane < p.N_out) {
+                const int img = p.fd_rbpi.div(static_cast<int>(rb_local));
+                unsigned long long* d = p.isums + (static_cast<long long>(img) * p.n_gran + gid) * 2;
+                atomicAdd(d, static_cast<unsigned long long>(__float2ll_rn(cs * ISUM_SCALE_S)));
+                atomicAdd(d + 1, static_cast<unsigned long long>(__float2ll_rn(cs2 * ISUM_SCALE_SS)));
+              }
+            }
           }
           IDB_TICK(5);   // staging (+ statistics)
           if (!(dbg & 0x10)) fence_proxy_async_smem();   // generic-proxy smem writes -> visible to the TMA (async proxy)
@@ -859,6 +890,86 @@ __global__ void splitk_finalize_kernel(const float* __restrict__ ws, int k_split
   }
 }
 
+// Split-K finalize of a tiny-M layer that ALSO needs GroupNorm statistics: one CTA = (32 output columns, image); its 256
+// threads are 8 column quads x 32 row lanes that walk the image's rows, add up the K splits (fixed order), apply the
+// epilogue, write the output and keep per-column sums, which a fixed-order smem reduction turns into the per-image channel
+// sums -- one launch instead of finalize + row-block statistics + GroupNorm finalize.
+__global__ void __launch_bounds__(256) splitk_finalize_sums_kernel(const float* __restrict__ ws, int k_splits, long long M, int N, int hw_conv,
+                                                                   int hw_img, const float* __restrict__ bias, const float* __restrict__ rowvec,
+                                                                   long long rowvec_ld, const float* __restrict__ prelu,
+                                                                   const float* __restrict__ residual, float* __restrict__ out_f32,
+                                                                   unsigned long long* __restrict__ isums, int gran) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float sh_s[32][33], sh_ss[32][33];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int col = blockIdx.x * 32 + tx * 4;
+  const int img = blockIdx.y;
+  const long long slice = M * N;
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), sl = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) bv = *reinterpret_cast<const float4*>(bias + col);
+  if (prelu) sl = *reinterpret_cast<const float4*>(prelu + col);
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int r = ty; r < hw_img; r += 32) {
+    const long long row = static_cast<long long>(img) * hw_img + r;
+    const long long e = row * N + col;
+    float4 a = *reinterpret_cast<const float4*>(ws + e);
+    int sp = 1;
+    for (; sp + 3 < k_splits; sp += 4) {   // same summation order as splitk_finalize_kernel
+      const float4 v0 = *reinterpret_cast<const float4*>(ws + (sp + 0) * slice + e);
+      const float4 v1 = *reinterpret_cast<const float4*>(ws + (sp + 1) * slice + e);
+      const float4 v2 = *reinterpret_cast<const float4*>(ws + (sp + 2) * slice + e);
+      const float4 v3 = *reinterpret_cast<const float4*>(ws + (sp + 3) * slice + e);
+      a.x += (v0.x + v1.x) + (v2.x + v3.x), a.y += (v0.y + v1.y) + (v2.y + v3.y);
+      a.z += (v0.z + v1.z) + (v2.z + v3.z), a.w += (v0.w + v1.w) + (v2.w + v3.w);
+    }
+    for (; sp < k_splits; ++sp) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + sp * slice + e);
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    a.x += bv.x, a.y += bv.y, a.z += bv.z, a.w += bv.w;
+    if (rowvec) {
+      const float4 v = *reinterpret_cast<const float4*>(rowvec + (row / hw_conv) * rowvec_ld + col);
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    if (prelu) {
+      a.x = a.x > 0.f ? a.x : a.x * sl.x, a.y = a.y > 0.f ? a.y : a.y * sl.y;
+      a.z = a.z > 0.f ? a.z : a.z * sl.z, a.w = a.w > 0.f ? a.w : a.w * sl.w;
+    }
+    if (residual) {
+      const float4 v = *reinterpret_cast<const float4*>(residual + e);
+      a.x += v.x, a.y += v.y, a.z += v.z, a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out_f32 + e) = a;
+    s[0] += a.x, s[1] += a.y, s[2] += a.z, s[3] += a.w;
+    ss[0] = fmaf(a.x, a.x, ss[0]), ss[1] = fmaf(a.y, a.y, ss[1]), ss[2] = fmaf(a.z, a.z, ss[2]), ss[3] = fmaf(a.w, a.w, ss[3]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sh_s[ty][tx * 4 + j] = s[j], sh_ss[ty][tx * 4 + j] = ss[j];
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // same fixed-point format and granule layout as the GEMM epilogue (a granule may straddle two CTAs' column blocks, so
+    // the totals are ADDED with integer atomics -- exact and order-independent; the accumulators are zero on entry)
+    float t = 0.f, tt = 0.f;
+#pragma unroll
+    for (int y = 0; y < 32; ++y) t += sh_s[y][threadIdx.x], tt += sh_ss[y][threadIdx.x];
+    const int lane = threadIdx.x, colg = blockIdx.x * 32 + lane;
+    const int gid = colg / gran;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float u = __shfl_down_sync(0xffffffffu, t, o), u2 = __shfl_down_sync(0xffffffffu, tt, o);
+      const int g2 = __shfl_down_sync(0xffffffffu, gid, o);
+      if (lane + o < 32 && g2 == gid) t += u, tt += u2;
+    }
+    const int gprev = __shfl_up_sync(0xffffffffu, gid, 1);
+    if (lane == 0 || gprev != gid) {
+      unsigned long long* d = isums + (static_cast<long long>(img) * (N / gran) + gid) * 2;
+      atomicAdd(d, static_cast<unsigned long long>(__float2ll_rn(t * ISUM_SCALE_S)));
+      atomicAdd(d + 1, static_cast<unsigned long long>(__float2ll_rn(tt * ISUM_SCALE_SS)));
+    }
+  }
+}
+
 // statistics of 32-row blocks of a finished fp32 [M, N] tensor (split-K path of tiny-M layers); the
 // row-block numbering matches the tile order of the fused epilogue only for raster-ordered tiles,
 // which is what the host guarantees before using this path (BW * BH multiple of 32 rows per image).
@@ -974,6 +1085,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   if (lora && (geglu || a->a1)) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: LoRA with GEGLU / second segment");
   if (geglu && a->out_f32) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: GEGLU writes bf16 only");
   if (a->stats_partials && !a->out_f32) return fail(IDB_E_BADARG, "idb_gemm_conv: stats_partials needs the fp32 output");
+  if (a->stats_image_sums && !a->out_f32) return fail(IDB_E_BADARG, "idb_gemm_conv: stats_image_sums needs the fp32 output");
   if (a->prelu && geglu) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: PReLU with GEGLU");
   if ((a->flags & IDB_EPI_GELU) && (geglu || a->k_splits > 1)) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: GELU with GEGLU / forced split-K");
   if ((a->flags & IDB_EPI_F16) && lora) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: fp16 operands with fused LoRA");
@@ -1113,6 +1225,24 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   p.workspace = a->workspace;
   p.stats = reinterpret_cast<float2*>(a->stats_partials);
   p.stats_rowblock0 = phased ? static_cast<long long>(2 * a->out_phase_y + a->out_phase_x) * ((p.M + 31) / 32) : 0;
+  p.n_rowblocks = (p.M + 31) / 32;
+  int stats_hw = 0, n_img = 0;
+  if (a->stats_image_sums) {
+    // per-image channel sums: the call's rows are n_img images of stats_hw rows each (a Linear over tokens passes the
+    // token count per image in stats_hw; a conv uses its output raster)
+    stats_hw = a->stats_hw > 0 ? a->stats_hw : p.Ho * p.Wo;
+    if (stats_hw % 32 || p.M % stats_hw) return fail(IDB_E_BADARG, "idb_gemm_conv: stats_hw must be a multiple of 32 that divides M");
+    const bool raster = (p.BW == p.Wo) || (p.BH == 1 && p.BB == 1) || (p.Ho == 1 && B == 1);
+    if (!raster || (static_cast<long long>(p.Ho) * p.Wo) % 32 != 0)
+      return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: stats_image_sums needs power-of-two Wo (or Wo % 128 == 0) and Ho*Wo % 32 == 0");
+    const int gran = a->stats_gran > 0 ? a->stats_gran : 1;
+    if (p.N_out % gran) return fail(IDB_E_BADARG, "idb_gemm_conv: stats_gran must divide N_out");
+    n_img = static_cast<int>(p.M / stats_hw);
+    p.fd_rbpi.set(stats_hw / 32);
+    p.fd_gran.set(gran);
+    p.n_gran = p.N_out / gran;
+    p.isums = reinterpret_cast<unsigned long long*>(a->stats_image_sums);
+  }
 
   // ---- tensor maps
   if (stride2) {
@@ -1190,7 +1320,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     }
   }
   GemmParams pk = p;
-  if (p.k_splits > 1) pk.stats = nullptr;   // statistics come from rowblock_stats_kernel after the finalize
+  if (p.k_splits > 1) pk.stats = nullptr, pk.isums = nullptr;   // statistics come from the finalize pass
   const int total_tiles = m_units * p.n_tiles_n * p.k_splits;
   const int grid = cg * (total_tiles < units ? total_tiles : units);
   // epilogue specialisation (generic whenever a profiling switch, split-K or both outputs are in play)
@@ -1215,7 +1345,14 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   else rc = launch_gemm<128, 6, false, 2>(pk, grid, stream, epi);
   if (rc) return rc;
 
-  if (p.k_splits > 1) {
+  if (p.k_splits > 1 && p.isums != nullptr && !p.stats && !(p.flags & IDB_EPI_F16) && p.out_f32 && !p.out_bf16) {
+    // finalize + per-image channel sums in one pass
+    launch_pdl(splitk_finalize_sums_kernel, dim3(p.N / 32, n_img), dim3(256), 0, stream, p.workspace, p.k_splits, p.M, p.N, p.Ho * p.Wo,
+               stats_hw, p.bias, p.rowvec, p.rowvec_ld, p.prelu, p.residual, p.out_f32, p.isums, p.fd_gran.d);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("splitk_finalize_sums launch: ") + cudaGetErrorString(e));
+  } else if (p.k_splits > 1) {
+    if (p.isums != nullptr) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: split-K with stats_image_sums needs a single fp32 output and no stats_partials");
     const long long total4 = p.M * p.N / 4;
     int blocks = static_cast<int>((total4 + 255) / 256);
     if (blocks > num_sms() * 8) blocks = num_sms() * 8;

@@ -41,6 +41,12 @@ struct GnParams {
   const float2* rb0;   // non-null selects the fused path; [row block][c0] (sum, sum of squares) of source 0
   const float2* rb1;   // same for source 1
   int rbpi, phases0;   // row blocks per image (<= GN_FUSE_MAX_RB), phased layout of source 0 (see gn_finalize_kernel)
+  // per-image channel sums accumulated by the producing GEMMs (idb_gemm_conv stats_image_sums): [batch][c] 64-bit fixed
+  // point (sum * 2^32, sum of squares * 2^24)
+  const longlong2* sums0;
+  const longlong2* sums1;
+  double inv_n;   // 1 / (hw * channels per group)
+  int gran;       // channels per granule of sums0 / sums1
 };
 
 __device__ __forceinline__ float4 gn_load(const GnParams& p, int b, int pix, int cq) {
@@ -208,7 +214,29 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const GnParams p) {
   __shared__ float g_mean[GN_MAX_GROUPS], g_rstd[GN_MAX_GROUPS];
   __shared__ double f_s[GN_FUSE_MAX_CQ], f_ss[GN_FUSE_MAX_CQ];
   const int chunk = blockIdx.x, b = blockIdx.y;
-  if (p.rb0 != nullptr) {
+  if (p.sums0 != nullptr) {
+    // Group statistics straight from the producers' per-image granule sums (a few hundred bytes per image): thread g adds
+    // up the cpg / gran granules of group g (which may lie in either of the two concatenated sources) -- integer sums,
+    // exact; the only double-precision work is the cancellation-prone E[x^2] - mean^2.  No statistics pass, no finalize.
+    const int g = threadIdx.x;
+    if (g < p.groups) {
+      const int per = p.cpg / p.gran, g0c = g * p.cpg;
+      const int n0 = p.c0 / p.gran, n1 = p.c1 / p.gran;
+      long long s = 0, ss = 0;
+      for (int i = 0; i < per; ++i) {
+        const int q = g0c / p.gran + i;     // granule index in the concatenated channel space
+        const longlong2 v = (q < n0) ? __ldg(p.sums0 + static_cast<long long>(b) * n0 + q)
+                                     : __ldg(p.sums1 + static_cast<long long>(b) * n1 + (q - n0));
+        s += v.x;
+        ss += v.y;
+      }
+      const double mean = static_cast<double>(s) * (1.0 / 4294967296.0) * p.inv_n;
+      double var = fma(-mean, mean, static_cast<double>(ss) * (1.0 / 16777216.0) * p.inv_n);
+      if (var < 0.0) var = 0.0;
+      g_mean[g] = static_cast<float>(mean);
+      g_rstd[g] = rsqrtf(static_cast<float>(var) + p.eps);
+    }
+  } else if (p.rb0 != nullptr) {
     // Fused finalize (rasters of <= 256 pixels: the row-block sums of an image are a few KB, so every CTA reduces
     // them itself instead of waiting for a separate tiny kernel).  Thread t owns channels 4t .. 4t+3 (one group,
     // cpg % 4 == 0); all its loads are issued before the first use; fixed summation order -> deterministic.
@@ -279,18 +307,22 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const GnParams p) {
     sc[i] = ga;
     sh[i] = p.beta[c + i] - g_mean[g] * ga;
   }
-  const int pbeg = chunk * p.pix_per_chunk;
-  const int pend = min(p.hw, pbeg + p.pix_per_chunk);
-  int pix = pbeg + py;
-  for (; pix + 3 * p.PY < pend; pix += 4 * p.PY) {
-    const float4 v0 = gn_load(p, b, pix, cq), v1 = gn_load(p, b, pix + p.PY, cq);
-    const float4 v2 = gn_load(p, b, pix + 2 * p.PY, cq), v3 = gn_load(p, b, pix + 3 * p.PY, cq);
-    gn_emit(p, b, pix, c, v0, sc, sh);
-    gn_emit(p, b, pix + p.PY, c, v1, sc, sh);
-    gn_emit(p, b, pix + 2 * p.PY, c, v2, sc, sh);
-    gn_emit(p, b, pix + 3 * p.PY, c, v3, sc, sh);
+  // a CTA walks chunks blockIdx.x, + gridDim.x, ... of its image: the grid is one resident wave, so the statistics
+  // prologue above is paid once per CTA instead of once per 16-pixel chunk
+  for (int ch = chunk; ch < p.nchunks; ch += gridDim.x) {
+    const int pbeg = ch * p.pix_per_chunk;
+    const int pend = min(p.hw, pbeg + p.pix_per_chunk);
+    int pix = pbeg + py;
+    for (; pix + 3 * p.PY < pend; pix += 4 * p.PY) {
+      const float4 v0 = gn_load(p, b, pix, cq), v1 = gn_load(p, b, pix + p.PY, cq);
+      const float4 v2 = gn_load(p, b, pix + 2 * p.PY, cq), v3 = gn_load(p, b, pix + 3 * p.PY, cq);
+      gn_emit(p, b, pix, c, v0, sc, sh);
+      gn_emit(p, b, pix + p.PY, c, v1, sc, sh);
+      gn_emit(p, b, pix + 2 * p.PY, c, v2, sc, sh);
+      gn_emit(p, b, pix + 3 * p.PY, c, v3, sc, sh);
+    }
+    for (; pix < pend; pix += p.PY) gn_emit(p, b, pix, c, gn_load(p, b, pix, cq), sc, sh);
   }
-  for (; pix < pend; pix += p.PY) gn_emit(p, b, pix, c, gn_load(p, b, pix, cq), sc, sh);
 }
 
 // ---------------------------------------------------------------------------------------- LayerNorm (warp per row)
@@ -778,7 +810,15 @@ extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
   if (threads < 64) threads = 64;  // the apply kernel's first `groups` threads publish mean / rstd
   dim3 grid(p.nchunks, a->batch);
   p.rb0 = p.rb1 = nullptr, p.rbpi = a->hw / 32, p.phases0 = a->x0_stats_phases;
-  if (fused) {
+  p.sums0 = p.sums1 = nullptr;
+  if (a->x0_sums != nullptr && (a->x1 == nullptr || a->x1_sums != nullptr)) {
+    p.gran = a->sums_gran > 0 ? a->sums_gran : 1;
+    if (p.cpg % p.gran || p.c0 % p.gran || p.c1 % p.gran)
+      return fail(IDB_E_BADARG, "idb_groupnorm: sums_gran must divide the channels per group and both source widths");
+    p.sums0 = reinterpret_cast<const longlong2*>(a->x0_sums);
+    p.sums1 = reinterpret_cast<const longlong2*>(a->x1_sums);
+    p.inv_n = 1.0 / (static_cast<double>(a->hw) * p.cpg);
+  } else if (fused) {
     p.rb0 = reinterpret_cast<const float2*>(a->x0_stats);
     p.rb1 = reinterpret_cast<const float2*>(a->x1_stats);
   } else if (have_stats) {   // statistics already produced by the GEMM epilogues of the sources
@@ -791,7 +831,16 @@ extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
     launch_pdl(gn_stats_kernel, dim3(grid), dim3(threads), stats_smem, stream, p);
     IDB_CHECK_LAUNCH("gn_stats");
   }
-  launch_pdl(gn_apply_kernel, dim3(grid), dim3(threads), 0, stream, p);
+  // apply: one resident wave (64 registers per thread), CTAs stride over the chunks of their image
+  static const int apply_waves = getenv("IDB_GN_APPLY_WAVES") ? atoi(getenv("IDB_GN_APPLY_WAVES")) : 1;   // 0 = one CTA per chunk (profiling)
+  int gx = p.nchunks;
+  if (apply_waves > 0) {
+    const int resident = 65536 / (64 * threads) > 0 ? 65536 / (64 * threads) : 1;
+    const long long slots = static_cast<long long>(num_sms()) * resident * apply_waves;
+    const int per_image = static_cast<int>((slots + a->batch - 1) / a->batch);
+    if (per_image < gx) gx = per_image < 1 ? 1 : per_image;
+  }
+  launch_pdl(gn_apply_kernel, dim3(dim3(gx, a->batch)), dim3(threads), 0, stream, p);
   IDB_CHECK_LAUNCH("gn_apply");
   return IDB_OK;
 }

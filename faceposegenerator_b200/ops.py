@@ -33,15 +33,55 @@ def _chk(t: Optional[torch.Tensor], dtype, name: str, allow_none: bool = False):
         raise ValueError(f"{name} must be contiguous")
 
 
+_IMAGE_SUMS_ON = __import__("os").environ.get("IDB_IMAGE_SUMS", "1") != "0"   # 0: row-block sums + finalize kernel (A/B profiling)
+IMAGE_SUMS_MAX_ROWS = 16384     # rows per image up to which the fixed-point per-image sums are used (range: see idb.h)
+
+
+class SumsPool:
+    """Zero-initialised int64 storage for the per-image channel sums (`stats_image_sums`) of MANY GEMMs: the GEMM epilogues
+    ADD into their slice with integer atomics, so every slice must start at zero -- one memset per forward instead of one
+    per GEMM.  A pool is used once (its slices are consumed by the GroupNorms of the same forward)."""
+
+    def __init__(self, device, capacity: int = 1 << 20):
+        self.device, self.capacity = device, capacity
+        self.buf, self.used = None, 0
+
+    def take(self, n_images: int, n: int) -> torch.Tensor:
+        """int64 [n_images, n, 2], zero (n = number of channel granules)"""
+        need = n_images * n * 2
+        if self.buf is None or self.used + need > self.buf.numel():
+            self.buf = torch.zeros(max(self.capacity, need), dtype=torch.int64, device=self.device)
+            self.used = 0
+        out = self.buf[self.used:self.used + need].view(n_images, n, 2)
+        self.used += need
+        return out
+
+
+def image_sums_supported(n_images: int, rows_per_image: int, n: int = 0, phased: bool = False) -> bool:
+    """Mirror of the `stats_image_sums` precondition of `idb_gemm_conv` that does not depend on the tile geometry: whole
+    32-row blocks per image, and few enough rows that the fixed-point accumulators cannot overflow on sane activations
+    (`rows_per_image` is per phase when the output is written by four phased calls)."""
+    rows = 4 * rows_per_image if phased else rows_per_image
+    return _IMAGE_SUMS_ON and rows_per_image % 32 == 0 and rows <= IMAGE_SUMS_MAX_ROWS
+
+
 def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optional[torch.Tensor] = None,
               bias=None, rowvec=None, rowvec_ld: int = 0, residual=None, lora_down=None, lora_up=None, lora_seg_n: int = 0,
               geglu: bool = False, out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None,
               want_f32: bool = False, want_bf16: bool = False, k_splits: int = 1,
               workspace: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, want_stats: bool = False,
               prelu: Optional[torch.Tensor] = None, half: bool = False, gelu: bool = False,
-              tap_off=(0, 0), out_phase=None):
+              tap_off=(0, 0), out_phase=None, sums: Optional[torch.Tensor] = None, stats_hw: int = 0,
+              sums_pool: Optional[SumsPool] = None, stats_gran: int = 1):
     """a0: bf16 [B,H,W,C0] (or [M,K] for a Linear); w: bf16 [N, Ktot].  Returns (out_f32, out_bf16).
-    half=True: the 16-bit tensors (a0, a1, w, out_bf16) are IEEE fp16 instead of bf16 (IDB_EPI_F16)."""
+    half=True: the 16-bit tensors (a0, a1, w, out_bf16) are IEEE fp16 instead of bf16 (IDB_EPI_F16).
+
+    want_stats=True additionally returns the GroupNorm statistics of the fp32 output, in the best form the geometry allows:
+    an int64 [n_images, N / stats_gran, 2] tensor of fixed-point per-image sums over granules of `stats_gran` channels
+    (`stats_image_sums`, accumulated by integer atomics in the epilogue; taken from `sums_pool` or zero-allocated;
+    `stats_hw` = rows per image when the operand is a token matrix; `stats_gran` must divide the group size of every
+    GroupNorm consuming the tensor), else a float32 row-block tensor (`stats_partials`), else None (GroupNorm then computes its own).
+    `groupnorm(x0_stats=...)` accepts any of the three.  An explicit `sums=` must be zero before the (first phase) call."""
     t16 = f16 if half else bf16
     _chk(a0, t16, "a0"); _chk(w, t16, "w")
     if a0.dim() == 2:
@@ -88,9 +128,15 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
     # row-block channel statistics of the fp32 output (consumed by groupnorm); geometries whose 128-pixel tiles are not
     # raster runs of one image (e.g. the 96 / 48 / 24 / 12-wide rasters of 768 x 768 images) return stats = None and the
     # GroupNorm that follows computes its own statistics (`gn_stats_kernel`)
-    if stats is None and want_stats and epilogue_stats_supported(B, Ho, Wo):
-        stats = torch.empty(((M + 31) // 32, n_out, 2), dtype=f32, device=a0.device)
+    if stats is None and sums is None and want_stats and epilogue_stats_supported(B, Ho, Wo):
+        hw_img = stats_hw or Ho * Wo
+        if out_phase is None and M % hw_img == 0 and n_out % stats_gran == 0 and image_sums_supported(M // hw_img, hw_img):
+            sums = sums_pool.take(M // hw_img, n_out // stats_gran) if sums_pool is not None else \
+                torch.zeros((M // hw_img, n_out // stats_gran, 2), dtype=torch.int64, device=a0.device)
+        else:
+            stats = torch.empty(((M + 31) // 32, n_out, 2), dtype=f32, device=a0.device)
     _chk(stats, f32, "stats", allow_none=True)
+    _chk(sums, torch.int64, "sums", allow_none=True)
     args = _lib.GemmConvArgs(
         a0=a0.data_ptr(), a0_mode=mode, c0=C0, a1=_lib.ptr(a1), c1=c1, batch=B, height=H, width=W_,
         w=w.data_ptr(), n=N, bias=_lib.ptr(bias), rowvec=_lib.ptr(rowvec), rowvec_ld=rowvec_ld, residual=_lib.ptr(residual),
@@ -99,6 +145,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
         flags=(EPI_GEGLU if geglu else 0) | (EPI_F16 if half else 0) | (EPI_GELU if gelu else 0), out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
         k_splits=k_splits, workspace=_lib.ptr(workspace),
         workspace_bytes=0 if workspace is None else workspace.numel() * 4, stats_partials=_lib.ptr(stats),
+        stats_image_sums=_lib.ptr(sums), stats_hw=stats_hw, stats_gran=stats_gran,
         prelu=_lib.ptr(prelu), tap_off_x=tap_off[1], tap_off_y=tap_off[0],
         out_scale=2 if out_phase is not None else 0, out_phase_y=0 if out_phase is None else out_phase[0],
         out_phase_x=0 if out_phase is None else out_phase[1])
@@ -106,8 +153,8 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
               desc=None if _lib.trace is None else dict(M=M, N=N, K=taps * C0 + c1, mode=mode, lora=lora_down is not None,
                                                         geglu=geglu, f32=out_f32 is not None, b16=out_bf16 is not None,
                                                         res=residual is not None, stats=stats is not None))
-    if want_stats or stats is not None:
-        return out_f32, out_bf16, stats
+    if want_stats or stats is not None or sums is not None:
+        return out_f32, out_bf16, (sums if sums is not None else stats)
     return out_f32, out_bf16
 
 
@@ -169,11 +216,30 @@ def groupnorm(x0, gamma, beta, *, groups: int, eps: float, silu: bool, x1=None, 
         out_raw = torch.empty(shape, dtype=bf16, device=x0.device)
     if partials is None:
         partials = groupnorm_workspace(B, groups, x0.device)
+    # statistics handed over by the producers: int64 = fixed-point per-image granule sums (one launch), float32 = row-block sums
+    grans = []
+
+    def split(st, c):
+        if st is None:
+            return None, None
+        if st.dtype == torch.int64:
+            if st.dim() != 3 or st.shape[0] != B or st.shape[2] != 2 or c % st.shape[1] or not st.is_contiguous():
+                raise ValueError("per-image granule sums must be contiguous int64 [batch, C / gran, 2]")
+            grans.append(c // st.shape[1])
+            return st, None
+        _chk(st, f32, "stats")
+        return None, st
+    x0_sums, x0_rb = split(x0_stats, c0)
+    x1_sums, x1_rb = split(x1_stats, c1)
+    one_launch = x0_sums is not None and (x1 is None or x1_sums is not None)
+    if one_launch and len(set(grans)) != 1:
+        raise ValueError("both sources must carry sums of the same channel granule")
     args = _lib.GroupNormArgs(x0=x0.data_ptr(), c0=c0, x1=_lib.ptr(x1), c1=c1, batch=B, hw=hw, groups=groups, eps=eps,
                               gamma=gamma.data_ptr(), beta=beta.data_ptr(), silu=int(silu),
                               out_norm=out_norm.data_ptr(), out_raw=_lib.ptr(out_raw), partials=partials.data_ptr(),
-                              x0_stats=_lib.ptr(x0_stats), x1_stats=_lib.ptr(x1_stats), x0_stats_phases=x0_stats_phases)
-    _lib.call("idb_groupnorm", C.byref(args), _lib.stream_ptr())
+                              x0_stats=_lib.ptr(x0_rb), x1_stats=_lib.ptr(x1_rb), x0_stats_phases=x0_stats_phases,
+                              x0_sums=_lib.ptr(x0_sums), x1_sums=_lib.ptr(x1_sums), sums_gran=grans[0] if grans else 0)
+    _lib.call("idb_groupnorm", C.byref(args), _lib.stream_ptr(), launches=1 if one_launch else 2)
     return out_norm, out_raw
 
 

@@ -53,6 +53,11 @@ class UNet2DConditionModel:
         self.groups = self.cfg["norm_num_groups"]
         self.eps = self.cfg["norm_eps"]
         self._lora_version = 0
+        self._sums = None
+        # channel granule of the per-image GroupNorm sums the GEMM epilogues accumulate: it must divide the group size of
+        # every GroupNorm (plain and skip-concatenated) and every concat offset = gcd(block widths) / groups (SD2.1: 10)
+        import math
+        self.stats_gran = math.gcd(*self.cfg["block_out_channels"]) // self.groups
         self._lora_token = None
         self.step_cache = {}          # CUDA-graph step states of the pipelines that share this UNet (pipeline.py)
         self._workspace = None
@@ -228,7 +233,7 @@ class UNet2DConditionModel:
         return self._workspace
 
     def _gemm(self, a0, w, **kw):
-        return ops.gemm_conv(a0, w, k_splits=0, workspace=self._ws(), **kw)
+        return ops.gemm_conv(a0, w, k_splits=0, workspace=self._ws(), sums_pool=self._sums, stats_gran=self.stats_gran, **kw)
 
     def _lin_lora(self, a0, w, lo, seg_n, **kw):
         ld, lu = lo
@@ -281,7 +286,8 @@ class UNet2DConditionModel:
         a = ops.layernorm(x2, *t.ln[2])
         _, g = self._gemm(a, t.w_ff1, bias=t.b_ff1, geglu=True, want_bf16=True)
         _, x3 = self._gemm(g, t.w_ff2, bias=t.b_ff2, residual=x2, want_bf16=True)
-        out, _, out_st = self._gemm(x3, t.w_out, bias=t.b_out, residual=h.view(M, Cc), want_f32=True, want_stats=True)
+        out, _, out_st = self._gemm(x3, t.w_out, bias=t.b_out, residual=h.view(M, Cc), want_f32=True, want_stats=True,
+                                    stats_hw=T)
         return out.view(B, H, W, Cc), out_st
 
     # ------------------------------------------------------------------ step-invariant context projections
@@ -324,6 +330,8 @@ class UNet2DConditionModel:
             raise RuntimeError("stale / mismatched encode_context() result")
         kvs = iter(context.kv)
         gnws = ops.groupnorm_workspace(B, self.groups, self.device)
+        # per-image GroupNorm sums of every residual-stream tensor of this forward: one zeroed pool (one memset), a slice per GEMM
+        self._sums = ops.SumsPool(self.device, capacity=B * 2 * 61440)
         if temb is None:
             temb = ops.time_embed(t, self.t_w1, self.t_b1, self.t_w2, self.t_b2, self.t_w_all, self.t_b_all)
         elif temb.shape != (B, self.t_w_all.shape[0]) or temb.dtype != f32 or not temb.is_contiguous():
@@ -372,11 +380,13 @@ class UNet2DConditionModel:
                     xb = ops.cast_bf16(ht)
                     o = torch.empty((B, 2 * Hl, 2 * Wl, Cu), dtype=f32, device=self.device)
                     o_st = torch.empty((4, B * Hl * Wl // 32, Cu, 2), dtype=f32, device=self.device)
+                    # per-image channel sums accumulated by the four phase calls (else: phased row-block sums)
+                    o_sums = self._sums.take(B, Cu // self.stats_gran) if ops.image_sums_supported(B, Hl * Wl, Cu, phased=True) else None
                     for a in range(2):
                         for c in range(2):
                             self._gemm(xb, blk.up[2][a][c], mode=ops.A_2X2, bias=blk.up[1], out_f32=o, stats=o_st,
-                                       tap_off=(a - 1, c - 1), out_phase=(a, c))
-                    h = (o, o_st, 4)
+                                       sums=o_sums, tap_off=(a - 1, c - 1), out_phase=(a, c))
+                    h = (o, o_sums, 0) if o_sums is not None else (o, o_st, 4)
                 else:
                     hu = ops.upsample2x(ht)
                     o, _, o_st = self._gemm(hu, blk.up[0], mode=ops.A_3X3, bias=blk.up[1], want_f32=True, want_stats=True)

@@ -66,6 +66,9 @@ class AutoencoderKL:
         self.groups = self.cfg["norm_num_groups"]
         self.eps = 1e-6
         self._workspace = None
+        self._sums = None
+        import math
+        self.stats_gran = max(1, math.gcd(*config["block_out_channels"]) // config["norm_num_groups"])   # see unet.py (SD2.1 VAE: 4)
         self._pack(state_dict)
 
     @classmethod
@@ -181,7 +184,7 @@ class AutoencoderKL:
         return self._workspace
 
     def _gemm(self, a0, w, **kw):
-        return ops.gemm_conv(a0, w, k_splits=0, workspace=self._ws(), **kw)
+        return ops.gemm_conv(a0, w, k_splits=0, workspace=self._ws(), sums_pool=self._sums, stats_gran=self.stats_gran, **kw)
 
     # stream value = (fp32 NHWC tensor, row-block channel statistics or None), see unet.py
     def _resnet(self, r, hs, gnws):
@@ -218,7 +221,8 @@ class AutoencoderKL:
             self._gemm(q[sl], k[sl], out_f32=s)                # S = Q K^T      [T, T]
             ops.softmax_rows(s, Cc ** -0.5, out=p)
             self._gemm(p, vt, out_bf16=o[sl])                  # O = P V        [T, C]
-        out, _, out_st = self._gemm(o, at.wo, bias=at.bo, residual=h.view(B * T, Cc), want_f32=True, want_stats=True)
+        out, _, out_st = self._gemm(o, at.wo, bias=at.bo, residual=h.view(B * T, Cc), want_f32=True, want_stats=True,
+                                    stats_hw=T)
         return out.view(B, H, W, Cc), out_st
 
     def decode(self, z, return_dict: bool = True, generator=None, output_image: bool = False,
@@ -230,6 +234,7 @@ class AutoencoderKL:
         z = z.to(device=self.device, dtype=f32).contiguous()
         B = z.shape[0]
         gnws = ops.groupnorm_workspace(B, self.groups, self.device)
+        self._sums = ops.SumsPool(self.device, capacity=B * 2 * 16384)
         x = ops.vae_latent_prep(z, self.pq_w, self.pq_b, 1.0)
         h0, _ = ops.conv3x3_small_cin(x, self.w_in, self.b_in, nchw=False)
         h = (h0, None)
@@ -248,11 +253,12 @@ class AutoencoderKL:
                     xb = ops.cast_bf16(ht)
                     o = torch.empty((B, 2 * Hl, 2 * Wl, Cu), dtype=f32, device=self.device)
                     o_st = torch.empty((4, B * Hl * Wl // 32, Cu, 2), dtype=f32, device=self.device)
+                    o_sums = self._sums.take(B, Cu // self.stats_gran) if ops.image_sums_supported(B, Hl * Wl, Cu, phased=True) else None
                     for a in range(2):
                         for c in range(2):
                             self._gemm(xb, blk.up[2][a][c], mode=ops.A_2X2, bias=blk.up[1], out_f32=o, stats=o_st,
-                                       tap_off=(a - 1, c - 1), out_phase=(a, c))
-                    h = (o, o_st, 4)
+                                       sums=o_sums, tap_off=(a - 1, c - 1), out_phase=(a, c))
+                    h = (o, o_sums, 0) if o_sums is not None else (o, o_st, 4)
                 else:
                     hu = ops.upsample2x(ht)
                     o, _, o_st = self._gemm(hu, blk.up[0], mode=ops.A_3X3, bias=blk.up[1], want_f32=True, want_stats=True)
@@ -276,6 +282,7 @@ class AutoencoderKL:
         if cin != 3 or H % 8 or W % 8:
             raise ValueError("expected [n, 3, H, W] with H, W multiples of 8")
         gnws = ops.groupnorm_workspace(B, self.groups, self.device)
+        self._sums = ops.SumsPool(self.device, capacity=B * 2 * 16384)
         x4 = torch.zeros((B, H, W, 4), dtype=f32, device=self.device)
         x4[..., :3] = x.permute(0, 2, 3, 1)
         h0, _ = ops.conv3x3_small_cin(x4, self.e_w_in, self.e_b_in, nchw=False)

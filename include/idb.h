@@ -45,6 +45,9 @@ int idb_last_error(char* buf, size_t n);
 /* 0 if the current device is sm_100 (B200), IDB_E_ARCH otherwise. */
 int idb_device_check(void);
 int idb_num_sms(void);
+/* sizeof of the argument structs below as THIS build sees them (0 = idb_gemm_conv_args, 1 = idb_attention_args,
+ * 2 = idb_groupnorm_args, 3 = idb_time_embed_args): a binding checks its own layout against it at load time. */
+size_t idb_sizeof_args(int32_t which);
 
 /* ------------------------------------------------------------------------------------------
  * idb_gemm_conv: D[M,N] = epilogue( sum_seg im2col(A_seg)[M,K_seg] . W[N, K]^T )
@@ -115,6 +118,18 @@ typedef struct {
    * (sum, sum of squares), written by the epilogue for free; idb_groupnorm consumes them instead of
    * re-reading the tensor.  Needs out_f32, Wo a power of two (or a multiple of 128) and Ho*Wo % 32 == 0. */
   float* stats_partials;
+  /* optional: per-IMAGE sums of the fp32 output over granules of stats_gran consecutive channels, in 64-bit fixed point:
+   * int64 [n_images, N_out / stats_gran, 2] = (sum * 2^32, sum of squares * 2^24) over the image's stats_hw rows,
+   * n_images = M / stats_hw.  stats_gran (0 = 1) must divide the group size of every GroupNorm that will consume the
+   * tensor and the channel offset at which it is concatenated (SD2.1 UNet: 10, VAE: 4).  The epilogue ADDS its 32-row
+   * sums with integer atomics (exact and order-independent: bit-reproducible without any ordering), so the caller ZEROES the
+   * tensor before the call -- before the first of the four phase calls that share it when out_scale = 2.
+   * idb_groupnorm(x0_sums) then needs neither a statistics pass nor a finalize launch.  Range: |sum| < 2^31 and sum of
+   * squares < 2^39 per (image, granule).  Same geometry precondition as stats_partials (which may be NULL).
+   * stats_hw: rows per image (0 = Ho*Wo; a Linear over tokens passes the tokens per image); a multiple of 32. */
+  int64_t* stats_image_sums;
+  int32_t stats_hw;
+  int32_t stats_gran;
   /* optional: per-output-channel PReLU slopes [N], applied after bias / rowvec and before the residual
    * (ArcFace IResNet: bn2 folded into conv1, then nn.PReLU(planes)).  Not combined with GEGLU. */
   const float* prelu;
@@ -179,6 +194,12 @@ typedef struct {
   /* 4 when x0 was written by four phased idb_gemm_conv calls (out_scale = 2): x0_stats is then
    * [4 phases][batch * hw/128][C0][2]; 0 / 1 otherwise */
   int32_t x0_stats_phases;
+  /* optional, preferred: per-image granule sums accumulated by idb_gemm_conv(stats_image_sums) for x0 / x1 (int64 fixed
+   * point [batch, C / sums_gran, 2] each; sums_gran divides the group size and c0).  When given for every source the call
+   * is ONE launch: each CTA derives the group statistics of its image from these few hundred bytes itself. */
+  const int64_t* x0_sums;
+  const int64_t* x1_sums;
+  int32_t sums_gran;
 } idb_groupnorm_args;
 int idb_groupnorm(const idb_groupnorm_args* args, void* stream);
 size_t idb_groupnorm_workspace_bytes(int32_t batch, int32_t groups);

@@ -19,6 +19,10 @@ def rb(t):  # bf16 round trip
     return t.to(torch.bfloat16)
 
 
+def fixed_sums(t):  # int64 [.., 2] fixed point (sum * 2^32, sum of squares * 2^24) -> float64 pair
+    return t[..., 0].double() / 2.0 ** 32, t[..., 1].double() / 2.0 ** 24
+
+
 def pack_conv_w(w):  # [Cout, Cin, 3, 3] -> [Cout, 9*Cin] tap-major
     return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).contiguous()
 
@@ -236,6 +240,65 @@ def test_upsample_conv_four_phase(ops, cuda_dev, B, H, W, C):
     y_ph, _ = ops.groupnorm(out, gamma, beta, groups=32, eps=1e-5, silu=True, x0_stats=st, x0_stats_phases=4)
     y_pl, _ = ops.groupnorm(out, gamma, beta, groups=32, eps=1e-5, silu=True)
     assert rel(y_ph.float(), y_pl.float()) < 2e-3
+    # the same four calls also accumulating the fixed-point per-image channel sums (zeroed once, before the first phase)
+    assert ops.image_sums_supported(B, H * W, C, phased=True)
+    out2 = torch.empty_like(out)
+    sums = torch.zeros((B, C, 2), dtype=torch.int64, device=cuda_dev)
+    for a in range(2):
+        for c in range(2):
+            ops.gemm_conv(xb, wph[a][c], mode=ops.A_2X2, bias=bias, out_f32=out2, sums=sums, tap_off=(a - 1, c - 1),
+                          out_phase=(a, c))
+    assert torch.equal(out2, out)
+    flat = out.view(B, 4 * H * W, C).double()
+    assert rel(fixed_sums(sums)[0], flat.sum(1)) < 1e-6 and rel(fixed_sums(sums)[1], (flat ** 2).sum(1)) < 1e-6
+    y_sm, _ = ops.groupnorm(out, gamma, beta, groups=32, eps=1e-5, silu=True, x0_stats=sums)
+    assert rel(y_sm.float(), y_pl.float()) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N,gran", [(8, 64, 64, 64, 320, 10), (8, 64, 64, 64, 320, 1),
+                                              (3, 8, 8, 64, 1280, 40),      # odd batch with two images per tile: padding row blocks
+                                              (1, 8, 8, 128, 640, 20), (5, 16, 16, 64, 1280, 10), (2, 32, 32, 64, 640, 4),
+                                              (8, 8, 8, 1280, 1280, 10),    # K = 11520, M = 512: split-K + fused finalize / sums kernel
+                                              (8, 16, 16, 1280, 1280, 1), (4, 64, 64, 64, 128, 4)])
+def test_gemm_image_sums(ops, cuda_dev, B, H, W, Cin, N, gran):
+    """`stats_image_sums`: per-image channel (sum, sum of squares) of the fp32 output in 64-bit fixed point, accumulated by
+    integer atomics in the conv GEMM's epilogue (exact and order-independent) or written by the fused split-K finalize --
+    against float64 sums of the output tensor, and bit-reproducible across calls."""
+    g = torch.Generator(device="cuda").manual_seed(B * H + N)
+    x = rb(torch.randn(B, H, W, Cin, device=cuda_dev, generator=g))
+    w = rb(torch.randn(N, Cin, 3, 3, device=cuda_dev, generator=g) / math.sqrt(9 * Cin))
+    bias = torch.randn(N, device=cuda_dev, generator=g)
+    ws = torch.empty(24 << 20, dtype=torch.float32, device=cuda_dev)
+    runs = []
+    for _ in range(3):
+        o, _, sm = ops.gemm_conv(x, pack_conv_w(w), mode=ops.A_3X3, bias=bias, want_f32=True, want_stats=True, k_splits=0, workspace=ws,
+                                 stats_gran=gran)
+        assert sm.dtype == torch.int64 and tuple(sm.shape) == (B, N // gran, 2)
+        runs.append((o.clone(), sm.clone()))
+    flat = runs[0][0].view(B, H * W, N // gran, gran).double().permute(0, 1, 3, 2).reshape(B, H * W * gran, N // gran)
+    assert rel(fixed_sums(runs[0][1])[0], flat.sum(1)) < 1e-6
+    assert rel(fixed_sums(runs[0][1])[1], (flat ** 2).sum(1)) < 1e-6
+    for o, sm in runs[1:]:
+        assert torch.equal(o, runs[0][0]) and torch.equal(sm, runs[0][1])
+
+
+def test_linear_image_sums_over_tokens(ops, cuda_dev):
+    """A Linear over a token matrix [B * T, K] (Transformer2DModel.proj_out + residual) hands the GroupNorm of the next
+    ResnetBlock2D its per-image sums: `stats_hw` = tokens per image."""
+    B, T, C = 4, 1024, 640
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = rb(torch.randn(B * T, C, device=cuda_dev, generator=g))
+    w = rb(torch.randn(C, C, device=cuda_dev, generator=g) / math.sqrt(C))
+    res = torch.randn(B * T, C, device=cuda_dev, generator=g)
+    o, _, sm = ops.gemm_conv(a, w, residual=res, want_f32=True, want_stats=True, stats_hw=T)
+    assert sm.dtype == torch.int64 and tuple(sm.shape) == (B, C, 2)
+    flat = o.view(B, T, C).double()
+    assert rel(fixed_sums(sm)[0], flat.sum(1)) < 1e-6 and rel(fixed_sums(sm)[1], (flat ** 2).sum(1)) < 1e-6
+    gamma = 1 + 0.1 * torch.randn(C, device=cuda_dev, generator=g)
+    beta = 0.1 * torch.randn(C, device=cuda_dev, generator=g)
+    y, _ = ops.groupnorm(o.view(B, T, C), gamma, beta, groups=32, eps=1e-5, silu=True, x0_stats=sm)
+    ref = F.silu(F.group_norm(o.view(B, T, C).permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
+    assert rel(y.float(), ref) < 4e-3
 
 
 def test_conv3x3_plus_shortcut_segment(ops, cuda_dev):
@@ -417,18 +480,28 @@ def test_groupnorm_from_epilogue_statistics(ops, cuda_dev, B, H, W, C0, C1, N):
     """GroupNorm fed by the row-block channel sums that the producing conv GEMM wrote in its epilogue
     (no statistics pass over the tensor) == GroupNorm that reads the tensor itself."""
     g = torch.Generator(device="cuda").manual_seed(H + C0)
+    gran = math.gcd(C0, C1 or C0) // 32      # divides the group size of the (concatenated) GroupNorm and the concat offset
+
     def produce(cin, cout):
         x = rb(torch.randn(B, H, W, cin, device=cuda_dev, generator=g))
         w = rb(torch.randn(cout, cin, 3, 3, device=cuda_dev, generator=g) / math.sqrt(9 * cin))
         bias = torch.randn(cout, device=cuda_dev, generator=g)
         o, _, st = ops.gemm_conv(x, pack_conv_w(w), mode=ops.A_3X3, bias=bias, want_f32=True, want_stats=True,
-                                 k_splits=0, workspace=torch.empty(16 << 20, dtype=torch.float32, device=cuda_dev))
+                                 k_splits=0, workspace=torch.empty(16 << 20, dtype=torch.float32, device=cuda_dev),
+                                 stats_gran=gran)
         return o.view(B, H * W, cout), st
     x0, s0 = produce(64, C0)
     x1, s1 = produce(64, C1) if C1 else (None, None)
-    # the partial sums themselves
-    ref_s = x0.view(B * H * W // 32, 32, C0).sum(1)
-    assert rel(s0[..., 0], ref_s) < 1e-5
+    # the sums themselves: fixed-point per-image channel sums (int64, accumulated inside the GEMM), or row-block sums where
+    # an image has more than 16384 pixels
+    if s0.dtype == torch.int64:
+        assert tuple(s0.shape) == (B, C0 // gran, 2)
+        xg = x0.double().view(B, H * W, C0 // gran, gran)
+        assert rel(fixed_sums(s0)[0], xg.sum((1, 3))) < 1e-6 and rel(fixed_sums(s0)[1], (xg ** 2).sum((1, 3))) < 1e-6
+    else:
+        assert H * W > 16384
+        ref_s = x0.view(B * H * W // 32, 32, C0).sum(1)
+        assert rel(s0[..., 0], ref_s) < 1e-5
     C = C0 + C1
     gamma = 1 + 0.1 * torch.randn(C, device=cuda_dev, generator=g)
     beta = 0.1 * torch.randn(C, device=cuda_dev, generator=g)
