@@ -293,7 +293,13 @@ __device__ __forceinline__ void exp2_poly2(float& y0, float& y1, float x0, float
   y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(xf1) << 23));
 }
 
-template <int POLY_MASK>   // pairs (i, i+1) with ((i >> 1) & POLY_MASK) == POLY_MASK take the polynomial exp2: 1 -> 1/2, 3 -> 1/4, 7 -> 1/8, 32 -> none
+// SPLIT: the two threads of a query row are independent online-softmax instances over disjoint key halves of every tile
+// (keys 0-63 / 64-127), each with its OWN exponent reference, row sum and 64-column O accumulator (O_x0 / O_x1 in TMEM:
+// S_a | S_b | O_a0 | O_a1 | O_b0 | O_b1 = 512 columns); the two partial results are merged once per item
+// (O = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1), w_h = 2^(m_h - max m)).  A tile is then read from TMEM ONCE, 32 scores
+// at a time with the lazy reference update done per 32-score chunk, and there is no per-tile exchange / named barrier
+// between the two threads of a row.
+template <int POLY_MASK, bool SPLIT>   // pairs (i, i+1) with ((i >> 1) & POLY_MASK) == POLY_MASK take the polynomial exp2: 1 -> 1/2, 3 -> 1/4, 7 -> 1/8, 32 -> none
 __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __grid_constant__ AttnParams p, int n_full, int qblocks, int n_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -423,13 +429,14 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
       }
       const uint32_t pbase = smem_base + 2 * ATT_TILE + AT2_RING * ATT_TILE + x * 2 * ATT_TILE;
       const uint32_t vbase = smem_base + 2 * ATT_TILE + slot * ATT_TILE;
-      const uint32_t tO = tmem_base + 256 + x * 64;
+      const uint32_t tO = tmem_base + 256 + (SPLIT ? x * 128 : x * 64);
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < ATT_BN / 16; ++kk) {
           const uint64_t ad = mk(pbase + (kk >> 2) * ATT_TILE + (kk & 3) * 32);
           const uint64_t bd = mk(vbase + kk * 2048);
-          umma_bf16(tO, ad, bd, IDESC_O, (j > 0 || kk > 0) ? 1u : 0u);
+          if (SPLIT) umma_bf16(tO + (kk >> 2) * 64, ad, bd, IDESC_O, (j > 0 || (kk & 3) > 0) ? 1u : 0u);   // keys 0-63 -> O_x0, 64-127 -> O_x1
+          else umma_bf16(tO, ad, bd, IDESC_O, (j > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit_a(bar_addr(I_OD + x));
         if (x == nl - 1) umma_commit_a(bar_addr(I_KVE + slot));
@@ -482,6 +489,143 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
     const int sw = r & 7;
     uint32_t gj = 0;   // tiles this lane has processed so far (barrier phases)
 
+    if constexpr (SPLIT) {
+      const uint32_t tOm = tmem_base + lane_off + 256 + (x * 2 + hs) * 64;          // my accumulator: my 64 keys, all 64 columns
+      const uint32_t tOo = tmem_base + lane_off + 256 + (x * 2 + (hs ^ 1)) * 64;    // the row's other key half
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        if (item >= n_full && x == 1) continue;   // lane b idles through single-lane items
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < n_tiles; ++j, ++gj) {
+          mbar_wait(&s_full[x], gj & 1);
+          tc_fence_after();
+          const int kv_valid = min(ATT_BN, p.Tkv - j * ATT_BN) - hs * 64;   // my keys < kv_valid are real
+          float l0 = 0.f, l1 = 0.f;
+          bool o_ready = (j == 0);  // PV(j-1) retired: O readable / writable, P buffer free
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t sv[32];
+            IDB_TMEM_LD_X32(tS + half * 32, sv);
+            tmem_ld_wait();
+            if (half == 1) {   // last read of S_x(j) by this warp: the next Q K^T may overwrite it
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&s_free[x]);
+            }
+            if (kv_valid < 64) {   // ragged last tile (warp-uniform branch)
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (half * 32 + i >= kv_valid) sv[i] = 0xff800000u;
+            }
+            float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              mx0 = fmaxf(mx0, fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
+              mx1 = fmaxf(mx1, fmaxf(__uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3])));
+            }
+            const float m_t = fmaxf(mx0, mx1) * c;
+            // lazy reference update: only when some row of the warp would otherwise produce P > 2^8
+            if (__any_sync(0xffffffffu, m_t > m_run + AT2_RESCALE_THRESHOLD)) {
+              const float m_upd = fmaxf(m_run, m_t);
+              const float alpha = ex2(m_run - m_upd);   // 0 on the first chunk (m_run = -inf), 1 for rows that do not move
+              m_run = m_upd;
+              l_run *= alpha, l0 *= alpha, l1 *= alpha;
+              if (j > 0) {
+                if (!o_ready) {
+                  mbar_wait(&o_done[x], (gj - 1) & 1);
+                  tc_fence_after();
+                  o_ready = true;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {   // my 64 O columns, 16 at a time (register pressure: sv and pk are live)
+                  uint32_t v[16];
+                  IDB_TMEM_LD_X16(tOm + q * 16, v);
+                  tmem_ld_wait();
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                  IDB_TMEM_ST_X16(tOm + q * 16, v);
+                }
+                tmem_st_wait();
+              }
+              if (half == 1) {   // the first 32 probabilities of this tile (already staged) were formed with the old reference
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  uint4* pp = reinterpret_cast<uint4*>(prow + ((q ^ sw) << 4));
+                  uint4 w = *pp;
+                  w.x = pack_bf16x2(__uint_as_float(w.x << 16) * alpha, __uint_as_float(w.x & 0xffff0000u) * alpha);
+                  w.y = pack_bf16x2(__uint_as_float(w.y << 16) * alpha, __uint_as_float(w.y & 0xffff0000u) * alpha);
+                  w.z = pack_bf16x2(__uint_as_float(w.z << 16) * alpha, __uint_as_float(w.z & 0xffff0000u) * alpha);
+                  w.w = pack_bf16x2(__uint_as_float(w.w << 16) * alpha, __uint_as_float(w.w & 0xffff0000u) * alpha);
+                  *pp = w;
+                }
+              }
+            }
+            const float neg_m = -m_run;
+            uint32_t pk[16];          // bf16x2 probabilities of these 32 keys
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {   // masked keys: exp2(-inf) = 0 (MUFU) / 2^-126 (polynomial)
+              float x0, x1, e0, e1;
+              ffma2(x0, x1, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]), c, c, neg_m, neg_m);
+              if (((i >> 1) & POLY_MASK) == POLY_MASK) {
+                exp2_poly2(e0, e1, x0, x1);
+              } else {
+                e0 = ex2(x0);
+                e1 = ex2(x1);
+              }
+              fadd2(l0, l1, l0, l1, e0, e1);
+              pk[i >> 1] = pack_bf16x2(e0, e1);
+            }
+            if (!o_ready) {   // the P buffer is still being read by P V of the previous tile
+              mbar_wait(&o_done[x], (gj - 1) & 1);
+              tc_fence_after();
+              o_ready = true;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              *reinterpret_cast<uint4*>(prow + (((half * 4 + q) ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+          }
+          l_run += l0 + l1;
+          fence_proxy_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[x]);
+        }
+        // ---- epilogue: merge the row's two key halves.  w_h = 2^(m_h - m), O = (O_0 w_0 + O_1 w_1) / (l_0 w_0 + l_1 w_1)
+        float* xm = xch_m + (x * 128 + r) * 2;
+        float* xl = xch_l + (x * 128 + r) * 2;
+        xm[hs] = m_run;
+        xl[hs] = l_run;
+        pair_barrier(pair_id);
+        const float m_o = xm[hs ^ 1], l_o = xl[hs ^ 1];
+        const float m_all = fmaxf(m_run, m_o);
+        const float w_me = ex2(m_run - m_all), w_o = ex2(m_o - m_all);
+        const float inv_l = 1.0f / (l_run * w_me + l_o * w_o);
+        const float f_me = w_me * inv_l, f_o = w_o * inv_l;
+        mbar_wait(&o_done[x], (gj - 1) & 1);
+        tc_fence_after();
+        const Item t = decode(item);
+        const int row = t.q0 + x * ATT_BM + r;
+        __nv_bfloat16* orow = p.out + (static_cast<long long>(t.b) * p.Tq + row) * p.ld_out + t.head * ATT_D + hs * 32;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {   // my 32 output columns, 16 at a time, from both accumulators
+          uint32_t va[16], vb[16];
+          IDB_TMEM_LD_X16(tOm + hs * 32 + q * 16, va);
+          IDB_TMEM_LD_X16(tOo + hs * 32 + q * 16, vb);
+          tmem_ld_wait();
+          if (row < p.Tq) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              w[i] = pack_bf16x2(fmaf(__uint_as_float(va[2 * i]), f_me, __uint_as_float(vb[2 * i]) * f_o),
+                                 fmaf(__uint_as_float(va[2 * i + 1]), f_me, __uint_as_float(vb[2 * i + 1]) * f_o));
+            uint4* dst = reinterpret_cast<uint4*>(orow + q * 16);
+            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+          }
+        }
+        tc_fence_before();   // the O reads above precede the next item's first P V (ordered through p_full)
+        pair_barrier(pair_id);   // the partner has read my (m, l) before the next item's epilogue overwrites them
+      }
+    } else {
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     if (item >= n_full && x == 1) continue;   // lane b idles through single-lane items
     float m_run = -INFINITY, l_run = 0.f;
@@ -609,6 +753,7 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
     }
     tc_fence_before();   // the O reads above precede the next item's first P V (ordered through p_full)
     }   // items
+    }   // !SPLIT
   }
 
   tc_fence_before();
@@ -920,17 +1065,16 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
   }
   static const int rs_poly = getenv("IDB_ATTN_RSPOLY") ? atoi(getenv("IDB_ATTN_RSPOLY")) : 3;
   if (use256) {   // row-split 256-query kernel (16 softmax warps)
-    void (*kern)(AttnParams, int, int, int) = attention_rs_kernel<3>;
-    if (rs_poly == 1) kern = attention_rs_kernel<1>;
-    else if (rs_poly == 7) kern = attention_rs_kernel<7>;
-    else if (rs_poly == 32) kern = attention_rs_kernel<32>;
-    static PerDeviceOnce configured3[4];
-    {
-      void (*all[4])(AttnParams, int, int, int) = {attention_rs_kernel<1>, attention_rs_kernel<3>, attention_rs_kernel<7>, attention_rs_kernel<32>};
-      for (int i = 0; i < 4; ++i) {
-        cudaError_t e3 = ensure_dynamic_smem(all[i], AT3_SMEM, configured3[i]);
-        if (e3 != cudaSuccess) return fail(IDB_E_CUDA, std::string("cudaFuncSetAttribute(attention_rs): ") + cudaGetErrorString(e3));
-      }
+    static const int rs_split = getenv("IDB_ATTN_SPLIT") ? atoi(getenv("IDB_ATTN_SPLIT")) : 1;   // 0: exchange the row maximum every tile (first version)
+    void (*all[8])(AttnParams, int, int, int) = {attention_rs_kernel<1, false>, attention_rs_kernel<3, false>, attention_rs_kernel<7, false>,
+                                                 attention_rs_kernel<32, false>, attention_rs_kernel<1, true>, attention_rs_kernel<3, true>,
+                                                 attention_rs_kernel<7, true>, attention_rs_kernel<32, true>};
+    const int pi = rs_poly == 1 ? 0 : (rs_poly == 7 ? 2 : (rs_poly == 32 ? 3 : 1));
+    void (*kern)(AttnParams, int, int, int) = all[pi + (rs_split ? 4 : 0)];
+    static PerDeviceOnce configured3[8];
+    for (int i = 0; i < 8; ++i) {
+      cudaError_t e3 = ensure_dynamic_smem(all[i], AT3_SMEM, configured3[i]);
+      if (e3 != cudaSuccess) return fail(IDB_E_CUDA, std::string("cudaFuncSetAttribute(attention_rs): ") + cudaGetErrorString(e3));
     }
     // 256-query units; the ones that would form a partial last wave run as two single-lane CTAs each
     const int qblocks = (a->t_q + 2 * ATT_BM - 1) / (2 * ATT_BM);
