@@ -49,6 +49,37 @@ class AttentionArgs(C.Structure):
         ("out", c_void_p), ("ld_out", c_int64),
         ("batch", c_int32), ("heads", c_int32), ("t_q", c_int32), ("t_kv", c_int32),
         ("scale", c_float), ("causal", c_int32),
+        ("lse", c_void_p),
+    ]
+
+
+class AttentionBwdArgs(C.Structure):
+    _fields_ = [
+        ("q", c_void_p), ("ld_q", c_int64), ("col0_q", c_int32),
+        ("k", c_void_p), ("ld_k", c_int64), ("col0_k", c_int32),
+        ("v", c_void_p), ("ld_v", c_int64), ("col0_v", c_int32),
+        ("o", c_void_p), ("ld_o", c_int64), ("col0_o", c_int32),
+        ("d_o", c_void_p), ("ld_do", c_int64), ("col0_do", c_int32),
+        ("lse", c_void_p), ("dsum", c_void_p),
+        ("dq", c_void_p), ("ld_dq", c_int64), ("col0_dq", c_int32),
+        ("dk", c_void_p), ("ld_dk", c_int64), ("col0_dk", c_int32),
+        ("dv", c_void_p), ("ld_dv", c_int64), ("col0_dv", c_int32),
+        ("batch", c_int32), ("heads", c_int32), ("t_q", c_int32), ("t_kv", c_int32),
+        ("scale", c_float),
+    ]
+
+
+class GroupNormBwdArgs(C.Structure):
+    _fields_ = [
+        ("dy", c_void_p),
+        ("x0", c_void_p), ("c0", c_int32),
+        ("x1", c_void_p), ("c1", c_int32),
+        ("batch", c_int32), ("hw", c_int32), ("groups", c_int32), ("silu", c_int32),
+        ("stats", c_void_p),
+        ("gamma", c_void_p), ("beta", c_void_p),
+        ("scratch", c_void_p),
+        ("dx0", c_void_p), ("dx1", c_void_p),
+        ("add0", c_int32), ("add1", c_int32),
     ]
 
 
@@ -90,6 +121,15 @@ EXPORTS = {
     "idb_sizeof_args": (c_size_t, [c_int32]),
     "idb_attention": (c_int32, [C.POINTER(AttentionArgs), c_void_p]),
     "idb_groupnorm": (c_int32, [C.POINTER(GroupNormArgs), c_void_p]),
+    "idb_attention_backward": (c_int32, [C.POINTER(AttentionBwdArgs), c_void_p]),
+    "idb_layernorm_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int32, c_float, c_void_p]),
+    "idb_groupnorm_backward": (c_int32, [C.POINTER(GroupNormBwdArgs), c_void_p]),
+    "idb_geglu_backward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
+    "idb_lora_wgrad_workspace_bytes": (c_size_t, [c_int32]),
+    "idb_lora_wgrad": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_float, c_int32,
+                                 c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "idb_zero_insert2x": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "idb_sumpool2x": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "idb_groupnorm_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "idb_layernorm": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),
     "idb_softmax_rows": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p]),
@@ -113,7 +153,7 @@ EXPORTS = {
 _lib: Optional[C.CDLL] = None
 trace = None      # profiling only: set to a list to record (entry point, description) per call
 launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"idb_time_embed": 4}   # entry points that always launch more than one kernel
+_LAUNCHES_PER_CALL = {"idb_time_embed": 4, "idb_attention_backward": 2, "idb_groupnorm_backward": 2, "idb_lora_wgrad": 2}   # entry points that always launch more than one kernel
 
 
 def load() -> C.CDLL:
@@ -129,7 +169,7 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        for which, struct in enumerate((GemmConvArgs, AttentionArgs, GroupNormArgs, TimeEmbedArgs)):
+        for which, struct in enumerate((GemmConvArgs, AttentionArgs, GroupNormArgs, TimeEmbedArgs, AttentionBwdArgs, GroupNormBwdArgs)):
             if lib.idb_sizeof_args(which) != C.sizeof(struct):   # a stale binding would make the library read past the struct
                 raise RuntimeError(f"{struct.__name__}: ctypes layout ({C.sizeof(struct)} B) does not match include/idb.h "
                                    f"({lib.idb_sizeof_args(which)} B); rebuild the library / update _lib.py")

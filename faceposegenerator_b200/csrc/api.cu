@@ -174,6 +174,8 @@ extern "C" size_t idb_sizeof_args(int32_t which) {
     case 1: return sizeof(idb_attention_args);
     case 2: return sizeof(idb_groupnorm_args);
     case 3: return sizeof(idb_time_embed_args);
+    case 4: return sizeof(idb_attention_bwd_args);
+    case 5: return sizeof(idb_groupnorm_bwd_args);
     default: return 0;
   }
 }

@@ -36,6 +36,7 @@ struct AttnParams {
   int B, heads, Tq, Tkv, n_kv_tiles;
   float scale_log2;
   int causal;
+  float* lse;   // optional [B, heads, Tq]: log2-domain log-sum-exp of the scaled scores (training forward)
 };
 
 __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_constant__ AttnParams p) {
@@ -230,6 +231,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attention_kernel(const __grid_
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const int row = q0 + r;
+    if (p.lse != nullptr && row < p.Tq) p.lse[(static_cast<long long>(b) * p.heads + head) * p.Tq + row] = m_run + log2f(l_run);
     __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Tq + row) * p.ld_out + head * ATT_D;
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
@@ -604,6 +606,8 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
         tc_fence_after();
         const Item t = decode(item);
         const int row = t.q0 + x * ATT_BM + r;
+        if (p.lse != nullptr && hs == 0 && row < p.Tq)
+          p.lse[(static_cast<long long>(t.b) * p.heads + t.head) * p.Tq + row] = m_all + log2f(l_run * w_me + l_o * w_o);
         __nv_bfloat16* orow = p.out + (static_cast<long long>(t.b) * p.Tq + row) * p.ld_out + t.head * ATT_D + hs * 32;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {   // my 32 output columns, 16 at a time, from both accumulators
@@ -736,6 +740,8 @@ __global__ void __launch_bounds__(AT3_THREADS, 1) attention_rs_kernel(const __gr
     tc_fence_after();
     const Item t = decode(item);   // decoded here, not before the tile loop: nothing item-specific is live across it
     const int row = t.q0 + x * ATT_BM + r;
+    if (p.lse != nullptr && hs == 0 && row < p.Tq)
+      p.lse[(static_cast<long long>(t.b) * p.heads + t.head) * p.Tq + row] = m_run + log2f(l_run + xl[hs ^ 1]);
     __nv_bfloat16* orow = p.out + (static_cast<long long>(t.b) * p.Tq + row) * p.ld_out + t.head * ATT_D + hs * 32;
     {
       uint32_t v[32];
@@ -960,6 +966,7 @@ __global__ void __launch_bounds__(ATX_THREADS, 2) attention_x_kernel(const __gri
       tc_fence_after();
       const float inv_l = 1.0f / l;
       const int row = (qt0 + i) * ATT_BM + r;
+      if (p.lse != nullptr && row < p.Tq) p.lse[(static_cast<long long>(b) * p.heads + head) * p.Tq + row] = -neg_m + log2f(l);
       __nv_bfloat16* orow = p.out + (static_cast<long long>(b) * p.Tq + row) * p.ld_out + head * ATT_D;
       uint32_t v0[32], v1[32];
       IDB_TMEM_LD_X32(tmem_base + lane_off + ATX_O_COL, v0);
@@ -1037,6 +1044,7 @@ extern "C" int idb_attention(const idb_attention_args* a, void* stream_) {
   p.n_kv_tiles = (a->t_kv + ATT_BN - 1) / ATT_BN;
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.causal = a->causal ? 1 : 0;
+  p.lse = a->lse;
   if (p.causal && a->t_kv > 96) return fail(IDB_E_UNSUPPORTED, "idb_attention: causal masking is implemented for t_kv <= 96 (short-context kernel)");
 
   static PerDeviceOnce configured;

@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libidb_b200.so")
-SOURCES = ["api.cu", "gemm_tc.cu", "attention.cu", "simt_kernels.cu"]
+SOURCES = ["api.cu", "gemm_tc.cu", "attention.cu", "attention_bwd.cu", "simt_kernels.cu", "backward_kernels.cu"]
 HEADERS = ["idb_common.cuh", "idb_host.h", os.path.join("..", "..", "include", "idb.h")]
 ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

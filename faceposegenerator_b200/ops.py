@@ -6,6 +6,7 @@ with torch when omitted) -- the library itself never allocates.
 from __future__ import annotations
 
 import ctypes as C
+import ctypes as C_
 from typing import Optional
 
 import torch
@@ -180,18 +181,161 @@ def epilogue_stats_supported(batch: int, ho: int, wo: int) -> bool:
 
 
 def attention(q, k, v, out=None, *, batch: int, heads: int, t_q: int, t_kv: int, scale: float,
-              col0_q: int = 0, col0_k: int = 0, col0_v: int = 0, causal: bool = False):
-    """q: bf16 [B*Tq, ld_q]; k, v: bf16 [B*Tkv, ld]; head h lives at columns col0 + h*64."""
+              col0_q: int = 0, col0_k: int = 0, col0_v: int = 0, causal: bool = False, lse: Optional[torch.Tensor] = None):
+    """q: bf16 [B*Tq, ld_q]; k, v: bf16 [B*Tkv, ld]; head h lives at columns col0 + h*64.
+    lse: optional fp32 [B, heads, Tq] output (log2-domain log-sum-exp of the scaled scores, for `attention_backward`)."""
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
         _chk(t, bf16, nm)
     if out is None:
         out = torch.empty((batch * t_q, heads * 64), dtype=bf16, device=q.device)
     _chk(out, bf16, "out")
+    _chk(lse, f32, "lse", allow_none=True)
+    if lse is not None and lse.numel() != batch * heads * t_q:
+        raise ValueError("lse must be fp32 [batch, heads, t_q]")
     args = _lib.AttentionArgs(q=q.data_ptr(), ld_q=q.shape[-1], col0_q=col0_q, k=k.data_ptr(), ld_k=k.shape[-1],
                               col0_k=col0_k, v=v.data_ptr(), ld_v=v.shape[-1], col0_v=col0_v, out=out.data_ptr(),
-                              ld_out=out.shape[-1], batch=batch, heads=heads, t_q=t_q, t_kv=t_kv, scale=scale, causal=int(causal))
+                              ld_out=out.shape[-1], batch=batch, heads=heads, t_q=t_q, t_kv=t_kv, scale=scale, causal=int(causal),
+                              lse=_lib.ptr(lse))
     _lib.call("idb_attention", C.byref(args), _lib.stream_ptr(),
               desc=None if _lib.trace is None else dict(B=batch, heads=heads, Tq=t_q, Tkv=t_kv))
+    return out
+
+
+def attention_backward(q, k, v, o, d_o, lse, *, batch: int, heads: int, t_q: int, t_kv: int, scale: float,
+                       col0_q: int = 0, col0_k: int = 0, col0_v: int = 0, dq=None, dk=None, dv=None, col0_dq: int = 0,
+                       col0_dk: int = 0, col0_dv: int = 0):
+    """Gradients of `attention` (same operand addressing; o / d_o are bf16 [B*Tq, heads*64]).  Returns (dq fp32
+    [B*Tq, ...] -- accumulated atomically, so a caller-provided dq must be zero --, dk, dv bf16 [B*Tkv, ...])."""
+    for t, nm in ((q, "q"), (k, "k"), (v, "v"), (o, "o"), (d_o, "d_o")):
+        _chk(t, bf16, nm)
+    _chk(lse, f32, "lse")
+    C = heads * 64
+    if dq is None:
+        dq = torch.zeros((batch * t_q, C), dtype=f32, device=q.device)
+    if dk is None:
+        dk = torch.empty((batch * t_kv, C), dtype=bf16, device=q.device)
+    if dv is None:
+        dv = torch.empty((batch * t_kv, C), dtype=bf16, device=q.device)
+    _chk(dq, f32, "dq"); _chk(dk, bf16, "dk"); _chk(dv, bf16, "dv")
+    dsum = torch.empty((batch, heads, t_q), dtype=f32, device=q.device)
+    args = _lib.AttentionBwdArgs(
+        q=q.data_ptr(), ld_q=q.shape[-1], col0_q=col0_q, k=k.data_ptr(), ld_k=k.shape[-1], col0_k=col0_k,
+        v=v.data_ptr(), ld_v=v.shape[-1], col0_v=col0_v, o=o.data_ptr(), ld_o=o.shape[-1], col0_o=0,
+        d_o=d_o.data_ptr(), ld_do=d_o.shape[-1], col0_do=0, lse=lse.data_ptr(), dsum=dsum.data_ptr(),
+        dq=dq.data_ptr(), ld_dq=dq.shape[-1], col0_dq=col0_dq, dk=dk.data_ptr(), ld_dk=dk.shape[-1], col0_dk=col0_dk,
+        dv=dv.data_ptr(), ld_dv=dv.shape[-1], col0_dv=col0_dv, batch=batch, heads=heads, t_q=t_q, t_kv=t_kv, scale=scale)
+    _lib.call("idb_attention_backward", C_.byref(args), _lib.stream_ptr())
+    return dq, dk, dv
+
+
+def layernorm_backward(dy, x, gamma, dx=None, add: bool = False, eps: float = 1e-5):
+    """dx (+)= d LayerNorm(x) / dx applied to dy; dy, x fp32 [rows, C]."""
+    _chk(dy, f32, "dy"); _chk(x, f32, "x"); _chk(gamma, f32, "gamma")
+    c = x.shape[-1]
+    if dx is None:
+        if add:
+            raise ValueError("add=True needs dx")
+        dx = torch.empty_like(x)
+    _chk(dx, f32, "dx")
+    _lib.call("idb_layernorm_backward", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), dx.data_ptr(), int(add), x.numel() // c, c, eps,
+              _lib.stream_ptr())
+    return dx
+
+
+def groupnorm_backward(dy, x0, gamma, beta, stats, *, groups: int, silu: bool, x1=None, dx0=None, dx1=None,
+                       add0: bool = False, add1: bool = False, want_dx1: bool = True):
+    """Input gradient of `groupnorm` over [x0 | x1]; dy fp32 [B, hw.., C0+C1]; stats fp32 [B, groups, 2] = (mean, rstd)."""
+    _chk(dy, f32, "dy"); _chk(x0, f32, "x0"); _chk(x1, f32, "x1", allow_none=True); _chk(stats, f32, "stats")
+    _chk(gamma, f32, "gamma"); _chk(beta, f32, "beta")
+    B, c0 = x0.shape[0], x0.shape[-1]
+    hw = x0.numel() // (B * c0)
+    c1 = 0 if x1 is None else x1.shape[-1]
+    if dx0 is None:
+        dx0 = torch.empty_like(x0)
+        add0 = False
+    if x1 is not None and dx1 is None and want_dx1:
+        dx1 = torch.empty_like(x1)
+        add1 = False
+    scratch = torch.empty((B, groups, 2), dtype=f32, device=x0.device)
+    args = _lib.GroupNormBwdArgs(dy=dy.data_ptr(), x0=x0.data_ptr(), c0=c0, x1=_lib.ptr(x1), c1=c1, batch=B, hw=hw, groups=groups,
+                                 silu=int(silu), stats=stats.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(),
+                                 scratch=scratch.data_ptr(), dx0=_lib.ptr(dx0), dx1=_lib.ptr(dx1), add0=int(add0), add1=int(add1))
+    _lib.call("idb_groupnorm_backward", C_.byref(args), _lib.stream_ptr())
+    return dx0, dx1
+
+
+def group_stats_from_sums(sums: torch.Tensor, channels: int, hw: int, groups: int, eps: float, sums1: Optional[torch.Tensor] = None,
+                          channels1: int = 0) -> torch.Tensor:
+    """(mean, rstd) fp32 [B, groups, 2] from the fixed-point per-image granule sums the forward GEMMs accumulated
+    (`gemm_conv(want_stats=True)`), for `groupnorm_backward` -- the same arithmetic as the forward's apply kernel."""
+    def dec(t, c):
+        gran = c // t.shape[1]
+        return t.double(), gran
+    a, g0 = dec(sums, channels)
+    parts = [a]
+    gran = g0
+    if sums1 is not None:
+        b_, g1 = dec(sums1, channels1)
+        if g1 != g0:
+            raise ValueError("both sources must use the same channel granule")
+        parts.append(b_)
+    allg = torch.cat(parts, dim=1)                                    # [B, (C0 + C1) / gran, 2]
+    C = channels + channels1
+    per = (C // groups) // gran
+    grp = allg.view(allg.shape[0], groups, per, 2).sum(2)
+    n = float(hw) * (C // groups)
+    mean = grp[..., 0] / 2.0 ** 32 / n
+    var = (grp[..., 1] / 2.0 ** 24 / n - mean * mean).clamp_min(0.0)
+    rstd = torch.rsqrt(var.float() + eps)
+    return torch.stack([mean.float(), rstd], -1).contiguous()
+
+
+def geglu_backward(dh, u, du=None):
+    """dh bf16 [M, H]; u bf16 [M, 2H] interleaved pre-activation -> du bf16 [M, 2H]."""
+    _chk(dh, bf16, "dh"); _chk(u, bf16, "u")
+    M, H = dh.shape
+    if du is None:
+        du = torch.empty_like(u)
+    _lib.call("idb_geglu_backward", dh.data_ptr(), u.data_ptr(), du.data_ptr(), M, H, _lib.stream_ptr())
+    return du
+
+
+_wgrad_ws = {}
+
+
+def lora_wgrad(wide, skinny, rank: int, *, out=None, transpose_out: bool = False, scale: float = 1.0, add: bool = False,
+               col0_w: int = 0, width: Optional[int] = None, col0_s: int = 0):
+    """out[w, r] (or out[r, w]) (+)= scale * sum_m wide[m, col0_w + w] * skinny[m, col0_s + r]; wide / skinny bf16 2-D."""
+    _chk(wide, bf16, "wide"); _chk(skinny, bf16, "skinny")
+    M = wide.shape[0]
+    W = width if width is not None else wide.shape[1] - col0_w
+    if out is None:
+        out = torch.zeros((rank, W) if transpose_out else (W, rank), dtype=f32, device=wide.device)
+    _chk(out, f32, "out")
+    key = (wide.device, W)
+    if key not in _wgrad_ws:
+        _wgrad_ws[key] = torch.empty(_lib.load().idb_lora_wgrad_workspace_bytes(W) // 4, dtype=f32, device=wide.device)
+    _lib.call("idb_lora_wgrad", wide.data_ptr(), wide.shape[1], col0_w, skinny.data_ptr(), skinny.shape[1], col0_s, out.data_ptr(),
+              out.shape[1], int(transpose_out), scale, int(add), M, W, rank, _wgrad_ws[key].data_ptr(), _lib.stream_ptr())
+    return out
+
+
+def zero_insert2x(g, out=None):
+    _chk(g, bf16, "g")
+    B, H, W_, c = g.shape
+    if out is None:
+        out = torch.empty((B, 2 * H, 2 * W_, c), dtype=bf16, device=g.device)
+    _lib.call("idb_zero_insert2x", g.data_ptr(), out.data_ptr(), B, H, W_, c, _lib.stream_ptr())
+    return out
+
+
+def sumpool2x(g, out=None, add: bool = False):
+    _chk(g, f32, "g")
+    B, H2, W2, c = g.shape
+    if out is None:
+        out = torch.empty((B, H2 // 2, W2 // 2, c), dtype=f32, device=g.device)
+        add = False
+    _lib.call("idb_sumpool2x", g.data_ptr(), out.data_ptr(), int(add), B, H2 // 2, W2 // 2, c, _lib.stream_ptr())
     return out
 
 

@@ -46,7 +46,8 @@ int idb_last_error(char* buf, size_t n);
 int idb_device_check(void);
 int idb_num_sms(void);
 /* sizeof of the argument structs below as THIS build sees them (0 = idb_gemm_conv_args, 1 = idb_attention_args,
- * 2 = idb_groupnorm_args, 3 = idb_time_embed_args): a binding checks its own layout against it at load time. */
+ * 2 = idb_groupnorm_args, 3 = idb_time_embed_args, 4 = idb_attention_bwd_args, 5 = idb_groupnorm_bwd_args): a binding
+ * checks its own layout against it at load time. */
 size_t idb_sizeof_args(int32_t which);
 
 /* ------------------------------------------------------------------------------------------
@@ -163,8 +164,34 @@ typedef struct {
   int32_t batch, heads, t_q, t_kv;
   float scale;
   int32_t causal;   /* 1: key j is visible to query i only if j <= i (CLIP text tower); supported for t_kv <= 96 */
+  /* optional: log-sum-exp of the scaled scores of every query row in the LOG2 domain, fp32 [batch, heads, t_q]
+   * (= log2 sum_j exp(scale * q.k_j)); saved by a training forward for idb_attention_backward */
+  float* lse;
 } idb_attention_args;
 int idb_attention(const idb_attention_args* args, void* stream);
+
+/* idb_attention_backward: dQ, dK, dV of O = softmax(Q K^T * scale) V given dO (LoRA-only training backward,
+ * train_ID-Booth.py:1140; the attention projections carry the trainable adapters, :672-678).  Same operand addressing as
+ * idb_attention; o = the forward output, lse = the forward's log2-domain log-sum-exp.
+ *   dq   : fp32 [batch * t_q, ld_dq], head h at columns col0_dq + 64 h; MUST BE ZERO on entry (every key tile adds its
+ *          contribution atomically; fp32 atomics: the last bits depend on the arrival order)
+ *   dk/dv: bf16 [batch * t_kv, ld], head h at col0 + 64 h (written, not accumulated)
+ *   dsum : fp32 scratch [batch, heads, t_q] (rowsum(dO o O), filled by the call) */
+typedef struct {
+  const void* q; int64_t ld_q; int32_t col0_q;
+  const void* k; int64_t ld_k; int32_t col0_k;
+  const void* v; int64_t ld_v; int32_t col0_v;
+  const void* o; int64_t ld_o; int32_t col0_o;
+  const void* d_o; int64_t ld_do; int32_t col0_do;
+  const float* lse;
+  float* dsum;
+  float* dq; int64_t ld_dq; int32_t col0_dq;
+  void* dk; int64_t ld_dk; int32_t col0_dk;
+  void* dv; int64_t ld_dv; int32_t col0_dv;
+  int32_t batch, heads, t_q, t_kv;
+  float scale;
+} idb_attention_bwd_args;
+int idb_attention_backward(const idb_attention_bwd_args* args, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * GroupNorm (+SiLU) over NHWC, fp32 statistics.  Replaces F.group_norm + F.silu in
@@ -289,6 +316,45 @@ int idb_channel_affine(const float* x, const float* scale, const float* shift, v
                        int32_t h, int32_t w, int32_t c, int32_t stride, void* stream);
 int idb_crop_resize_norm(const float* img_nhwc, const int32_t* bbox_xyxy, void* out_16, int32_t out_f16, int32_t n, int32_t h,
                          int32_t w, int32_t size, int32_t c_pad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LoRA-only training backward (train_ID-Booth.py:1140-1146 with the adapters of :672-678 as the only
+ * trainable tensors).  The contractions of the backward run on idb_gemm_conv (transposed packed weights; the fused-LoRA
+ * form covers dX = dY W + (dY B) A with the adapter roles swapped) and idb_attention_backward; these are the
+ * bandwidth-bound pieces.  All reductions run in a fixed order.
+ * ---------------------------------------------------------------------------------------- */
+/* dx (+)= LayerNorm input gradient: dy, x fp32 [rows, C]; C % 4 == 0, C <= 2048 */
+int idb_layernorm_backward(const float* dy, const float* x, const float* gamma, float* dx, int32_t add, int64_t rows, int32_t c,
+                           float eps, void* stream);
+/* GroupNorm(+SiLU) input gradient over the logical concatenation [x0 | x1] (as idb_groupnorm reads it).  dy fp32
+ * [batch, hw, C0+C1] = gradient with respect to act(GN(x)); stats fp32 [batch, groups, 2] = (mean, rstd) of the forward;
+ * scratch fp32 [batch, groups, 2]; dx0 / dx1 fp32 like x0 / x1 (either may be NULL), accumulated into when add0 / add1. */
+typedef struct {
+  const float* dy;
+  const float* x0; int32_t c0;
+  const float* x1; int32_t c1;
+  int32_t batch, hw, groups, silu;
+  const float* stats;
+  const float* gamma; const float* beta;
+  float* scratch;
+  float* dx0; float* dx1;
+  int32_t add0, add1;
+} idb_groupnorm_bwd_args;
+int idb_groupnorm_backward(const idb_groupnorm_bwd_args* args, void* stream);
+/* GEGLU backward: dh bf16 [M, H]; u bf16 [M, 2H] = the pre-activation in the interleaved [a(16) | g(16)] layout of
+ * IDB_EPI_GEGLU (recomputed by the caller); du bf16 [M, 2H] in the same layout */
+int idb_geglu_backward(const void* dh_bf16, const void* u_bf16, void* du_bf16, int64_t m, int32_t h, void* stream);
+/* Adapter weight gradient: out[w, r] (+)= scale * sum_m wide[m, col0_w + w] * skinny[m, col0_s + r], r < rank <= 16
+ * (dB = dY^T (x A^T); dA = ((dY B)^T x) with transpose_out = 1: out[r, w]).  wide / skinny bf16 with row strides ld_w /
+ * ld_s; out fp32 with row stride out_ld; workspace: idb_lora_wgrad_workspace_bytes(w) bytes. */
+size_t idb_lora_wgrad_workspace_bytes(int32_t w);
+int idb_lora_wgrad(const void* wide_bf16, int64_t ld_w, int32_t col0_w, const void* skinny_bf16, int64_t ld_s, int32_t col0_s,
+                   float* out, int32_t out_ld, int32_t transpose_out, float scale, int32_t add, int64_t m, int32_t w, int32_t r,
+                   float* workspace, void* stream);
+/* z[b, 2y, 2x, :] = g[b, y, x, :], zero elsewhere (bf16 NHWC): operand of the input gradient of a stride-2 conv */
+int idb_zero_insert2x(const void* g_bf16, void* z_bf16, int32_t batch, int32_t h, int32_t w, int32_t c, void* stream);
+/* out[b, y, x, :] (+)= sum of the 2x2 block of g (fp32 NHWC [batch, 2h, 2w, c]): input gradient of nearest-2x upsampling */
+int idb_sumpool2x(const float* g, float* out, int32_t add, int32_t batch, int32_t h, int32_t w, int32_t c, void* stream);
 
 #ifdef __cplusplus
 }

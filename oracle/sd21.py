@@ -297,7 +297,7 @@ class DDPMSchedulerRef:
         return prev, x0
 
     def add_noise(self, x0: Tensor, noise: Tensor, t: Tensor) -> Tensor:
-        acp = self.alphas_cumprod.to(x0.dtype)[t]
+        acp = self.alphas_cumprod.to(device=x0.device, dtype=x0.dtype)[t.to(x0.device)]
         sa = (acp ** 0.5).view(-1, *([1] * (x0.ndim - 1)))
         sb = ((1 - acp) ** 0.5).view(-1, *([1] * (x0.ndim - 1)))
         return sa * x0 + sb * noise
