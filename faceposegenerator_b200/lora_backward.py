@@ -412,3 +412,60 @@ class UNetLoRAGrad:
         dh = dout.clone()
         ops.groupnorm_backward(dn.view(B, H, W, Cc), h, t.gn_g, t.gn_b, stats, groups=u.groups, silu=False, dx0=dh, add0=True)
         return dh
+
+
+class LoRATrainer:
+    """The optimisation step of `/root/reference/train_ID-Booth.py:1012-1146` for the denoising loss (`which_loss == ""`:
+    `instance_loss = F.mse_loss(model_pred, target)`), LoRA-only: `add_noise` (`:1018`) -> UNet (`:1040-1046`) -> epsilon /
+    v target (`:1055-1058`) -> MSE (`:1137-1138`) -> backward (`:1140`) -> `clip_grad_norm_(max_grad_norm)` (`:1143`) ->
+    AdamW (`:1144`; lr 1e-4, betas (0.9, 0.999), weight decay 1e-2, eps 1e-8: `configs/config_train_SD21.py:58-66`).
+
+    Forward and backward run on the hand-written kernels (`UNetLoRAGrad`); the 128 fp32 adapter factors (829,952 values)
+    and their AdamW state are ordinary torch tensors updated by `torch.optim.AdamW`, then re-installed in place into the
+    UNet's packed adapter buffers (`set_lora`).  The identity / triplet losses of the reference additionally differentiate
+    through the VAE decoder and the ArcFace backbone (`:1081-1133`); that backward is not built (forward only:
+    `iresnet.training_forward_identity`)."""
+
+    def __init__(self, unet, lora, scheduler, lr: float = 1e-4, betas=(0.9, 0.999), weight_decay: float = 1e-2, eps: float = 1e-8,
+                 max_grad_norm: float = 1.0):
+        self.unet, self.scheduler, self.max_grad_norm = unet, scheduler, max_grad_norm
+        dev = unet.device
+        self.params = {k: (torch.nn.Parameter(d.detach().to(dev, f32).clone()), torch.nn.Parameter(u.detach().to(dev, f32).clone()), float(s))
+                       for k, (d, u, s) in lora.items()}
+        self.opt = torch.optim.AdamW([p for d, u, _ in self.params.values() for p in (d, u)], lr=lr, betas=betas,
+                                     weight_decay=weight_decay, eps=eps)
+        self._install()
+
+    def lora(self):
+        return {k: (d.detach(), u.detach(), s) for k, (d, u, s) in self.params.items()}
+
+    def _install(self):
+        self.unet.set_lora({k: (d.detach().cpu(), u.detach().cpu(), s) for k, (d, u, s) in self.params.items()})
+        self.engine = UNetLoRAGrad(self.unet, self.lora())
+
+    @torch.no_grad()
+    def step(self, latents, noise, timesteps, encoder_hidden_states):
+        """One training step on clean latents [B, 4, h, w] (already scaled by the VAE factor), noise, long timesteps [B],
+        text states [B, 77, 1024].  Returns (loss, gradient norm before clipping)."""
+        dev = self.unet.device
+        latents, noise = latents.to(dev, f32), noise.to(dev, f32)
+        timesteps = timesteps.to(dev)
+        noisy = self.scheduler.add_noise(latents, noise, timesteps)
+        pred = self.engine.forward(noisy, timesteps.to(f32), encoder_hidden_states)
+        if self.scheduler.config.prediction_type == "v_prediction":
+            target = self.scheduler.get_velocity(latents, noise, timesteps)
+        else:
+            target = noise
+        diff = pred - target
+        loss = (diff * diff).mean()
+        grads = self.engine.backward(diff * (2.0 / diff.numel()))
+        sq = torch.zeros((), device=dev)
+        for k, (d, u, _) in self.params.items():
+            d.grad, u.grad = grads[k][0], grads[k][1]
+            sq = sq + d.grad.pow(2).sum() + u.grad.pow(2).sum()
+        norm = sq.sqrt()
+        torch.nn.utils.clip_grad_norm_([p for d, u, _ in self.params.values() for p in (d, u)], self.max_grad_norm)
+        self.opt.step()
+        self.opt.zero_grad(set_to_none=True)
+        self._install()
+        return float(loss), float(norm)

@@ -233,3 +233,25 @@ def test_unet_lora_gradients_vs_oracle(cuda_dev):
     assert abs(float(loss) - float(loss_ref)) < 1e-2 * float(loss_ref)
     assert worst_cos >= 0.98
     assert e <= 5e-2
+
+
+def test_lora_trainer_reduces_the_denoising_loss(cuda_dev):
+    """`LoRATrainer.step` = add_noise -> UNet -> MSE -> backward -> clip -> AdamW (train_ID-Booth.py:1012-1146) on a fixed
+    batch: the loss must go down, the adapters must move, the frozen base weights must not."""
+    from faceposegenerator_b200 import DDPMScheduler
+    from faceposegenerator_b200.lora_backward import LoRATrainer
+    from faceposegenerator_b200.unet import UNet2DConditionModel
+    from faceposegenerator_b200.weights import random_lora, random_state_dict, unet_manifest
+    unet = UNet2DConditionModel(random_state_dict(unet_manifest(), 0), device=cuda_dev)
+    lora = random_lora(seed=1)
+    base = unet.transformers[0].w_qkv.clone()
+    tr = LoRATrainer(unet, lora, DDPMScheduler.from_pretrained("stabilityai/stable-diffusion-2-1-base", subfolder="scheduler"), lr=1e-3)
+    g = torch.Generator().manual_seed(2)
+    x0, noise = torch.randn(2, 4, 64, 64, generator=g), torch.randn(2, 4, 64, 64, generator=g)
+    ctx, t = torch.randn(2, 77, 1024, generator=g), torch.tensor([500, 120])
+    losses = [tr.step(x0, noise, t, ctx.to(cuda_dev))[0] for _ in range(6)]
+    print("denoising loss over 6 AdamW steps:", [round(v, 5) for v in losses])
+    assert losses[-1] < losses[0] and min(losses[1:]) < losses[0]
+    moved = max(float((tr.params[k][1].detach().cpu() - lora[k][1]).abs().max()) for k in lora)
+    assert moved > 1e-4
+    assert torch.equal(unet.transformers[0].w_qkv, base)
