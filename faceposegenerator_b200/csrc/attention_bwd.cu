@@ -10,7 +10,9 @@
 // LSE_i (log2 domain) comes from the forward kernels (idb_attention_args.lse), D_i = rowsum(dO o O) from attn_bwd_prep_kernel.
 //   warps 0-3 : thread r = query row r of the tile (P / dS formation, dQ read-out), finally key row r (dK / dV read-out)
 //   warp  4   : TMA producer          warp 5 : tcgen05.mma issuer, owns the TMEM allocation
-// A first, correctness-oriented version: single-buffered tiles, the phases of one query tile run back to back.
+// A first version: Q / dO tiles are double-buffered (the next tile loads, and its S / dP MMAs queue, behind the current
+// tile's dV / dK / dQ MMAs); S, dP, P, dS are single-buffered, so the softmax-backward phase and the MMAs of one query
+// tile still alternate.
 #include <cstdlib>
 #include <string>
 
@@ -24,7 +26,7 @@ constexpr int AB_TILE = 16384;   // 128 x 64 bf16
 constexpr int AB_THREADS = 192;
 constexpr int AB_TMEM_COLS = 512;
 constexpr int AB_S = 0, AB_DP = 128, AB_DV = 256, AB_DK = 320, AB_DQ = 384;
-constexpr int AB_SMEM = 8 * AB_TILE /* K V Q dO | P(2) dS(2) */ + 1024 + 256;
+constexpr int AB_SMEM = 10 * AB_TILE /* K V | Q(2) dO(2) | P(2) dS(2) */ + 1024 + 256;
 
 struct AttnBwdParams {
   CUtensorMap tmQ, tmK, tmV, tmDO;
@@ -81,18 +83,19 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
   uint8_t* sV = sK + AB_TILE;
-  uint8_t* sQ = sV + AB_TILE;
-  uint8_t* sDO = sQ + AB_TILE;
-  uint8_t* sP = sDO + AB_TILE;        // [2 key atoms][128 query rows x 64 keys]
+  uint8_t* sQ = sV + AB_TILE;         // [2 slots]: the next query tile's Q / dO load while this one is being worked on
+  uint8_t* sDO = sQ + 2 * AB_TILE;    // [2 slots]
+  uint8_t* sP = sDO + 2 * AB_TILE;    // [2 key atoms][128 query rows x 64 keys]
   uint8_t* sDS = sP + 2 * AB_TILE;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDS + 2 * AB_TILE);
   uint64_t* kv_full = bars;
-  uint64_t* qdo_full = bars + 1;
-  uint64_t* sdp_full = bars + 2;
-  uint64_t* pds_full = bars + 3;      // count 4 (softmax warps)
-  uint64_t* mma2_done = bars + 4;     // dV / dK / dQ MMAs of the query tile retired: Q, dO, P, dS free, dQ readable
-  uint64_t* dq_free = bars + 5;       // count 4: dQ read out of TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* qdo_full = bars + 1;      // [2]
+  uint64_t* qdo_empty = bars + 3;     // [2] every MMA that reads the slot has retired
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* pds_full = bars + 6;      // count 4 (softmax warps)
+  uint64_t* mma2_done = bars + 7;     // dV / dK / dQ MMAs of the query tile retired: P, dS free, dQ readable
+  uint64_t* dq_free = bars + 8;       // count 4: dQ read out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x, head = blockIdx.y, b = blockIdx.z;
@@ -104,7 +107,10 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
     tma_prefetch_desc(&p.tmV);
     tma_prefetch_desc(&p.tmDO);
     mbar_init(kv_full, 1);
-    mbar_init(qdo_full, 1);
+    for (int k = 0; k < 2; ++k) {
+      mbar_init(&qdo_full[k], 1);
+      mbar_init(&qdo_empty[k], 1);
+    }
     mbar_init(sdp_full, 1);
     mbar_init(pds_full, 4);
     mbar_init(mma2_done, 1);
@@ -126,10 +132,11 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
       tma_load_3d(sK, &p.tmK, kv_full, p.col0_k + head * 64, j * 128, b);
       tma_load_3d(sV, &p.tmV, kv_full, p.col0_v + head * 64, j * 128, b);
       for (int i = 0; i < nq; ++i) {
-        if (i > 0) mbar_wait(mma2_done, (i - 1) & 1);   // every MMA that reads Q_{i-1} / dO_{i-1} has retired
-        mbar_expect_tx(qdo_full, 2 * AB_TILE);
-        tma_load_3d(sQ, &p.tmQ, qdo_full, p.col0_q + head * 64, i * 128, b);
-        tma_load_3d(sDO, &p.tmDO, qdo_full, p.col0_do + head * 64, i * 128, b);
+        const int slot = i & 1;
+        mbar_wait(&qdo_empty[slot], ((i >> 1) & 1) ^ 1);   // every MMA that read the slot's previous tile has retired
+        mbar_expect_tx(&qdo_full[slot], 2 * AB_TILE);
+        tma_load_3d(sQ + slot * AB_TILE, &p.tmQ, &qdo_full[slot], p.col0_q + head * 64, i * 128, b);
+        tma_load_3d(sDO + slot * AB_TILE, &p.tmDO, &qdo_full[slot], p.col0_do + head * 64, i * 128, b);
       }
     }
   } else if (warp == 5) {
@@ -138,13 +145,15 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
     constexpr uint32_t IDESC_T = umma_idesc_bf16(128, 64, 1, 1);    // dV = P^T dO, dK = dS^T Q: A and B MN-major
     constexpr uint32_t IDESC_Q = umma_idesc_bf16(128, 64, 0, 1);    // dQ = dS K: A K-major, B (= K_j) MN-major
     const uint64_t kdesc = umma_smem_desc_sw128(smem_u32(sK)), vdesc = umma_smem_desc_sw128(smem_u32(sV));
-    const uint64_t qdesc = umma_smem_desc_sw128(smem_u32(sQ)), dodesc = umma_smem_desc_sw128(smem_u32(sDO));
+    const uint64_t qdesc0 = umma_smem_desc_sw128(smem_u32(sQ)), dodesc0 = umma_smem_desc_sw128(smem_u32(sDO));
     const uint64_t pdesc_mn = umma_smem_desc_sw128_mn2(smem_u32(sP)), dsdesc_mn = umma_smem_desc_sw128_mn2(smem_u32(sDS));
     const uint64_t dsdesc_k = umma_smem_desc_sw128(smem_u32(sDS));
     mbar_wait(kv_full, 0);
     tc_fence_after();
     for (int i = 0; i < nq; ++i) {
-      mbar_wait(qdo_full, i & 1);
+      const int slot = i & 1;
+      const uint64_t qdesc = qdesc0 + static_cast<uint64_t>((slot * AB_TILE) >> 4), dodesc = dodesc0 + static_cast<uint64_t>((slot * AB_TILE) >> 4);
+      mbar_wait(&qdo_full[slot], (i >> 1) & 1);
       tc_fence_after();
       if (lane == 0) {
 #pragma unroll
@@ -175,6 +184,7 @@ __global__ void __launch_bounds__(AB_THREADS, 1) attention_bwd_kernel(const __gr
           umma_bf16(tmem_base + AB_DQ, ad, bd, IDESC_Q, kk > 0 ? 1u : 0u);
         }
         umma_commit(mma2_done);
+        umma_commit(&qdo_empty[slot]);
       }
       __syncwarp();
     }

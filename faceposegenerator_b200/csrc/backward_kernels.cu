@@ -101,7 +101,8 @@ struct GnBwdParams {
   const float* stats;    // [B, groups, 2] (mean, rstd) of the forward
   const float* gamma;
   const float* beta;
-  float* red;            // [B, groups, 2] scratch: (sum g, sum g * xhat)
+  float* red;            // [B, groups, nslab, 2] scratch: per pixel-slab partials of (sum g, sum g * xhat)
+  int nslab;
   float* dx0;
   float* dx1;            // outputs, same geometry as x0 / x1
   int add0, add1;        // accumulate into the output instead of overwriting it
@@ -115,17 +116,21 @@ __device__ __forceinline__ float gn_bwd_g(const GnBwdParams& p, float dy, float 
   return dy * (s * (1.0f + z * (1.0f - s))) * ga;
 }
 
-// one CTA per (group, image): fixed-order reduction of (sum g, sum g * xhat)
+// CTAs (group, image, pixel slab): fixed-order partial reductions of (sum g, sum g * xhat) -> red[b][g][slab][2]; the apply
+// kernel adds the slabs up in index order
 __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p) {
   pdl_trigger();
   pdl_wait();
-  const int g = blockIdx.x, b = blockIdx.y;
+  const int g = blockIdx.x, b = blockIdx.y, slab = blockIdx.z, nslab = gridDim.z;
   const float mean = p.stats[(static_cast<long long>(b) * p.groups + g) * 2], rstd = p.stats[(static_cast<long long>(b) * p.groups + g) * 2 + 1];
-  const long long n = static_cast<long long>(p.hw) * p.cpg;
+  const int pix_per = (p.hw + nslab - 1) / nslab;
+  const int pix0 = slab * pix_per, pix1 = min(p.hw, pix0 + pix_per);
+  const long long n = static_cast<long long>(max(0, pix1 - pix0)) * p.cpg;
   float s = 0.f, sx = 0.f;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const int pix = static_cast<int>(i / p.cpg);
-    const int c = g * p.cpg + static_cast<int>(i - static_cast<long long>(pix) * p.cpg);
+    const int pl = static_cast<int>(i / p.cpg);
+    const int pix = pix0 + pl;
+    const int c = g * p.cpg + static_cast<int>(i - static_cast<long long>(pl) * p.cpg);
     const float xv = c < p.c0 ? p.x0[(static_cast<long long>(b) * p.hw + pix) * p.c0 + c]
                               : p.x1[(static_cast<long long>(b) * p.hw + pix) * p.c1 + (c - p.c0)];
     const float xhat = (xv - mean) * rstd;
@@ -144,8 +149,9 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const GnBwdParams p)
   if (threadIdx.x == 0) {
     float a = 0.f, c2 = 0.f;
     for (int w = 0; w < 8; ++w) a += sh[0][w], c2 += sh[1][w];
-    p.red[(static_cast<long long>(b) * p.groups + g) * 2] = a;
-    p.red[(static_cast<long long>(b) * p.groups + g) * 2 + 1] = c2;
+    float* dst = p.red + ((static_cast<long long>(b) * p.groups + g) * nslab + slab) * 2;
+    dst[0] = a;
+    dst[1] = c2;
   }
 }
 
@@ -160,7 +166,11 @@ __global__ void gn_bwd_apply_kernel(const GnBwdParams p) {
     const int c = static_cast<int>(i - static_cast<long long>(pix) * p.C);
     const int g = c / p.cpg;
     const float mean = p.stats[(static_cast<long long>(b) * p.groups + g) * 2], rstd = p.stats[(static_cast<long long>(b) * p.groups + g) * 2 + 1];
-    const float sg = p.red[(static_cast<long long>(b) * p.groups + g) * 2], sgx = p.red[(static_cast<long long>(b) * p.groups + g) * 2 + 1];
+    float sg = 0.f, sgx = 0.f;
+    {
+      const float2* part = reinterpret_cast<const float2*>(p.red) + (static_cast<long long>(b) * p.groups + g) * p.nslab;
+      for (int k = 0; k < p.nslab; ++k) sg += part[k].x, sgx += part[k].y;   // fixed order (the partials are L1 / L2 resident)
+    }
     const bool first = c < p.c0;
     const long long off = first ? (static_cast<long long>(b) * p.hw + pix) * p.c0 + c : (static_cast<long long>(b) * p.hw + pix) * p.c1 + (c - p.c0);
     const float xv = first ? p.x0[off] : p.x1[off];
@@ -198,48 +208,68 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ dh, const __n
 // grid = (ceil(W / 64), n_slabs): a CTA reduces its slab of rows for 64 columns; the slab partials are then added up in
 // slab order by lora_wgrad_finish_kernel (deterministic; no float atomics).
 constexpr int WG_R = 16;
+constexpr int WG_ROWS = 64;   // rows per round
 __global__ void __launch_bounds__(256) lora_wgrad_partial_kernel(const __nv_bfloat16* __restrict__ wide, long long ld_w, int col0_w,
                                                                  const __nv_bfloat16* __restrict__ skinny, long long ld_s, int col0_s,
                                                                  float* __restrict__ partial, long long M, int W, int R) {
   pdl_trigger();
   pdl_wait();
-  const int wl = threadIdx.x & 63, rl = threadIdx.x >> 6;   // 64 columns x 4 row lanes
-  const int w = blockIdx.x * 64 + wl;
-  const long long rows_per = (M + gridDim.y - 1) / gridDim.y;
+  const int cp = threadIdx.x & 31, rl = threadIdx.x >> 5;   // 32 column pairs (64 columns) x 8 row lanes
+  const int w = blockIdx.x * 64 + 2 * cp;
+  const long long rows_per = ((M + gridDim.y - 1) / gridDim.y + WG_ROWS - 1) / WG_ROWS * WG_ROWS;
   const long long m0 = blockIdx.y * rows_per, m1 = min(M, m0 + rows_per);
-  float acc[WG_R];
+  float acc0[WG_R], acc1[WG_R];
 #pragma unroll
-  for (int r = 0; r < WG_R; ++r) acc[r] = 0.f;
-  __shared__ float sk[16][WG_R];
-  for (long long mb = m0; mb < m1; mb += 16) {
-    // sixteen rows per round: their skinny vectors go through smem (every thread needs all R values of its rows), each
-    // thread then handles rows mb + rl, + 4, + 8, + 12 with four independent loads of `wide` in flight
-    {
-      const int rr = threadIdx.x >> 4, cc = threadIdx.x & 15;
+  for (int r = 0; r < WG_R; ++r) acc0[r] = acc1[r] = 0.f;
+  __shared__ float sk[WG_ROWS][WG_R];
+  const bool pair_ok = (w + 1 < W) && ((ld_w | col0_w) % 2 == 0);
+  for (long long mb = m0; mb < m1; mb += WG_ROWS) {
+    // sixty-four rows per round: their skinny vectors go through smem (every thread needs all R values of its rows);
+    // each thread then handles rows mb + rl, + 8, ... with eight independent 4-byte loads of `wide` in flight
+#pragma unroll
+    for (int k = 0; k < WG_ROWS * WG_R / 256; ++k) {
+      const int idx = threadIdx.x + k * 256, rr = idx >> 4, cc = idx & 15;
       const long long m = mb + rr;
       sk[rr][cc] = (m < m1 && cc < R) ? __bfloat162float(skinny[m * ld_s + col0_s + cc]) : 0.f;
     }
     __syncthreads();
-    float x[4];
+    float x0[8], x1[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long m = mb + rl + 4 * k;
-      x[k] = (m < m1 && w < W) ? __bfloat162float(wide[m * ld_w + col0_w + w]) : 0.f;
+    for (int k = 0; k < 8; ++k) {
+      const long long m = mb + rl + 8 * k;
+      x0[k] = x1[k] = 0.f;
+      if (m < m1 && w < W) {
+        if (pair_ok) {
+          const uint32_t v = *reinterpret_cast<const uint32_t*>(wide + m * ld_w + col0_w + w);
+          x0[k] = __uint_as_float(v << 16), x1[k] = __uint_as_float(v & 0xffff0000u);
+        } else {
+          x0[k] = __bfloat162float(wide[m * ld_w + col0_w + w]);
+          if (w + 1 < W) x1[k] = __bfloat162float(wide[m * ld_w + col0_w + w + 1]);
+        }
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 8; ++k)
 #pragma unroll
-      for (int r = 0; r < WG_R; ++r) acc[r] = fmaf(x[k], sk[rl + 4 * k][r], acc[r]);
+      for (int r = 0; r < WG_R; ++r) {
+        const float sv = sk[rl + 8 * k][r];
+        acc0[r] = fmaf(x0[k], sv, acc0[r]);
+        acc1[r] = fmaf(x1[k], sv, acc1[r]);
+      }
     __syncthreads();
   }
-  __shared__ float red[4][64][WG_R + 1];
+  __shared__ float red[8][64][WG_R + 1];
 #pragma unroll
-  for (int r = 0; r < WG_R; ++r) red[rl][wl][r] = acc[r];
+  for (int r = 0; r < WG_R; ++r) red[rl][2 * cp][r] = acc0[r], red[rl][2 * cp + 1][r] = acc1[r];
   __syncthreads();
-  if (rl == 0 && w < W) {
-    float* dst = partial + (static_cast<long long>(blockIdx.y) * W + w) * WG_R;
+  for (int i = threadIdx.x; i < 64 * WG_R; i += 256) {   // fixed-order sum over the eight row lanes
+    const int wl = i >> 4, r = i & 15;
+    if (blockIdx.x * 64 + wl < W) {
+      float t = 0.f;
 #pragma unroll
-    for (int r = 0; r < WG_R; ++r) dst[r] = (red[0][wl][r] + red[1][wl][r]) + (red[2][wl][r] + red[3][wl][r]);
+      for (int k = 0; k < 8; ++k) t += red[k][wl][r];
+      partial[(static_cast<long long>(blockIdx.y) * W + blockIdx.x * 64 + wl) * WG_R + r] = t;
+    }
   }
 }
 
@@ -342,7 +372,8 @@ extern "C" int idb_groupnorm_backward(const idb_groupnorm_bwd_args* a, void* str
   p.dy = a->dy, p.x0 = a->x0, p.x1 = a->x1, p.c0 = a->c0, p.c1 = a->x1 ? a->c1 : 0, p.C = C, p.hw = a->hw, p.groups = a->groups;
   p.cpg = C / a->groups, p.silu = a->silu, p.stats = a->stats, p.gamma = a->gamma, p.beta = a->beta, p.red = a->scratch;
   p.dx0 = a->dx0, p.dx1 = a->dx1, p.add0 = a->add0, p.add1 = a->add1;
-  launch_pdl(gn_bwd_reduce_kernel, dim3(dim3(a->groups, a->batch)), dim3(256), 0, stream, p);
+  p.nslab = a->hw >= 2048 ? 16 : (a->hw >= 256 ? 4 : 1);   // (scratch holds 16 slabs)
+  launch_pdl(gn_bwd_reduce_kernel, dim3(dim3(a->groups, a->batch, p.nslab)), dim3(256), 0, stream, p);
   IDB_CHECK_LAUNCH_B("gn_bwd_reduce");
   const long long per_image = static_cast<long long>(a->hw) * C;
   launch_pdl(gn_bwd_apply_kernel, dim3(dim3(grid_for_b(per_image, 256, num_sms() * 8 / (a->batch > 8 ? 8 : a->batch) + 1), a->batch)), dim3(256), 0, stream, p);

@@ -256,7 +256,7 @@ def groupnorm_backward(dy, x0, gamma, beta, stats, *, groups: int, silu: bool, x
     if x1 is not None and dx1 is None and want_dx1:
         dx1 = torch.empty_like(x1)
         add1 = False
-    scratch = torch.empty((B, groups, 2), dtype=f32, device=x0.device)
+    scratch = torch.empty((B, groups, 16, 2), dtype=f32, device=x0.device)     # up to 16 pixel slabs per (image, group)
     args = _lib.GroupNormBwdArgs(dy=dy.data_ptr(), x0=x0.data_ptr(), c0=c0, x1=_lib.ptr(x1), c1=c1, batch=B, hw=hw, groups=groups,
                                  silu=int(silu), stats=stats.data_ptr(), gamma=gamma.data_ptr(), beta=beta.data_ptr(),
                                  scratch=scratch.data_ptr(), dx0=_lib.ptr(dx0), dx1=_lib.ptr(dx1), add0=int(add0), add1=int(add1))

@@ -328,7 +328,7 @@ int idb_layernorm_backward(const float* dy, const float* x, const float* gamma, 
                            float eps, void* stream);
 /* GroupNorm(+SiLU) input gradient over the logical concatenation [x0 | x1] (as idb_groupnorm reads it).  dy fp32
  * [batch, hw, C0+C1] = gradient with respect to act(GN(x)); stats fp32 [batch, groups, 2] = (mean, rstd) of the forward;
- * scratch fp32 [batch, groups, 2]; dx0 / dx1 fp32 like x0 / x1 (either may be NULL), accumulated into when add0 / add1. */
+ * scratch fp32 [batch, groups, 16, 2]; dx0 / dx1 fp32 like x0 / x1 (either may be NULL), accumulated into when add0 / add1. */
 typedef struct {
   const float* dy;
   const float* x0; int32_t c0;
