@@ -435,7 +435,8 @@ def run_sweep_config(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
-        n0 = _lib.launch_count
+        from faceposegenerator_b200 import pipeline as _pl
+        n0 = _lib.launch_count + _pl.graph_launches
         t0 = time.perf_counter()
         stats = sweep.run_sweep(cfg, rank=rank, world_size=world, device=str(dev), batch_prompts=args.batch_prompts)
         torch.cuda.synchronize(dev)
@@ -455,7 +456,7 @@ def run_sweep_config(args):
                                          "CFG 5.0, prompt strings -> CLIP tower -> pipe -> PNG files (async writer), identities sharded "
                                          f"over {world} GPU(s)", "batch_prompts": args.batch_prompts, "wall_s": dt,
                              "timing": "host wall clock around the whole sweep incl. file writes, max over ranks"},
-                  "gpu_launches": int(_lib.launch_count - n0)})
+                  "gpu_launches": int(_lib.launch_count + _pl.graph_launches - n0)})
     finally:
         shutil.rmtree(root, ignore_errors=True)
         if world > 1:

@@ -31,6 +31,7 @@ from .weights import (LORA_FILE, UNET_CONFIG, VAE_CONFIG, load_lora_state, rando
 f32 = torch.float32
 _COMPONENT_CACHE = {}   # (model id, device) -> components with packed base weights (LoRA hot-swaps on top)
 MAX_STEP_STATES = 4     # CUDA-graph step states kept per UNet (each owns its activations' private pool)
+graph_launches = 0      # kernels of this library launched through CUDA-graph replays (not seen by `_lib.launch_count`)
 # keyword arguments of diffusers' `StableDiffusionPipeline.__call__` that are accepted and have no effect on this path
 _IGNORED_CALL_KWARGS = {"callback_on_step_end_tensor_inputs": None, "callback_steps": None, "eta": 0.0,
                         "guidance_rescale": 0.0, "clip_skip": None, "cross_attention_kwargs": None, "callback": None,
@@ -412,6 +413,9 @@ class StableDiffusionPipeline:
                     images = [Image.fromarray(a) for a in arr]
                 else:
                     raise ValueError(f"unknown output_type {output_type!r}")
+        if graphs:
+            global graph_launches
+            graph_launches += st.launches_ctx + len(timesteps) * st.launches_per_step + (0 if output_type == "latent" else st.launches_vae)
         if not return_dict:
             return (images, None)
         out = StableDiffusionPipelineOutput(images)
