@@ -14,4 +14,28 @@ from .unet import UNet2DConditionModel  # noqa: F401
 from .vae import AutoencoderKL  # noqa: F401
 
 __all__ = ["StableDiffusionPipeline", "DDPMScheduler", "UNet2DConditionModel", "AutoencoderKL",
-           "AutoPipelineForText2Image", "DPMSolverMultistepScheduler", "StableDiffusionPipelineOutput"]
+           "AutoPipelineForText2Image", "DPMSolverMultistepScheduler", "StableDiffusionPipelineOutput", "patch"]
+
+
+def patch(pipe, lora=None, device=None):
+    """Swap the B200 components into an existing diffusers-style pipeline object IN PLACE: `pipe.unet`,
+    `pipe.vae` and `pipe.scheduler` are rebuilt from the pipeline's own `state_dict()`s / scheduler config (the key names
+    and call surfaces are the diffusers ones), LoRA adapters (`lora`: a directory / file written by the reference trainer,
+    `train_ID-Booth.py:696-720`, or a {path: (down, up, scale)} dict) are installed fused and unmerged instead of through
+    peft injection.  Returns `pipe`."""
+    import torch
+    from .weights import UNET_CONFIG, VAE_CONFIG, load_lora_state
+    dev = torch.device(device or getattr(pipe, "device", None) or "cuda:0")
+    if dev.type != "cuda":
+        raise RuntimeError("patch(): the pipeline must live on a CUDA device (sm_100a); there is no CPU path")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(dev):
+        unet = UNet2DConditionModel({k: v.detach().float().cpu() for k, v in pipe.unet.state_dict().items()}, UNET_CONFIG, dev)
+        vae = AutoencoderKL({k: v.detach().float().cpu() for k, v in pipe.vae.state_dict().items()}, VAE_CONFIG, dev)
+        cfg = pipe.scheduler.config
+        sched = DDPMScheduler.from_config(dict(cfg) if isinstance(cfg, dict) else cfg)
+        if lora is not None:
+            unet.set_lora(lora if isinstance(lora, dict) else load_lora_state(str(lora)))
+    pipe.unet, pipe.vae, pipe.scheduler = unet, vae, sched
+    return pipe

@@ -301,3 +301,26 @@ def test_missing_weights_raise_unless_random_init_is_asked_for(cuda_dev, monkeyp
         p = StableDiffusionPipeline.from_pretrained(MODEL, allow_random_weights=True)
         p.unet = object()
         p(prompt="x", cross_attention_kwargs={"scale": 0.5})
+
+
+def test_patch_replaces_the_components_of_a_pipeline_object(world):
+    """`faceposegenerator_b200.patch(pipe)`: a stand-in for a real diffusers pipeline object (modules exposing
+    `state_dict()`, a scheduler with `.config`) gets the B200 UNet / VAE / scheduler built from its own tensors; the patched
+    UNet reproduces the directly constructed one bit for bit."""
+    from types import SimpleNamespace
+    import faceposegenerator_b200 as idb
+    from faceposegenerator_b200.weights import SCHEDULER_CONFIG
+    w, dev = world, world["dev"]
+    fake = SimpleNamespace(unet=SimpleNamespace(state_dict=lambda: w["sd"]), vae=SimpleNamespace(state_dict=lambda: w["vsd"]),
+                           scheduler=SimpleNamespace(config=dict(SCHEDULER_CONFIG, prediction_type="v_prediction")), device=dev)
+    out = idb.patch(fake, lora=w["lora"])
+    assert out is fake and isinstance(fake.unet, idb.UNet2DConditionModel) and isinstance(fake.vae, idb.AutoencoderKL)
+    assert fake.scheduler.config.prediction_type == "v_prediction"
+    g = torch.Generator().manual_seed(3)
+    x, ctx = torch.randn(2, 4, 64, 64, generator=g).to(dev), torch.randn(2, 77, 1024, generator=g).to(dev)
+    w["unet"].set_lora(w["lora"])
+    a = fake.unet(x, 321, ctx, return_dict=False)[0]
+    b = w["unet"](x, 321, ctx, return_dict=False)[0]
+    assert torch.equal(a, b)
+    z = torch.randn(1, 4, 64, 64, generator=g).to(dev)
+    assert torch.equal(fake.vae.decode(z).sample, w["vae"].decode(z).sample)

@@ -404,6 +404,41 @@ def test_no_cpu_fallback():
         ops.layernorm(torch.zeros(4, 8), torch.ones(8), torch.zeros(8))
 
 
+def test_integration_stub_matches_the_binding():
+    """The ctypes struct a maintainer copies out of INTEGRATION.md has exactly the fields of the shipped binding, in order
+    (a shorter struct would make the library read past it: VERDICT r1 weak #12)."""
+    import ctypes as C
+    from faceposegenerator_b200 import _lib
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    body = text[text.index("class GemmConvArgs(C.Structure):"):text.index("_lib.idb_gemm_conv.argtypes")]
+    fields = re.findall(r'\("(\w+)", C\.(c_\w+)\)', body)
+    assert [(n, getattr(C, t)) for n, t in fields] == list(_lib.GemmConvArgs._fields_)
+    assert "idb_sizeof_args(0) == C.sizeof(GemmConvArgs)" in text
+
+
+def test_weight_policy_and_snapshot_resolution(tmp_path, monkeypatch):
+    """Random-init stand-ins are an explicit opt-in; hub ids resolve through the local Hugging Face cache."""
+    from faceposegenerator_b200 import pipeline as pl
+    monkeypatch.delenv("IDB_ALLOW_RANDOM_WEIGHTS", raising=False)
+    assert pl.random_weights_allowed() is False and pl.random_weights_allowed(True) is True
+    monkeypatch.setenv("IDB_ALLOW_RANDOM_WEIGHTS", "1")
+    assert pl.random_weights_allowed() is True and pl.random_weights_allowed(False) is False
+    snap = tmp_path / "hub" / "models--org--name" / "snapshots" / "abc123"
+    (snap / "unet").mkdir(parents=True)
+    (tmp_path / "hub" / "models--org--name" / "refs").mkdir()
+    (tmp_path / "hub" / "models--org--name" / "refs" / "main").write_text("abc123")
+    monkeypatch.setenv("HF_HUB_CACHE", str(tmp_path / "hub"))
+    assert pl.resolve_snapshot("org/name") == str(snap)
+    assert pl.resolve_snapshot(str(snap)) == str(snap)
+    assert pl.resolve_snapshot("org/other") is None
+    # .bin checkpoints are read, not silently replaced
+    import torch
+    torch.save({"w": torch.ones(2)}, snap / "unet" / "diffusion_pytorch_model.bin")
+    sd = pl._load_component_state(str(snap), "unet")
+    assert sd is not None and torch.equal(sd["w"], torch.ones(2))
+    assert pl._load_component_state(str(snap), "vae") is None
+
+
 def test_c_abi_library_exports_every_declared_symbol():
     """include/idb.h <-> libidb_b200.so <-> the ctypes binding agree (no compute calls)."""
     import ctypes
@@ -421,7 +456,8 @@ def test_c_abi_library_exports_every_declared_symbol():
     import subprocess
     import tempfile
     structs = {"idb_gemm_conv_args": _lib.GemmConvArgs, "idb_attention_args": _lib.AttentionArgs,
-               "idb_groupnorm_args": _lib.GroupNormArgs, "idb_time_embed_args": _lib.TimeEmbedArgs}
+               "idb_groupnorm_args": _lib.GroupNormArgs, "idb_time_embed_args": _lib.TimeEmbedArgs,
+               "idb_attention_bwd_args": _lib.AttentionBwdArgs, "idb_groupnorm_bwd_args": _lib.GroupNormBwdArgs}
     prog = '#include <stdio.h>\n#include <stddef.h>\n#include "idb.h"\nint main(void){\n'
     for cname, cls in structs.items():
         prog += f'printf("{cname} %zu\\n", sizeof({cname}));\n'
