@@ -40,15 +40,25 @@ def crop_to_bbox(image: torch.Tensor, bbox) -> torch.Tensor:
     return image[max(0, y0):min(y1, lim), max(0, x0):min(x1, lim)]
 
 
-def load_arcface(weights: Optional[str] = "ArcFace_files/ArcFace_r100_ms1mv3_backbone.pth", device="cuda:0"):
-    """`prepare_locked_ArcFace_model` (ArcFace_functions.py:27-37): r100, frozen, eval.  Without the checkpoint file
-    (offline) the backbone gets deterministic random weights keyed by parameter name."""
+def load_arcface(weights: Optional[str] = "ArcFace_files/ArcFace_r100_ms1mv3_backbone.pth", device="cuda:0",
+                 allow_random_weights: Optional[bool] = None):
+    """`prepare_locked_ArcFace_model` (ArcFace_functions.py:27-37): r100, frozen, eval.  A missing checkpoint RAISES:
+    "ground-truth" embeddings from a random backbone would be silently useless.  Deterministic random weights keyed by
+    parameter name are an explicit opt-in for benchmarking / tests (`allow_random_weights=True` or
+    IDB_ALLOW_RANDOM_WEIGHTS=1)."""
     from .iresnet import IResNet
+    from .pipeline import random_weights_allowed
     from .weights import random_iresnet_state_dict
     if weights and os.path.isfile(weights):
-        sd = torch.load(weights, map_location="cpu")
-    else:
+        sd = torch.load(weights, map_location="cpu", weights_only=True)
+    elif random_weights_allowed(allow_random_weights):
+        import warnings
+        warnings.warn(f"ArcFace checkpoint {weights!r} not found: RANDOM-INIT IResNet-100 (benchmarking / testing only; the "
+                      "embeddings carry no identity information)", stacklevel=2)
         sd = random_iresnet_state_dict("r100", 0)
+    else:
+        raise FileNotFoundError(f"ArcFace checkpoint not found: {weights!r} (ArcFace_functions.py:29-30 loads "
+                                "ArcFace_r100_ms1mv3_backbone.pth); pass its path, or opt in to random weights for benchmarking")
     return IResNet(sd, "r100", device)
 
 

@@ -58,14 +58,15 @@ def pack_lora_dgrad(adapters, n_in: int, seg_in: int, device=None):
     k = live[0][0].shape[1]
     if r * len(adapters) > 16:
         raise ValueError("fused LoRA backward supports total rank <= 16")
-    down = torch.zeros((16, len(adapters) * seg_in), dtype=f32)
-    up = torch.zeros((k, 64), dtype=f32)
+    src = live[0][0].device
+    down = torch.zeros((16, len(adapters) * seg_in), dtype=f32, device=src)
+    up = torch.zeros((k, 64), dtype=f32, device=src)
     for s_, a in enumerate(adapters):
         if a is None:
             continue
         A, B, scale = a
-        down[s_ * r:(s_ + 1) * r, s_ * seg_in:(s_ + 1) * seg_in] = (B.float().cpu() * float(scale)).t()
-        up[:, s_ * r:(s_ + 1) * r] = A.float().cpu().t()
+        down[s_ * r:(s_ + 1) * r, s_ * seg_in:(s_ + 1) * seg_in] = (B.detach().float().to(src) * float(scale)).t()
+        up[:, s_ * r:(s_ + 1) * r] = A.detach().float().to(src).t()
     return down.to(device=device, dtype=bf16).contiguous(), up.to(device=device, dtype=bf16).contiguous()
 
 
@@ -125,23 +126,29 @@ class UNetLoRAGrad:
         wo = wo.view(u.out_channels, 3, 3, -1).permute(0, 3, 1, 2)                                                 # [4, 320, 3, 3]
         self.w_out_dgrad = wo.flip(2, 3).permute(1, 2, 3, 0).contiguous().to(dev, f32)                              # [320, 3, 3, 4]
         for t in u.transformers:
-            tb = t.path + ".transformer_blocks.0"
-            a1, a2 = tb + ".attn1", tb + ".attn2"
-            g = self.lora.get
-            C = t.c
-            ff1 = t.w_ff1          # interleaved [8C, C]
             self.tr_w[id(t)] = SimpleNamespace(
                 d_in=t.w_in.t().contiguous(), d_out=t.w_out.t().contiguous(),
                 d_qkv=t.w_qkv.t().contiguous(), d_o1=t.w_o1.t().contiguous(), d_q2=t.w_q2.t().contiguous(), d_o2=t.w_o2.t().contiguous(),
-                d_ff1=ff1.t().contiguous(), d_ff2=t.w_ff2.t().contiguous(),
-                l_qkv=pack_lora_dgrad([g(a1 + ".to_q"), g(a1 + ".to_k"), g(a1 + ".to_v")], C, C, dev),
-                l_o1=pack_lora_dgrad([g(a1 + ".to_out.0")], C, C, dev),
-                l_q2=pack_lora_dgrad([g(a2 + ".to_q")], C, C, dev),
-                l_o2=pack_lora_dgrad([g(a2 + ".to_out.0")], C, C, dev),
-                # skinny operands of the weight gradients: T = x A^T (columns = rank, padded to 32 GEMM columns) and U = dY (s B)
-                A={k: pad_rows(self.lora[k][0].to(dev, bf16), 32) for k in self._keys(t) if k in self.lora},
-                Bs={k: pad_rows((self.lora[k][1].float() * float(self.lora[k][2])).t().contiguous().to(dev, bf16), 32)
-                    for k in self._keys(t) if k in self.lora})
+                d_ff1=t.w_ff1.t().contiguous(), d_ff2=t.w_ff2.t().contiguous())
+        self.update_lora(self.lora)
+
+    def update_lora(self, lora):
+        """(Re)pack only the adapter operands of the backward (a few MB): the transposed base weights are packed once."""
+        self.lora, dev = lora, self.dev
+        g = lora.get
+        for t in self.u.transformers:
+            tb = t.path + ".transformer_blocks.0"
+            a1, a2 = tb + ".attn1", tb + ".attn2"
+            C = t.c
+            w = self.tr_w[id(t)]
+            w.l_qkv = pack_lora_dgrad([g(a1 + ".to_q"), g(a1 + ".to_k"), g(a1 + ".to_v")], C, C, dev)
+            w.l_o1 = pack_lora_dgrad([g(a1 + ".to_out.0")], C, C, dev)
+            w.l_q2 = pack_lora_dgrad([g(a2 + ".to_q")], C, C, dev)
+            w.l_o2 = pack_lora_dgrad([g(a2 + ".to_out.0")], C, C, dev)
+            # skinny operands of the weight gradients: T = x A^T (columns = rank, padded to 32 GEMM columns) and U = dY (s B)
+            w.A = {k: pad_rows(lora[k][0].detach().to(dev, bf16), 32) for k in self._keys(t) if k in lora}
+            w.Bs = {k: pad_rows((lora[k][1].detach().float() * float(lora[k][2])).t().contiguous().to(dev, bf16), 32)
+                    for k in self._keys(t) if k in lora}
 
     @staticmethod
     def _keys(t):
@@ -440,8 +447,14 @@ class LoRATrainer:
         return {k: (d.detach(), u.detach(), s) for k, (d, u, s) in self.params.items()}
 
     def _install(self):
-        self.unet.set_lora({k: (d.detach().cpu(), u.detach().cpu(), s) for k, (d, u, s) in self.params.items()})
-        self.engine = UNetLoRAGrad(self.unet, self.lora())
+        """Re-install the updated adapters: in place into the UNet's persistent packed buffers (packed on the GPU) and into
+        the backward's adapter operands; base weights (forward and transposed backward packing) are untouched."""
+        lora = self.lora()
+        self.unet.set_lora(lora)
+        if getattr(self, "engine", None) is None:
+            self.engine = UNetLoRAGrad(self.unet, lora)
+        else:
+            self.engine.update_lora(lora)
 
     @torch.no_grad()
     def step(self, latents, noise, timesteps, encoder_hidden_states):

@@ -74,12 +74,13 @@ def pack_lora(adapters: Sequence[Optional[Tuple[torch.Tensor, torch.Tensor, floa
     rank_pad = (r + 3) // 4 * 4
     k = k or live[0][0].shape[1]
     seg_n = seg_n or live[0][1].shape[0]
-    down = torch.zeros((len(adapters) * 16, k), dtype=f32)
-    up = torch.zeros((len(adapters) * seg_n, LORA_UP_COLS), dtype=f32)
+    src = live[0][0].device      # adapters that already live on the GPU (training) are packed there, without a host round trip
+    down = torch.zeros((len(adapters) * 16, k), dtype=f32, device=src)
+    up = torch.zeros((len(adapters) * seg_n, LORA_UP_COLS), dtype=f32, device=src)
     for s, a in enumerate(adapters):
         if a is None:
             continue
         d, u, scale = a
-        down[s * 16:s * 16 + d.shape[0]] = d.float().cpu()
-        up[s * seg_n:(s + 1) * seg_n, :u.shape[1]] = u.float().cpu() * float(scale)
+        down[s * 16:s * 16 + d.shape[0]] = d.detach().float().to(src)
+        up[s * seg_n:(s + 1) * seg_n, :u.shape[1]] = u.detach().float().to(src) * float(scale)
     return down.to(device=device, dtype=bf16).contiguous(), up.to(device=device, dtype=bf16).contiguous()

@@ -50,6 +50,21 @@ for _ in range(n):
     bw += b.elapsed_time(c)
 line = {"B": B, "forward_ms": round(fw / n, 2), "backward_ms": round(bw / n, 2), "step_ms": round((fw + bw) / n, 2)}
 print(json.dumps(line), flush=True)
+# the whole optimisation step of the reference (add_noise, forward, MSE, backward, clip, AdamW, re-install of the adapters)
+from faceposegenerator_b200 import DDPMScheduler  # noqa: E402
+from faceposegenerator_b200.lora_backward import LoRATrainer  # noqa: E402
+tr = LoRATrainer(unet, lora, DDPMScheduler.from_pretrained("stabilityai/stable-diffusion-2-1-base", subfolder="scheduler"))
+ti = t.long()
+for _ in range(2):
+    tr.step(x, tgt, ti, ctx)
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(5):
+    tr.step(x, tgt, ti, ctx)
+torch.cuda.synchronize()
+line["trainer_step_wall_ms"] = round((time.perf_counter() - t0) / 5 * 1e3, 2)
+print(json.dumps(line), flush=True)
+unet.set_lora(lora)
 # comparator: torch autograd through the oracle module graph, bf16 weights / activations, fp32 adapters (the reference trains
 # with fp16 autocast + fp32 adapters, train_ID-Booth.py:779-785), SDPA attention, eager
 try:
