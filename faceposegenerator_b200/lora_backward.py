@@ -89,7 +89,6 @@ class UNetLoRAGrad:
         self.dev = unet.device
         self.lora = lora
         self.rank = next(iter(lora.values()))[0].shape[0]
-        self._packed = {}
         self._pack_backward_weights()
 
     # ------------------------------------------------------------------ one-time packing of the backward operands
@@ -133,22 +132,44 @@ class UNetLoRAGrad:
         self.update_lora(self.lora)
 
     def update_lora(self, lora):
-        """(Re)pack only the adapter operands of the backward (a few MB): the transposed base weights are packed once."""
+        """(Re)pack only the adapter operands of the backward (a few MB), in place into persistent buffers: the transposed
+        base weights are packed once.  Per adapter: s B^T and A^T slices of the fused-LoRA dgrad operands (down' [16, n_seg C],
+        up' [K, 64], see `pack_lora_dgrad`) and the skinny GEMM weights of the weight gradients (A and s B^T padded to 32 rows)."""
         self.lora, dev = lora, self.dev
-        g = lora.get
+        r = self.rank
         for t in self.u.transformers:
             tb = t.path + ".transformer_blocks.0"
             a1, a2 = tb + ".attn1", tb + ".attn2"
             C = t.c
             w = self.tr_w[id(t)]
-            w.l_qkv = pack_lora_dgrad([g(a1 + ".to_q"), g(a1 + ".to_k"), g(a1 + ".to_v")], C, C, dev)
-            w.l_o1 = pack_lora_dgrad([g(a1 + ".to_out.0")], C, C, dev)
-            w.l_q2 = pack_lora_dgrad([g(a2 + ".to_q")], C, C, dev)
-            w.l_o2 = pack_lora_dgrad([g(a2 + ".to_out.0")], C, C, dev)
-            # skinny operands of the weight gradients: T = x A^T (columns = rank, padded to 32 GEMM columns) and U = dY (s B)
-            w.A = {k: pad_rows(lora[k][0].detach().to(dev, bf16), 32) for k in self._keys(t) if k in lora}
-            w.Bs = {k: pad_rows((lora[k][1].detach().float() * float(lora[k][2])).t().contiguous().to(dev, bf16), 32)
-                    for k in self._keys(t) if k in lora}
+            if not hasattr(w, "A"):
+                w.A, w.Bs = {}, {}
+                for name, keys in (("l_qkv", [a1 + ".to_q", a1 + ".to_k", a1 + ".to_v"]), ("l_o1", [a1 + ".to_out.0"]),
+                                   ("l_q2", [a2 + ".to_q"]), ("l_o2", [a2 + ".to_out.0"])):
+                    if all(k in lora for k in keys):
+                        setattr(w, name, (torch.zeros((16, len(keys) * C), dtype=bf16, device=dev), torch.zeros((C, 64), dtype=bf16, device=dev)))
+                    else:    # partially adapted projection groups take the generic (allocating) packer
+                        setattr(w, name, pack_lora_dgrad([lora.get(k) for k in keys], C, C, dev))
+                w._groups = (("l_qkv", [a1 + ".to_q", a1 + ".to_k", a1 + ".to_v"]), ("l_o1", [a1 + ".to_out.0"]),
+                             ("l_q2", [a2 + ".to_q"]), ("l_o2", [a2 + ".to_out.0"]))
+            for name, keys in w._groups:
+                if not all(k in lora for k in keys):
+                    setattr(w, name, pack_lora_dgrad([lora.get(k) for k in keys], C, C, dev))
+                    continue
+                down, up = getattr(w, name)
+                for s_, k in enumerate(keys):
+                    A, B, scale = lora[k]
+                    down[s_ * r:(s_ + 1) * r, s_ * C:(s_ + 1) * C].copy_((B.detach().float() * float(scale)).t())
+                    up[:, s_ * r:(s_ + 1) * r].copy_(A.detach().t())
+            for k in self._keys(t):
+                if k not in lora:
+                    continue
+                A, B, scale = lora[k]
+                if k not in w.A:
+                    w.A[k] = torch.zeros((32, A.shape[1]), dtype=bf16, device=dev)
+                    w.Bs[k] = torch.zeros((32, B.shape[0]), dtype=bf16, device=dev)
+                w.A[k][:r].copy_(A.detach())
+                w.Bs[k][:r].copy_((B.detach().float() * float(scale)).t())
 
     @staticmethod
     def _keys(t):
@@ -472,12 +493,9 @@ class LoRATrainer:
         diff = pred - target
         loss = (diff * diff).mean()
         grads = self.engine.backward(diff * (2.0 / diff.numel()))
-        sq = torch.zeros((), device=dev)
         for k, (d, u, _) in self.params.items():
             d.grad, u.grad = grads[k][0], grads[k][1]
-            sq = sq + d.grad.pow(2).sum() + u.grad.pow(2).sum()
-        norm = sq.sqrt()
-        torch.nn.utils.clip_grad_norm_([p for d, u, _ in self.params.values() for p in (d, u)], self.max_grad_norm)
+        norm = torch.nn.utils.clip_grad_norm_([p for d, u, _ in self.params.values() for p in (d, u)], self.max_grad_norm)   # (foreach)
         self.opt.step()
         self.opt.zero_grad(set_to_none=True)
         self._install()

@@ -194,29 +194,45 @@ class UNet2DConditionModel:
             get = (lambda k: lora.get(k)) if lora else (lambda k: None)
             a1, a2 = tb + ".attn1", tb + ".attn2"
             known.update(f"{a}.{m}" for a in (a1, a2) for m in ("to_q", "to_k", "to_v", "to_out.0"))
-            packed = {
-                "qkv": pack_lora([get(a1 + ".to_q"), get(a1 + ".to_k"), get(a1 + ".to_v")], self.device, seg_n=t.c, k=t.c),
-                "o1": pack_lora([get(a1 + ".to_out.0")], self.device, seg_n=t.c, k=t.c),
-                "q2": pack_lora([get(a2 + ".to_q")], self.device, seg_n=t.c, k=t.c),
-                "kv2": pack_lora([get(a2 + ".to_k"), get(a2 + ".to_v")], self.device, seg_n=t.c, k=self.cross_dim),
-                "o2": pack_lora([get(a2 + ".to_out.0")], self.device, seg_n=t.c, k=t.c),
+            groups = {
+                "qkv": ([get(a1 + ".to_q"), get(a1 + ".to_k"), get(a1 + ".to_v")], t.c),
+                "o1": ([get(a1 + ".to_out.0")], t.c),
+                "q2": ([get(a2 + ".to_q")], t.c),
+                "kv2": ([get(a2 + ".to_k"), get(a2 + ".to_v")], self.cross_dim),
+                "o2": ([get(a2 + ".to_out.0")], t.c),
             }
             bufs = t.__dict__.setdefault("lora_buf", {})
             active = {}
-            for name, (ld, lu) in packed.items():
-                if ld is None:
+            for name, (ads, k) in groups.items():
+                live = [a for a in ads if a is not None]
+                if not live:
                     active[name] = (None, None)       # the buffers (if any) stay alive for graphs captured with them
+                    topo.append(False)
+                    continue
+                old = bufs.get(name)
+                if old is not None and all(a is not None and a[0].shape[0] <= 16 for a in ads):
+                    # in place: two slice copies per adapter straight into the persistent packed buffers (graphs captured
+                    # with them stay valid; a training loop re-installs 128 adapters per step this way)
+                    ld, lu = old
+                    for s_, (d, u, scale) in enumerate(ads):
+                        r = d.shape[0]
+                        ld[s_ * 16:s_ * 16 + r].copy_(d.detach())
+                        if r < 16:
+                            ld[s_ * 16 + r:(s_ + 1) * 16].zero_()
+                        lu[s_ * t.c:(s_ + 1) * t.c, :r].copy_(u.detach() * float(scale))
+                        if r < lu.shape[1]:
+                            lu[s_ * t.c:(s_ + 1) * t.c, r:].zero_()
                 else:
-                    old = bufs.get(name)
+                    ld, lu = pack_lora(ads, self.device, seg_n=t.c, k=k)
+                    if old is not None and (old[0].shape != ld.shape or old[1].shape != lu.shape):
+                        self.step_cache.clear()   # captured graphs hold the old buffers' addresses
                     if old is not None and old[0].shape == ld.shape and old[1].shape == lu.shape:
                         old[0].copy_(ld)
                         old[1].copy_(lu)
                     else:
-                        if old is not None:
-                            self.step_cache.clear()   # captured graphs hold the old buffers' addresses
                         bufs[name] = (ld, lu)
-                    active[name] = bufs[name]
-                topo.append(ld is not None)
+                active[name] = bufs[name]
+                topo.append(True)
             t.lora = active
         if lora:
             unknown = set(lora) - known
