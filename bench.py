@@ -328,13 +328,20 @@ def run_native(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    step_events = []
-    pipe.step_events = step_events   # CUDA events on the launching stream around every denoise-step graph launch
+    # CUDA events on the launching stream around the denoising launches: one pair per whole-loop graph (30 steps in one
+    # launch, the default) or one pair per step graph (IDB_LOOP_GRAPH=0)
+    step_events, loop_events = [], []
+    if pipe.use_loop_graph and pipe.use_cuda_graph:
+        pipe.loop_events = loop_events
+    else:
+        pipe.step_events = step_events
     launches0 = _lib.launch_count
     ms_total = timed(call_resident, args.steps)
-    pipe.step_events = None
+    pipe.step_events = pipe.loop_events = None
     clocks = sampler.stop() if rank == 0 else None
     unet_ms = [a.elapsed_time(b) for a, b in step_events]
+    for a, b, k in loop_events:
+        unet_ms += [a.elapsed_time(b) / k] * k
     eager_launches = _lib.launch_count - launches0
     # graph replays do not pass through the ctypes counter: add their content (counted at capture time)
     gpu_launches = eager_launches + args.steps * pipe.launches_per_call(NUM_STEPS)
@@ -395,7 +402,8 @@ def run_native(args):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": (achieved / peaks["bf16_sustained"]) if achieved else None,
                          "traffic": None if big else _step_traffic(),
-                         "kernel": "UNet step graph (gemm_tc_kernel / attention_rs_kernel dominate; see profiles/)",
+                         "kernel": "UNet step (CFG pair forward + fused CFG/DDPM update) inside the denoising graph: gemm_tc_kernel / "
+                                   "attention_rs_kernel dominate; see profiles/",
                          "flops_per_launch": rows * tflop_row * 1e12,
                          "peak_source": peaks["source"] + ", sustained figure (timed inside a long step)"},
             "clocks": clocks,

@@ -116,6 +116,7 @@ EXPORTS = {
     "idb_last_error": (c_int32, [C.c_char_p, c_size_t]),
     "idb_device_check": (c_int32, []),
     "idb_num_sms": (c_int32, []),
+    "idb_launch_count": (C.c_uint64, []),
     "idb_gemm_conv": (c_int32, [C.POINTER(GemmConvArgs), c_void_p]),
     "idb_gemm_conv_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "idb_sizeof_args": (c_size_t, [c_int32]),
@@ -152,8 +153,7 @@ EXPORTS = {
 
 _lib: Optional[C.CDLL] = None
 trace = None      # profiling only: set to a list to record (entry point, description) per call
-launch_count = 0  # kernels launched through this binding (bench.py reports it as gpu_launches)
-_LAUNCHES_PER_CALL = {"idb_time_embed": 4, "idb_attention_backward": 2, "idb_groupnorm_backward": 2, "idb_lora_wgrad": 2}   # entry points that always launch more than one kernel
+launch_count = 0  # kernels launched by the library so far (exact: the library counts every launch; bench.py's gpu_launches)   # entry points that always launch more than one kernel
 
 
 def load() -> C.CDLL:
@@ -197,11 +197,13 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def call(name: str, *args, desc=None, launches: int = 0) -> None:
-    """`launches`: kernels this call enqueues when the caller knows (idb_groupnorm: 1 with producer sums, else 2)."""
+    """Calls an entry point; `launch_count` follows the library's own exact kernel-launch counter (`idb_launch_count`).
+    (`launches` is accepted for callers that know the count; the library's counter is authoritative.)"""
     global launch_count
     if trace is not None:
         trace.append((name, desc))
-    rc = getattr(load(), name)(*args)
+    lib = load()
+    rc = getattr(lib, name)(*args)
     if rc != 0:
         raise RuntimeError(f"{name} failed (code {rc}): {last_error()}")
-    launch_count += launches or _LAUNCHES_PER_CALL.get(name, 1)
+    launch_count = int(lib.idb_launch_count())

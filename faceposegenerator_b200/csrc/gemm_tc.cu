@@ -1026,6 +1026,7 @@ static int launch_gemm_e(const GemmParams& p, int grid, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  note_launch();
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
   if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("gemm_tc launch: ") + cudaGetErrorString(e));
   return IDB_OK;

@@ -41,6 +41,10 @@ inline cudaError_t ensure_dynamic_smem(K kern, int bytes, PerDeviceOnce& once) {
   return e;
 }
 
+// every kernel launch of the library goes through one of two sites (launch_pdl below, launch_gemm_e in gemm_tc.cu); both
+// count it, so a caller can report exactly how many kernels its calls enqueued (idb_launch_count())
+void note_launch();
+
 // kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-dependent-launch attribute (IDB_PDL=0 disables)
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
@@ -56,6 +60,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  note_launch();
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

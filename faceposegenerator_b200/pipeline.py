@@ -118,7 +118,11 @@ class StableDiffusionPipeline:
         self._progress = {}
         self._last_state = None          # step state (CUDA graphs + static buffers) used by the last call
         self.use_cuda_graph = os.environ.get("IDB_CUDA_GRAPH", "1") != "0"
-        self.step_events = None    # set to a list to collect (start, end) CUDA events around every denoise step
+        # one CUDA graph for ALL denoising steps of a call (the generator draws do not depend on the latents, so the noise
+        # tape is drawn up front in the same order); IDB_LOOP_GRAPH=0: one graph launch per step
+        self.use_loop_graph = os.environ.get("IDB_LOOP_GRAPH", "1") != "0"
+        self.step_events = None    # set to a list to collect (start, end) CUDA events around every denoise step (per-step graphs)
+        self.loop_events = None    # set to a list to collect (start, end, steps) around every whole-loop graph launch
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -226,16 +230,18 @@ class StableDiffusionPipeline:
         return prompt_embeds, negative_prompt_embeds
 
     # ------------------------------------------------------------------ one denoising step (graph-captured)
-    def _step_eager(self, st):
+    def _step_eager(self, st, temb=None, noise=None, coef=None):
+        """One denoising step on the state's static buffers (per-step graph), or on the given per-step rows of the
+        whole-loop tables (loop graph)."""
         n = st.n
         if st.do_cfg:
             st.x2[:n].copy_(st.latents)
             st.x2[n:].copy_(st.latents)
         else:
             st.x2.copy_(st.latents)
-        eps2 = self.unet.forward(st.x2, st.t_dev, context=st.context, temb=st.temb, return_dict=False)[0]
-        ops.cfg_ddpm_step(eps2, st.latents, st.noise, st.coef, guidance_scale=st.guidance_scale,
-                          use_cfg=st.do_cfg, v_prediction=st.vpred, x_prev=st.lat_next)
+        eps2 = self.unet.forward(st.x2, st.t_dev, context=st.context, temb=st.temb if temb is None else temb, return_dict=False)[0]
+        ops.cfg_ddpm_step(eps2, st.latents, st.noise if noise is None else noise, st.coef if coef is None else coef,
+                          guidance_scale=st.guidance_scale, use_cfg=st.do_cfg, v_prediction=st.vpred, x_prev=st.lat_next)
         st.latents.copy_(st.lat_next)
 
     def _step_state(self, n, h, w, do_cfg, guidance_scale, n_ctx, ctx_dim):
@@ -261,7 +267,10 @@ class StableDiffusionPipeline:
             t_dev=torch.zeros((rows,), dtype=f32, device=dev),
             temb=torch.zeros((rows, self.unet.t_w_all.shape[0]), dtype=f32, device=dev),
             coef=torch.zeros((5,), dtype=f32, device=dev), graph=None, ctx_graph=None, vae_graph=None, image=None,
-            launches_per_step=0, launches_ctx=0, launches_vae=0)
+            launches_per_step=0, launches_ctx=0, launches_vae=0,
+            # whole-loop graph (all steps of a call in ONE launch): per-step rows of the noise tape / time embedding /
+            # scheduler coefficients are static tables the captured steps read directly
+            loop_graph=None, loop_key=None, tape=None, temb_all=None, coef_all=None, launches_loop=0)
         if self.use_cuda_graph:
             cache[key] = st
             while len(cache) > MAX_STEP_STATES:
@@ -352,12 +361,48 @@ class StableDiffusionPipeline:
                 if st.ctx_graph is None:
                     st.ctx_graph, st.context, st.launches_ctx = self._capture(lambda: self.unet.encode_context(st.ctx_in))
                 st.ctx_graph.replay()
+                # the replay recomputed K/V from the adapters installed NOW (in-place buffers): the result is current
+                st.context.lora_version = self.unet._lora_version
             st.latents.copy_(latents)
             # the time embedding + all 22 time_emb_proj layers depend on the timestep only: one batched call for
             # every step, cached per schedule
             temb_table = self._time_embedding_table(timesteps)
 
-            for i in self.progress_bar(range(len(timesteps))):
+            steps = len(timesteps)
+            use_loop = graphs and self.use_loop_graph and teacher is None and collected is None and self.step_events is None
+            if use_loop:
+                lkey = (tuple(timesteps), self.scheduler.config.prediction_type)
+                if st.loop_graph is None or st.loop_key != lkey or st.tape.shape[0] != 1 + steps:
+                    st.tape = torch.zeros((1 + steps, n, 4, h, w), dtype=f32, device=dev)
+                    st.temb_all = temb_table[:, None, :].expand(steps, st.temb.shape[0], temb_table.shape[1]).contiguous()
+                    st.coef_all = torch.stack([self.scheduler.coef_row(i, timesteps[i], dev) for i in range(steps)]).contiguous()
+                    st.loop_graph = None
+                # every generator draw of the call, in diffusers' order (initial latents were drawn above)
+                if noise_tape is not None:
+                    st.tape.copy_(noise_tape)
+                else:
+                    for i, t in enumerate(timesteps):
+                        if t > 0:
+                            st.tape[1 + i].copy_(randn_tensor((n, 4, h, w), generator=generator, device=dev, dtype=draw_dtype))
+                        else:
+                            st.tape[1 + i].zero_()
+                if st.loop_graph is None:
+                    saved = st.latents.clone()
+
+                    def all_steps():
+                        for i in range(steps):
+                            self._step_eager(st, st.temb_all[i], st.tape[1 + i], st.coef_all[i])
+                    st.loop_graph, _, st.launches_loop = self._capture(all_steps)
+                    st.loop_key = lkey
+                    st.latents.copy_(saved)
+                if self.loop_events is not None:
+                    ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                    ev[0].record()
+                st.loop_graph.replay()
+                if self.loop_events is not None:
+                    ev[1].record()
+                    self.loop_events.append((ev[0], ev[1], steps))
+            for i in (() if use_loop else self.progress_bar(range(steps))):
                 t = timesteps[i]
                 st.temb.copy_(temb_table[i].expand_as(st.temb))
                 st.coef.copy_(self.scheduler.coef_row(i, t, dev))
@@ -415,7 +460,9 @@ class StableDiffusionPipeline:
                     raise ValueError(f"unknown output_type {output_type!r}")
         if graphs:
             global graph_launches
-            graph_launches += st.launches_ctx + len(timesteps) * st.launches_per_step + (0 if output_type == "latent" else st.launches_vae)
+            graph_launches += st.launches_ctx + (st.launches_loop if use_loop else steps * st.launches_per_step) + \
+                (0 if output_type == "latent" else st.launches_vae)
+            self._last_loop = use_loop
         if not return_dict:
             return (images, None)
         out = StableDiffusionPipelineOutput(images)
@@ -428,7 +475,8 @@ class StableDiffusionPipeline:
         st = self._last_state
         if st is None:
             return 0
-        return st.launches_ctx + num_inference_steps * st.launches_per_step + (st.launches_vae if decode else 0)
+        body = st.launches_loop if getattr(self, "_last_loop", False) else num_inference_steps * st.launches_per_step
+        return st.launches_ctx + body + (st.launches_vae if decode else 0)
 
 
 class AutoPipelineForText2Image:

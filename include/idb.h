@@ -45,6 +45,8 @@ int idb_last_error(char* buf, size_t n);
 /* 0 if the current device is sm_100 (B200), IDB_E_ARCH otherwise. */
 int idb_device_check(void);
 int idb_num_sms(void);
+/* Kernels this library has launched (or captured into a CUDA graph) so far in this process: monotonic, exact. */
+uint64_t idb_launch_count(void);
 /* sizeof of the argument structs below as THIS build sees them (0 = idb_gemm_conv_args, 1 = idb_attention_args,
  * 2 = idb_groupnorm_args, 3 = idb_time_embed_args, 4 = idb_attention_bwd_args, 5 = idb_groupnorm_bwd_args): a binding
  * checks its own layout against it at load time. */

@@ -277,12 +277,12 @@ def test_two_live_pipelines_keep_their_own_adapters_and_graphs_survive_swaps(wor
     assert torch.equal(a1, a2) and torch.equal(b1, b2)
     assert rel(a1, b1) > 1e-3, "the adapters must change the result"
     st = tuned._last_state
-    graph = st.graph
+    graph = st.loop_graph          # all denoising steps of a call are one graph launch
     assert graph is not None
     lora2 = random_lora(seed=2)
     tuned.load_lora_weights(lora2)
     c = tuned(**kw).images
-    assert tuned._last_state is st and st.graph is graph, "adapter hot-swap re-captured the step graph"
+    assert tuned._last_state is st and st.loop_graph is graph, "adapter hot-swap re-captured the denoising graph"
     eager = _pipe(w)
     eager.use_cuda_graph = False
     eager.load_lora_weights(lora2)
@@ -290,6 +290,29 @@ def test_two_live_pipelines_keep_their_own_adapters_and_graphs_survive_swaps(wor
     assert torch.equal(c, c_ref), "graph replay after an in-place adapter swap differs from the eager run"
     assert rel(c, a1) > 1e-3
     w["unet"].set_lora(w["lora"])     # leave the module's UNet as the other tests expect it
+
+
+def test_whole_loop_graph_equals_per_step_graphs_and_eager_with_a_generator(world):
+    """The default call replays ONE graph holding every denoising step; the generator draws (initial latents, then one
+    per step with t > 0, `DDPMScheduler.step`) are made up front in the same order.  Same seed -> same bits as one graph
+    launch per step and as the un-graphed run; a second call with a fresh seed reuses the graph."""
+    w, dev = world, world["dev"]
+    g = torch.Generator().manual_seed(5)
+    kw = dict(prompt_embeds=torch.randn(2, 77, 1024, generator=g).to(dev),
+              negative_prompt_embeds=torch.randn(2, 77, 1024, generator=g).to(dev), num_inference_steps=4,
+              guidance_scale=5.0, output_type="latent")
+    outs = {}
+    for mode in ("loop", "step", "eager"):
+        p = _pipe(w)
+        p.use_loop_graph = mode == "loop"
+        p.use_cuda_graph = mode != "eager"
+        outs[mode] = [p(generator=torch.Generator(device=dev).manual_seed(s), **kw).images for s in (3, 4, 3)]
+        if mode == "loop":
+            assert p._last_state.loop_graph is not None and p.launches_per_call(4, decode=False) > 4 * 300
+    for mode in ("step", "eager"):
+        for a, b in zip(outs["loop"], outs[mode]):
+            assert torch.equal(a, b), mode
+    assert torch.equal(outs["loop"][0], outs["loop"][2]) and not torch.equal(outs["loop"][0], outs["loop"][1])
 
 
 def test_missing_weights_raise_unless_random_init_is_asked_for(cuda_dev, monkeypatch):

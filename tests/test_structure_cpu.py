@@ -446,7 +446,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     from faceposegenerator_b200.csrc import build
     lib_path = build.build()
     header = open(os.path.join(ROOT, "include", "idb.h")).read()
-    declared = set(re.findall(r"^\s*(?:int|size_t)\s+(idb_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^\s*(?:int|size_t|uint64_t)\s+(idb_\w+)\s*\(", header, flags=re.M))
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     lib = ctypes.CDLL(lib_path)
     for name in declared:
