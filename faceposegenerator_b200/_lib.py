@@ -117,6 +117,8 @@ EXPORTS = {
     "idb_device_check": (c_int32, []),
     "idb_num_sms": (c_int32, []),
     "idb_launch_count": (C.c_uint64, []),
+    "idb_stream_k_launch_count": (C.c_uint64, []),
+    "idb_stream_k_mode": (c_int32, []),
     "idb_gemm_conv": (c_int32, [C.POINTER(GemmConvArgs), c_void_p]),
     "idb_gemm_conv_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
     "idb_sizeof_args": (c_size_t, [c_int32]),

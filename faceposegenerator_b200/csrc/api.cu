@@ -70,6 +70,8 @@ static EncodeTiledFn encode_fn() {
 
 static std::atomic<unsigned long long> g_launches{0};
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+static std::atomic<unsigned long long> g_sk_launches{0};
+void note_stream_k_launch() { g_sk_launches.fetch_add(1, std::memory_order_relaxed); }
 
 bool pdl_enabled() {
   static const bool on = !(getenv("IDB_PDL") && atoi(getenv("IDB_PDL")) == 0);
@@ -184,6 +186,7 @@ extern "C" size_t idb_sizeof_args(int32_t which) {
 }
 
 extern "C" uint64_t idb_launch_count(void) { return idb::g_launches.load(std::memory_order_relaxed); }
+extern "C" uint64_t idb_stream_k_launch_count(void) { return idb::g_sk_launches.load(std::memory_order_relaxed); }
 
 extern "C" int idb_device_check(void) { return idb::require_sm100(); }
 extern "C" int idb_num_sms(void) { return idb::num_sms(); }

@@ -18,6 +18,7 @@
 // TMA-loads its own 128 A rows and HALF of the B tile; the leader issues tcgen05.mma.cta_group::2
 // which reads both CTAs' smem and writes rows 0-127 / 128-255 of D into the two CTAs' TMEM.  Operand
 // bytes per MAC drop by (128 + N/2) / (128 + N): the big convs are L2->SM bandwidth bound otherwise.
+#include <atomic>
 #include <cstdlib>
 #include <string>
 
@@ -97,10 +98,90 @@ struct GemmParams {
   FastDiv fd_gran;             // channels per granule
   int n_gran;                  // N_out / gran
   long long n_rowblocks;       // row blocks of this call (M / 32)
+  // stream-K instantiations only (see WorkIter): groups = images, CTA pairs per group, tiles per group; partial tiles
+  // travel through `workspace`, arrival counters live in g_sk_flags
+  int sk_groups, sk_units, sk_tiles;
 };
 
 constexpr float ISUM_SCALE_S = 4294967296.0f;    // 2^32: |sum of an (image, channel)| < 2^31
 constexpr float ISUM_SCALE_SS = 16777216.0f;     // 2^24: sum of squares < 2^39 (rms 11,000 over 4096 pixels)
+
+// ---------------------------------------------------------------------------------------- stream-K schedule
+// The one-wave layers (16x16 latents at the bench batch: 64 single-N tiles on 74 CTA pairs, L2-feed bound) and the
+// quantised last wave of the others leave SMs idle.  SK instantiations run the dual-N tiles of ONE IMAGE (a "group")
+// as a linear space of (tile, k-block) work split evenly over P = pairs / images CTA pairs: a pair's range is
+// [tail of a tile some earlier pair started] [whole tiles] [head of a tile].  The pair that holds a tile's k-block 0
+// owns its epilogue; the pairs that hold later k-blocks ("contributors") write their raw fp32 accumulators to the
+// workspace FIRST THING in their range and bump the tile's arrival counter; the owner finishes its head segment last,
+// waits for the counter (all CTAs of the grid are co-resident: grid <= SM count, 1 CTA / SM), adds the partials in
+// slot order and runs the normal epilogue.  Every image has the same schedule, so a result does not depend on where the
+// image sits in the batch, and the summation order is fixed: deterministic, position independent.
+constexpr int SK_MINSEG = 8;          // no segment shorter than this many k-blocks (boundaries snap to the tile edge)
+constexpr int SK_MAX_TILES = 4096;
+__device__ unsigned int g_sk_flags[SK_MAX_TILES * 4];   // per (tile, CTA rank): [arrived contributor warps, owner warps done]; zero between launches
+
+__device__ __forceinline__ int sk_bound(int s, int W, int P, int nkb) {
+  int x = static_cast<int>(static_cast<long long>(s) * W / P);
+  const int rem = x % nkb;
+  if (rem != 0) {
+    if (rem < SK_MINSEG) x -= rem;
+    else if (nkb - rem < SK_MINSEG) x += nkb - rem;
+  }
+  return x;
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* ptr) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
+
+// Work items of one CTA (pair): (tile, k-block range).  !SK: tile = unit, unit + num_units, ... with the split-K slice
+// encoded in the tile index (decode_tile); SK: the per-image stream-K range described above.
+template <bool SK>
+struct WorkIter {
+  int tile, kb_begin, kb_end;
+  int n_contrib;   // SK owner of a split tile: contributors to wait for (they are the next n_contrib units)
+  int num_units, total_tiles;
+  int pos, hi, tile0, nkb, slot, W, P;
+  __device__ __forceinline__ void load(const GemmParams& p) {
+    if (SK) {
+      const int t = pos / nkb;
+      kb_begin = pos - t * nkb;
+      kb_end = min(nkb, kb_begin + (hi - pos));
+      tile = tile0 + t;
+      n_contrib = 0;
+      if (kb_begin == 0 && kb_end < nkb) {
+        const int tile_end = (t + 1) * nkb;
+        for (int s2 = slot + 1; s2 < P && sk_bound(s2, W, P, nkb) < tile_end; ++s2) ++n_contrib;
+      }
+    }
+  }
+  __device__ __forceinline__ void init(const GemmParams& p, int unit, int nunits, int ntiles, int nkb_total) {
+    num_units = nunits, total_tiles = ntiles, nkb = nkb_total;
+    tile = unit, kb_begin = 0, kb_end = nkb_total, n_contrib = 0;
+    pos = hi = 0;
+    if (SK) {
+      P = p.sk_units;
+      const int g = unit / P;
+      slot = unit - g * P;
+      W = p.sk_tiles * nkb;
+      tile0 = g * p.sk_tiles;
+      if (g < p.sk_groups) pos = sk_bound(slot, W, P, nkb), hi = sk_bound(slot + 1, W, P, nkb);
+      if (pos < hi) load(p);
+    }
+  }
+  __device__ __forceinline__ bool valid() const { return SK ? (pos < hi) : (tile < total_tiles); }
+  __device__ __forceinline__ bool contrib() const { return SK && kb_begin > 0; }
+  __device__ __forceinline__ void next(const GemmParams& p) {
+    if (SK) {
+      pos += kb_end - kb_begin;
+      if (pos < hi) load(p);
+    } else {
+      tile += num_units;
+    }
+  }
+};
 
 template <int CG>
 __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, int rank) {
@@ -123,8 +204,9 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile, 
 // UMMAs per K step.  Operand bytes per MAC drop by a further (128 + N) / (128 + N/2) over the CTA pair, which is what
 // the big-K convolutions are bound by (L2 -> SM operand feed); the three BLOCK_N-column TMEM buffers are used as a ring
 // of which a tile occupies two, so the next tile's mainloop starts once the epilogue has drained the first half.
-template <int BLOCK_N, int STAGES, bool LORA, int CG, int EPI, int NSUB>
+template <int BLOCK_N, int STAGES, bool LORA, int CG, int EPI, int NSUB, bool SK>
 __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  static_assert(!SK || (NSUB == 2 && EPI == 3 && !LORA), "stream-K: dual-N tiles with the fp32 epilogue only");
   constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
   constexpr int TILE_N = BLOCK_N * NSUB;
   constexpr int B_ROWS = UMMA_N / CG;                 // B rows this CTA stages per accumulator (half of them in a pair)
@@ -221,15 +303,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       int stage = 0, pit = 0;
       uint32_t phase = 0;
       const uint32_t smem_base = smem_u32(smem);
-      for (int tile = unit; tile < total_tiles; tile += num_units) {
+      WorkIter<SK> wi;
+      for (wi.init(p, unit, num_units, total_tiles, nkb_total); wi.valid(); wi.next(p)) {
+        const int tile = wi.tile;
         const TileCoord tc_ = decode_tile<CG>(p, tile, rank);
         const int n_blk = tc_.n_blk, ks = tc_.ks;
         const int tx = tc_.tx, ty = tc_.ty, tb = tc_.tb;   // tb >= number of batch tiles for a padding block: TMA zero-fills
         const int x0 = tx * p.BW, y0 = ty * p.BH, b0 = tb * p.BB;
         const int n0 = n_blk * TILE_N + rank * B_ROWS;
         const int lora_row = LORA ? p.fd_seg.div(n_blk * BLOCK_N) * 16 : 0;   // this tile's adapter (16 padded down-projection rows)
-        const int kb_begin = ks * p.kb_per_split;
-        const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
+        const int kb_begin = SK ? wi.kb_begin : ks * p.kb_per_split;
+        const int kb_end = SK ? wi.kb_end : min(nkb_total, kb_begin + p.kb_per_split);
         // running (tap, channel-block) counters instead of a division per k-block
         int tap = (kb_begin > 0 && kb_begin < p.nkb0) ? kb_begin / p.cpb0 : 0;   // (only split-K tiles divide)
         int cbi = (kb_begin < p.nkb0) ? kb_begin - tap * p.cpb0 : 0;
@@ -370,10 +454,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         }
         __syncwarp();
       };
-      for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
+      WorkIter<SK> wi;
+      for (wi.init(p, unit, num_units, total_tiles, nkb_total); wi.valid(); wi.next(p), ++it) {
+        const int tile = wi.tile;
         const int ks = decode_tile<CG>(p, tile, 0).ks;
-        const int kb_begin = ks * p.kb_per_split;
-        const int kb_end = min(nkb_total, kb_begin + p.kb_per_split);
+        const int kb_begin = SK ? wi.kb_begin : ks * p.kb_per_split;
+        const int kb_end = SK ? wi.kb_end : min(nkb_total, kb_begin + p.kb_per_split);
         const uint32_t c0 = IDB_EPI_PROF ? clock() : 0u;
         int buf_b = 0;
         if (NSUB == 2) {   // this tile's two accumulators: ring positions dpos, dpos + 1 (mod 3); each waits for its own drain
@@ -521,10 +607,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         pre_bias[ci] = (ok && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
       }
     };
-    if (unit < total_tiles) prefetch_tables(unit, 0);
+    if (!SK && unit < total_tiles) prefetch_tables(unit, 0);
 
     int it = 0;
-    for (int tile = unit; tile < total_tiles; tile += num_units, ++it) {
+    WorkIter<SK> wi;
+    for (wi.init(p, unit, num_units, total_tiles, nkb_total); wi.valid(); wi.next(p), ++it) {
+      const int tile = wi.tile;
+      const bool contrib = wi.contrib();          // stream-K: this item only adds a K segment to a tile another pair owns
+      const int n_contrib = SK ? wi.n_contrib : 0;
+      const bool res_item = res_tma && !contrib;
+      unsigned int* sk_flag = SK ? &g_sk_flags[(tile * CG + static_cast<int>(rank)) * 2] : nullptr;
+      if (SK) prefetch_tables(tile, it);          // (no look-ahead: the loads retire while the accumulator is still being computed)
       const TileCoord tc_ = decode_tile<CG>(p, tile, rank);
       const int n_blk = tc_.n_blk, ks = tc_.ks, m_blk = tc_.m_blk;
       const int tx = tc_.tx, ty = tc_.ty, tb = tc_.tb;
@@ -537,7 +630,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
       // ---- before the accumulator is ready: residual of the first chunk (TMA), bias and LoRA-up weights of
       // all of this warp's chunks of the tile (lane c fetches column col + c, coalesced; kept in per-warp smem)
-      if (res_tma && chunk0 < NCH && n0 + chunk0 * 32 < p.N && lane == 0) {
+      if (res_item && chunk0 < NCH && n0 + chunk0 * 32 < p.N && lane == 0) {
         tma_store_wait_read();                      // the previous store has finished reading the staging buffer
         mbar_expect_tx_a(rbar, EPI_BUF_BYTES);
         tma_load_4d_a(sbuf, &p.tmRes, rbar, n0 + chunk0 * 32, cx, cy, cb);
@@ -550,7 +643,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         if (p.bias != nullptr) bsm[ci * 32 + lane] = pre_bias[ci];
       }
       __syncwarp();
-      if (tile + num_units < total_tiles) prefetch_tables(tile + num_units, it + 1);
+      if (!SK && tile + num_units < total_tiles) prefetch_tables(tile + num_units, it + 1);
       IDB_TICK(0);   // tile prologue (bias / LoRA prefetch, residual request)
       int buf_b = 0;
       uint32_t full_phase = bphase;
@@ -609,13 +702,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       tc_fence_after();
       IDB_TICK(1);   // waiting for the accumulator
       bool released_a = false;
+      if (SK && n_contrib > 0) {   // the other K segments of this tile: every epilogue warp of every contributor has stored and fenced
+        if (lane == 0) {
+          const unsigned int need = static_cast<unsigned int>(n_contrib) * NUM_EPI_WARPS;
+          while (ld_acquire_gpu(sk_flag) < need) __nanosleep(64);
+        }
+        __syncwarp();
+      }
 
       int ci = 0;
       for (int chunk = chunk0; chunk < NCH; chunk += 4, ++ci) {
         const int col = n0 + chunk * 32;
         uint32_t v[32];
         if ((dbg & 15) == 5) continue;   // profiling: no TMEM read, no stores
-        if (res_tma && ci > 0 && col < p.N && lane == 0) {   // (the first chunk's residual was requested above)
+        if (res_item && ci > 0 && col < p.N && lane == 0) {   // (the first chunk's residual was requested above)
           tma_store_wait_read();
           mbar_expect_tx_a(rbar, EPI_BUF_BYTES);
           tma_load_4d_a(sbuf, &p.tmRes, rbar, col, cx, cy, cb);
@@ -638,6 +738,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
 
+        if (SK && contrib) {   // raw fp32 segment sums -> this unit's slot of the workspace, [chunk][lane quarter][column][lane]:
+          // one coalesced 128-byte line per accumulator column
+          float* dst = p.workspace + (((static_cast<long long>(unit) * CG + rank) * NCH + chunk) * 4 + quarter) * 1024 + lane;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) __stcg(dst + j * 32, acc[j]);
+          continue;
+        }
+        if (SK && n_contrib > 0) {   // add the contributors' segments in slot order (fixed summation order)
+          for (int jc = 0; jc < n_contrib; ++jc) {
+            const float* src = p.workspace + (((static_cast<long long>(unit + 1 + jc) * CG + rank) * NCH + chunk) * 4 + quarter) * 1024 + lane;
+            float pv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pv[j] = __ldcg(src + j * 32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] += pv[j];
+          }
+        }
         if (ksplit) {  // raw partial sums (tiny-M layers only); the finalize kernel applies the epilogue
           if (row_ok) {
             float4* dst = reinterpret_cast<float4*>(p.workspace + (static_cast<long long>(ks) * p.M + orow) * p.N + col);
@@ -686,7 +803,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           nc = 16, ocol = col >> 1;
         }
         IDB_TICK(3);   // bias / rowvec / LoRA / GEGLU math
-        if (res_tma) {
+        if (res_item) {
           // this chunk's residual has landed in the staging buffer: add it in place (each lane touches only its row)
           mbar_wait(reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + RES_BAR_OFFSET) + warp, g & 1);
           ++g;
@@ -799,6 +916,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           }
         }
         IDB_TICK(7);   // store issue
+      }
+      if (SK && contrib) {   // publish this warp's share of the segment: stores -> fence -> one arrival per warp
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(sk_flag, 1u);
+      } else if (SK && n_contrib > 0) {   // the last owner warp through re-arms the tile's counters for the next launch
+        __syncwarp();
+        if (lane == 0 && atomicAdd(sk_flag + 1, 1u) == NUM_EPI_WARPS - 1) sk_flag[0] = 0u, sk_flag[1] = 0u;
       }
       // this warp is done reading the accumulator buffer(s)
       tc_fence_before();
@@ -999,13 +1124,16 @@ static int pow2_divisor(int v, int cap) {
   return d;
 }
 
-template <int BLOCK_N, int STAGES, bool LORA, int CG, int EPI, int NSUB = 1>
+// stream-K launches: 0 = cooperative + programmatic dependent launch, 1 = cooperative only, 2 = unavailable on this driver
+static std::atomic<int> g_sk_launch_mode{0};
+
+template <int BLOCK_N, int STAGES, bool LORA, int CG, int EPI, int NSUB = 1, bool SK = false>
 static int launch_gemm_e(const GemmParams& p, int grid, cudaStream_t stream) {
   constexpr int UMMA_N = BLOCK_N + (LORA ? 16 : 0);
   constexpr int smem_bytes = STAGES * (A_TILE_BYTES + NSUB * (UMMA_N / CG) * BLOCK_K * 2) + 1024 + 1024 + EPI_STAGING_BYTES +
                              epi_bias_bytes(BLOCK_N * NSUB) + (LORA ? 1024 + A_TILE_BYTES + 2 * (BLOCK_N / CG) * BLOCK_K * 2 : 0);   // ring + slack + barriers + staging + bias (+ LoRA T / U tiles)
   static_assert(smem_bytes <= 227 * 1024, "shared memory budget");
-  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, LORA, CG, EPI, NSUB>;
+  auto kern = gemm_tc_kernel<BLOCK_N, STAGES, LORA, CG, EPI, NSUB, SK>;
   static PerDeviceOnce configured;  // per instantiation (and per device inside)
   {
     cudaError_t e = ensure_dynamic_smem(kern, smem_bytes, configured);
@@ -1017,19 +1145,41 @@ static int launch_gemm_e(const GemmParams& p, int grid, cudaStream_t stream) {
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  note_launch();
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
-  if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("gemm_tc launch: ") + cudaGetErrorString(e));
-  return IDB_OK;
+  if (!SK) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    note_launch();
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("gemm_tc launch: ") + cudaGetErrorString(e));
+    return IDB_OK;
+  }
+  // stream-K: CTAs wait for each other inside the launch, so the WHOLE grid must be resident at once.  A cooperative
+  // launch makes the driver guarantee that (also against kernels of other streams); the combination with programmatic
+  // dependent launch is tried first and dropped for the process if this driver refuses it.
+  attr[1].id = cudaLaunchAttributeCooperative;
+  attr[1].val.cooperative = 1;
+  attr[2].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[2].val.programmaticStreamSerializationAllowed = 1;
+  for (;;) {
+    const int mode = g_sk_launch_mode.load(std::memory_order_relaxed);
+    if (mode >= 2) return IDB_E_UNSUPPORTED;   // (the caller re-plans without stream-K)
+    cfg.numAttrs = (mode == 0 && pdl_enabled()) ? 3 : 2;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e == cudaSuccess) {
+      note_launch();
+      return IDB_OK;
+    }
+    cudaGetLastError();   // clear the sticky launch-configuration error and try the next mode
+    int expect = mode;
+    g_sk_launch_mode.compare_exchange_strong(expect, (mode == 0 && !pdl_enabled()) ? 2 : mode + 1);
+  }
 }
 
 // epi: 0 generic, 1 / 2 / 3 specialised (see gemm_tc_kernel); only the CTA-pair kernels the UNet spends its time in are
@@ -1052,6 +1202,8 @@ static int env_int(const char* name, int dflt) {
 }  // namespace idb
 
 using namespace idb;
+
+extern "C" int idb_stream_k_mode(void) { return g_sk_launch_mode.load(std::memory_order_relaxed); }
 
 extern "C" size_t idb_gemm_conv_workspace_bytes(int64_t m, int64_t n, int32_t k_splits) {
   return k_splits > 1 ? static_cast<size_t>(m) * n * k_splits * sizeof(float) : 0;
@@ -1180,10 +1332,42 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
       if (force_dual == 1 || (p.nkb0 + p.nkb1 >= dual_min_kb && cost < cost1) || splitk_regime || dual_split) dual = true, block_n = 160;
     }
   }
+  // stream-K over the dual-N tiles of each image (see WorkIter).  IDB_GEMM_SK: 0 = off, 1 = the layers whose dual-N grid
+  // leaves at least half of the machine idle (16x16 latents at the bench batch; default), 2 = every eligible layer.
+  const int nkb = p.nkb0 + p.nkb1;
+  bool sk = false;
+  p.sk_groups = p.sk_units = p.sk_tiles = 0;
+  {
+    static const int sk_mode = env_int("IDB_GEMM_SK", 1);
+    static const int sk_min_kb = env_int("IDB_GEMM_SK_MINKB", 32);   // shortest K range (k-blocks) worth a pair
+    static const int dbg0 = env_int("IDB_GEMM_DEBUG", 0);
+    static const int no_spec0 = env_int("IDB_GEMM_NOSPEC", 0);
+    const int blocks_per_img = p.tiles_x * p.tiles_y;   // 128-row blocks of one image
+    const bool shape_ok = !lora && cg == 2 && !geglu && !phased && !(a->flags & (IDB_EPI_GELU | IDB_EPI_F16)) && a->n % 320 == 0 &&
+                          a->k_splits == 0 && a->workspace && a->out_f32 && !a->out_bf16 && dbg0 == 0 && !no_spec0 && max_sms == 0 &&
+                          p.BB == 1 && blocks_per_img % 2 == 0 && units == num_sms() / 2;
+    if (sk_mode > 0 && shape_ok && p.Ho > 1 && g_sk_launch_mode.load(std::memory_order_relaxed) < 2) {   // (rasters only: a group is an image)
+      const int groups = B;                                               // one group per image
+      const int tiles_per_group = (blocks_per_img / 2) * (a->n / 320);
+      const long long tiles_dual = static_cast<long long>(groups) * tiles_per_group;
+      int P = groups <= units ? units / groups : 0;
+      static const int force_p = env_int("IDB_GEMM_SK_P", 0);   // profiling only
+      if (force_p > 0 && force_p < P) P = force_p;
+      const long long W = static_cast<long long>(tiles_per_group) * nkb;
+      if (P > W / sk_min_kb) P = static_cast<int>(W / sk_min_kb);
+      const size_t need = static_cast<size_t>(units) * 2 * 128 * 320 * sizeof(float);
+      const bool fills = P >= 1 && static_cast<long long>(groups) * P * 10 >= static_cast<long long>(units) * 9;   // >= 90 % of the pairs busy
+      const bool regime = sk_mode >= 2 || tiles_dual * 2 <= units;
+      if (fills && regime && P > 1 && tiles_dual <= SK_MAX_TILES && W < (1ll << 30) && need <= a->workspace_bytes && nkb >= 2 * SK_MINSEG) {
+        sk = true, dual = true, block_n = 160;
+        p.sk_groups = groups, p.sk_units = P, p.sk_tiles = tiles_per_group;
+      }
+    }
+  }
   p.n_tiles_n = (a->n + block_n * (dual ? 2 : 1) - 1) / (block_n * (dual ? 2 : 1));
 
-  const int nkb = p.nkb0 + p.nkb1;
   int ksp = a->k_splits;
+  if (sk) ksp = 1;
   if (ksp == 0) {  // auto: split K when the tile grid leaves most SMs idle
     ksp = 1;
     const long long tiles = static_cast<long long>(m_units) * p.n_tiles_n;
@@ -1323,7 +1507,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   GemmParams pk = p;
   if (p.k_splits > 1) pk.stats = nullptr, pk.isums = nullptr;   // statistics come from the finalize pass
   const int total_tiles = m_units * p.n_tiles_n * p.k_splits;
-  const int grid = cg * (total_tiles < units ? total_tiles : units);
+  const int grid = sk ? cg * units : cg * (total_tiles < units ? total_tiles : units);
   // epilogue specialisation (generic whenever a profiling switch, split-K or both outputs are in play)
   int epi = 0;
   static const int no_spec = env_int("IDB_GEMM_NOSPEC", 0);
@@ -1338,6 +1522,12 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   else if (cg == 1 && block_n == 256) rc = launch_gemm<256, 3, false, 1>(pk, grid, stream, epi);
   else if (cg == 1 && block_n == 160) rc = launch_gemm<160, 4, false, 1>(pk, grid, stream, epi);
   else if (cg == 1) rc = launch_gemm<128, 4, false, 1>(pk, grid, stream, epi);
+  else if (sk && epi == 3) {
+    rc = launch_gemm_e<160, 4, false, 2, 3, 2, true>(pk, grid, stream);
+    if (rc == IDB_E_UNSUPPORTED) return idb_gemm_conv(a, stream_);   // cooperative launch refused: plan again without stream-K
+    if (rc == IDB_OK) note_stream_k_launch();
+  }
+  else if (sk) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: internal: stream-K schedule chosen for a non-fp32 epilogue");
   else if (dual && epi == 1) rc = launch_gemm_e<160, 4, false, 2, 1, 2>(pk, grid, stream);
   else if (dual && epi == 3) rc = launch_gemm_e<160, 4, false, 2, 3, 2>(pk, grid, stream);
   else if (dual) rc = launch_gemm_e<160, 4, false, 2, 0, 2>(pk, grid, stream);

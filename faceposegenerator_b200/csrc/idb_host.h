@@ -44,6 +44,7 @@ inline cudaError_t ensure_dynamic_smem(K kern, int bytes, PerDeviceOnce& once) {
 // every kernel launch of the library goes through one of two sites (launch_pdl below, launch_gemm_e in gemm_tc.cu); both
 // count it, so a caller can report exactly how many kernels its calls enqueued (idb_launch_count())
 void note_launch();
+void note_stream_k_launch();   // idb_gemm_conv calls that took the stream-K schedule (idb_stream_k_launch_count())
 
 // kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-dependent-launch attribute (IDB_PDL=0 disables)
 bool pdl_enabled();

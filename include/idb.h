@@ -47,6 +47,11 @@ int idb_device_check(void);
 int idb_num_sms(void);
 /* Kernels this library has launched (or captured into a CUDA graph) so far in this process: monotonic, exact. */
 uint64_t idb_launch_count(void);
+/* idb_gemm_conv calls so far that ran the stream-K schedule (a diagnostic for tests and benchmarks). */
+uint64_t idb_stream_k_launch_count(void);
+/* How stream-K kernels are launched in this process: 0 = cooperative + programmatic dependent launch, 1 = cooperative
+ * only (the driver refused the combination), 2 = cooperative launch unavailable, stream-K disabled. */
+int idb_stream_k_mode(void);
 /* sizeof of the argument structs below as THIS build sees them (0 = idb_gemm_conv_args, 1 = idb_attention_args,
  * 2 = idb_groupnorm_args, 3 = idb_time_embed_args, 4 = idb_attention_bwd_args, 5 = idb_groupnorm_bwd_args): a binding
  * checks its own layout against it at load time. */

@@ -2,6 +2,7 @@
 operands, fp32 math, TF32 off).  Tolerances: fp32 outputs rel-L2 <= 2e-5 (accumulation
 order only), bf16 outputs <= 4e-3 (one bf16 rounding)."""
 import math
+import os
 
 import pytest
 import torch
@@ -161,6 +162,50 @@ def test_conv3x3(ops, cuda_dev, B, H, W, Cin, Cout):
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1) + rowvec[:, :, None, None]
     ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout)
     assert rel(o32, ref) < 2e-5, rel(o32, ref)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,C1,sk", [(8, 16, 16, 1280, 1280, 0, 1), (8, 16, 16, 1280, 1280, 640, 1), (4, 16, 16, 1280, 1280, 0, 1),
+                                                  (8, 16, 16, 128, 640, 0, 0),    # K too short to share: plain tiles
+                                                  (6, 16, 16, 2560, 1280, 0, 1), (2, 16, 16, 1280, 1280, 0, 0)])
+def test_conv3x3_stream_k(ops, cuda_dev, B, H, W, Cin, Cout, C1, sk):
+    """One-wave conv layers (16x16 latents) take the per-image stream-K schedule: dual-N tiles whose K range is shared by
+    several CTA pairs, partial tiles summed by the owning pair in a fixed order.  Against fp32 conv2d (+ 1x1 shortcut
+    segment, bias, time-embedding row vector, residual, per-image sums); bit-reproducible across calls (the arrival
+    counters re-arm themselves) and independent of where an image sits in the batch."""
+    from faceposegenerator_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(B * H + Cin + C1)
+    x = rb(torch.randn(B, H, W, Cin, device=cuda_dev, generator=g))
+    w = rb(torch.randn(Cout, Cin, 3, 3, device=cuda_dev, generator=g) / math.sqrt(9 * Cin))
+    x1 = rb(torch.randn(B, H, W, C1, device=cuda_dev, generator=g)) if C1 else None
+    w1 = rb(torch.randn(Cout, C1, device=cuda_dev, generator=g) / math.sqrt(C1)) if C1 else None
+    wk = torch.cat([pack_conv_w(w), w1], 1).contiguous() if C1 else pack_conv_w(w)
+    bias = torch.randn(Cout, device=cuda_dev, generator=g)
+    rowvec = torch.randn(B, Cout, device=cuda_dev, generator=g)
+    res = torch.randn(B * H * W, Cout, device=cuda_dev, generator=g)
+    ws = torch.empty(24 << 20, dtype=torch.float32, device=cuda_dev)
+
+    def run(xa, x1a, rv, rs):
+        return ops.gemm_conv(xa, wk, mode=ops.A_3X3, a1=x1a, bias=bias, rowvec=rv, residual=rs, want_f32=True, want_stats=True,
+                             k_splits=0, workspace=ws, stats_gran=10)
+    n0 = _lib.load().idb_stream_k_launch_count()
+    o, _, sm = run(x, x1, rowvec, res)
+    took_sk = _lib.load().idb_stream_k_launch_count() - n0
+    if os.environ.get("IDB_GEMM_SK", "1") == "1":
+        assert took_sk == sk, "schedule selection changed: update the test's expectation"
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), bias, padding=1)
+    if C1:
+        ref = ref + F.conv2d(x1.float().permute(0, 3, 1, 2), w1.float()[:, :, None, None])
+    ref = (ref + rowvec[:, :, None, None]).permute(0, 2, 3, 1).reshape(B * H * W, Cout) + res
+    assert rel(o, ref) < 2e-5, rel(o, ref)
+    flat = o.view(B, H * W, Cout // 10, 10).double().permute(0, 1, 3, 2).reshape(B, H * W * 10, Cout // 10)
+    assert rel(fixed_sums(sm)[0], flat.sum(1)) < 1e-6
+    for _ in range(3):
+        o2, _, sm2 = run(x, x1, rowvec, res)
+        assert torch.equal(o2, o) and torch.equal(sm2, sm)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(1)).to(cuda_dev)
+    op, _, smp = run(x[perm].contiguous(), x1[perm].contiguous() if C1 else None, rowvec[perm].contiguous(),
+                     res.view(B, H * W, Cout)[perm].reshape(B * H * W, Cout).contiguous())
+    assert torch.equal(op.view(B, H * W, Cout), o.view(B, H * W, Cout)[perm]) and torch.equal(smp, sm[perm])
 
 
 @pytest.mark.parametrize("B,H,W,C", [(2, 64, 64, 320), (2, 16, 16, 1280), (1, 8, 8, 64)])
