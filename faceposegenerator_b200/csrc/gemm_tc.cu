@@ -101,6 +101,7 @@ struct GemmParams {
   // stream-K instantiations only (see WorkIter): groups = images, CTA pairs per group, tiles per group; partial tiles
   // travel through `workspace`, arrival counters live in g_sk_flags
   int sk_groups, sk_units, sk_tiles;
+  int ws_tma;   // split-K partials leave through the staged TMA-store path (tmOutF spans the workspace, batch = k_splits x B)
 };
 
 constexpr float ISUM_SCALE_S = 4294967296.0f;    // 2^32: |sum of an (image, channel)| < 2^31
@@ -754,6 +755,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; ++j) acc[j] += pv[j];
           }
+        }
+        if (ksplit && p.ws_tma) {   // raw partial sums -> staging buffer -> one TMA store into slice `ks` of the workspace
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+          const uint32_t row = sbuf + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + ((j ^ sw) << 4)), "f"(acc[4 * j]),
+                         "f"(acc[4 * j + 1]), "f"(acc[4 * j + 2]), "f"(acc[4 * j + 3])
+                         : "memory");
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (cb < p.B) tma_store_4d(&p.tmOutF, sbuf, col, cx, cy, ks * p.B + cb);   // (a box past the batch would land in the next slice)
+            tma_store_commit();
+          }
+          continue;
         }
         if (ksplit) {  // raw partial sums (tiny-M layers only); the finalize kernel applies the epilogue
           if (row_ok) {
@@ -1491,7 +1509,15 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     const uint64_t sx = phased ? 2 : 1;
     const uint64_t row_elems = sx * uint64_t(p.Wo) * No;                    // elements per output row of the target tensor
     const uint64_t base_off = phased ? (uint64_t(a->out_phase_y) * row_elems + uint64_t(a->out_phase_x) * No) : 0;
-    if (a->out_f32) {
+    static const int ws_tma_on = env_int("IDB_GEMM_WS_TMA", 1);
+    p.ws_tma = 0;
+    if (p.k_splits > 1 && ws_tma_on && !geglu && p.N_out == p.N && B % bb32 == 0) {
+      // split-K partials: slice ks of the workspace is a [B, Ho, Wo, N] fp32 tensor; the slices are stacked on the batch axis
+      uint64_t wdims[4] = {No, uint64_t(p.Wo), uint64_t(p.Ho), uint64_t(B) * uint64_t(p.k_splits)};
+      uint64_t strides[3] = {No * 4, uint64_t(p.Wo) * No * 4, uint64_t(p.Ho) * p.Wo * No * 4};
+      if (int rc = make_tmap(&p.tmOutF, a->workspace, 4, 128, 4, wdims, strides, box)) return rc;
+      p.ws_tma = 1;
+    } else if (a->out_f32) {
       uint64_t strides[3] = {sx * No * 4, sx * row_elems * 4, sx * uint64_t(p.Ho) * row_elems * 4};
       if (int rc = make_tmap(&p.tmOutF, a->out_f32 + base_off, 4, geglu ? 0 : 128, 4, dims, strides, box)) return rc;
     }
