@@ -94,7 +94,7 @@ class GroupNormArgs(C.Structure):
         ("out_norm", c_void_p), ("out_raw", c_void_p),
         ("partials", c_void_p),
         ("x0_stats", c_void_p), ("x1_stats", c_void_p), ("x0_stats_phases", c_int32),
-        ("x0_sums", c_void_p), ("x1_sums", c_void_p), ("sums_gran", c_int32),
+        ("x0_sums", c_void_p), ("x1_sums", c_void_p), ("sums_gran", c_int32), ("x1_batch", c_int32),
     ]
 
 

@@ -47,12 +47,14 @@ struct GnParams {
   const longlong2* sums1;
   double inv_n;   // 1 / (hw * channels per group)
   int gran;       // channels per granule of sums0 / sums1
+  int b1_mod;     // > 0: source 1 (and its sums) holds b1_mod images, image b reads image b % b1_mod (a skip tensor shared by the CFG pair)
 };
 
 __device__ __forceinline__ float4 gn_load(const GnParams& p, int b, int pix, int cq) {
   const int c = cq * 4;
   if (c < p.c0) return *reinterpret_cast<const float4*>(p.x0 + (static_cast<long long>(b) * p.hw + pix) * p.c0 + c);
-  return *reinterpret_cast<const float4*>(p.x1 + (static_cast<long long>(b) * p.hw + pix) * p.c1 + (c - p.c0));
+  const int b1 = p.b1_mod > 0 ? b % p.b1_mod : b;
+  return *reinterpret_cast<const float4*>(p.x1 + (static_cast<long long>(b1) * p.hw + pix) * p.c1 + (c - p.c0));
 }
 
 // Deterministic: per-thread partial sums go to smem and are combined in a fixed order (no float
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(1024) gn_apply_kernel(const GnParams p) {
       for (int i = 0; i < per; ++i) {
         const int q = g0c / p.gran + i;     // granule index in the concatenated channel space
         const longlong2 v = (q < n0) ? __ldg(p.sums0 + static_cast<long long>(b) * n0 + q)
-                                     : __ldg(p.sums1 + static_cast<long long>(b) * n1 + (q - n0));
+                                     : __ldg(p.sums1 + static_cast<long long>(p.b1_mod > 0 ? b % p.b1_mod : b) * n1 + (q - n0));
         s += v.x;
         ss += v.y;
       }
@@ -782,6 +784,12 @@ extern "C" int idb_groupnorm(const idb_groupnorm_args* a, void* stream_) {
   p.x0 = a->x0, p.x1 = a->x1, p.c0 = a->c0, p.c1 = a->x1 ? a->c1 : 0, p.C = C, p.CQ = C / 4;
   p.PY = p.CQ >= 256 ? 1 : 256 / p.CQ;
   p.hw = a->hw, p.groups = a->groups, p.cpg = C / a->groups, p.eps = a->eps;
+  p.b1_mod = 0;
+  if (a->x1 && a->x1_batch > 0 && a->x1_batch != a->batch) {
+    if (a->batch % a->x1_batch) return fail(IDB_E_BADARG, "idb_groupnorm: x1_batch must divide batch");
+    if (a->x1_stats != nullptr) return fail(IDB_E_UNSUPPORTED, "idb_groupnorm: a shared source 1 (x1_batch) takes per-image sums or no statistics, not row-block sums");
+    p.b1_mod = a->x1_batch;
+  }
   const bool have_stats = a->x0_stats != nullptr && (a->x1 == nullptr || a->x1_stats != nullptr) && a->hw % 32 == 0 &&
                           (a->x0_stats_phases <= 1 || (a->x0_stats_phases == 4 && a->hw % 128 == 0));
   // small rasters: the apply CTAs finalize the statistics themselves (one launch instead of two).  Measured on the UNet

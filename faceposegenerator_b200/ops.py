@@ -363,18 +363,25 @@ def groupnorm(x0, gamma, beta, *, groups: int, eps: float, silu: bool, x1=None, 
     # statistics handed over by the producers: int64 = fixed-point per-image granule sums (one launch), float32 = row-block sums
     grans = []
 
-    def split(st, c):
+    def split(st, c, nb):
         if st is None:
             return None, None
         if st.dtype == torch.int64:
-            if st.dim() != 3 or st.shape[0] != B or st.shape[2] != 2 or c % st.shape[1] or not st.is_contiguous():
+            if st.dim() != 3 or st.shape[0] != nb or st.shape[2] != 2 or c % st.shape[1] or not st.is_contiguous():
                 raise ValueError("per-image granule sums must be contiguous int64 [batch, C / gran, 2]")
             grans.append(c // st.shape[1])
             return st, None
         _chk(st, f32, "stats")
         return None, st
-    x0_sums, x0_rb = split(x0_stats, c0)
-    x1_sums, x1_rb = split(x1_stats, c1)
+    # x1 may hold fewer images than x0 (a skip tensor computed once for both halves of a CFG pair): image b reads b % B1
+    B1 = B if x1 is None else x1.shape[0]
+    if B1 != B:
+        if B % B1 or x1.numel() != B1 * hw * c1:
+            raise ValueError("x1 must hold batch / k images of the same raster")
+        if (x0_stats is not None and x0_stats.dtype != torch.int64) or (x1_stats is not None and x1_stats.dtype != torch.int64):
+            x0_stats = x1_stats = None       # row-block sums cannot be shared between images: own statistics pass
+    x0_sums, x0_rb = split(x0_stats, c0, B)
+    x1_sums, x1_rb = split(x1_stats, c1, B1)
     one_launch = x0_sums is not None and (x1 is None or x1_sums is not None)
     if one_launch and len(set(grans)) != 1:
         raise ValueError("both sources must carry sums of the same channel granule")
@@ -382,7 +389,8 @@ def groupnorm(x0, gamma, beta, *, groups: int, eps: float, silu: bool, x1=None, 
                               gamma=gamma.data_ptr(), beta=beta.data_ptr(), silu=int(silu),
                               out_norm=out_norm.data_ptr(), out_raw=_lib.ptr(out_raw), partials=partials.data_ptr(),
                               x0_stats=_lib.ptr(x0_rb), x1_stats=_lib.ptr(x1_rb), x0_stats_phases=x0_stats_phases,
-                              x0_sums=_lib.ptr(x0_sums), x1_sums=_lib.ptr(x1_sums), sums_gran=grans[0] if grans else 0)
+                              x0_sums=_lib.ptr(x0_sums), x1_sums=_lib.ptr(x1_sums), sums_gran=grans[0] if grans else 0,
+                              x1_batch=0 if B1 == B else B1)
     _lib.call("idb_groupnorm", C.byref(args), _lib.stream_ptr(), launches=1 if one_launch else 2)
     return out_norm, out_raw
 

@@ -121,6 +121,8 @@ class StableDiffusionPipeline:
         # one CUDA graph for ALL denoising steps of a call (the generator draws do not depend on the latents, so the noise
         # tape is drawn up front in the same order); IDB_LOOP_GRAPH=0: one graph launch per step
         self.use_loop_graph = os.environ.get("IDB_LOOP_GRAPH", "1") != "0"
+        # CFG: evaluate the layers that see identical inputs in both halves of the pair once (IDB_CFG_SHARED=0: duplicated batch)
+        self.cfg_shared_prefix = os.environ.get("IDB_CFG_SHARED", "1") != "0"
         self.step_events = None    # set to a list to collect (start, end) CUDA events around every denoise step (per-step graphs)
         self.loop_events = None    # set to a list to collect (start, end, steps) around every whole-loop graph launch
 
@@ -234,12 +236,18 @@ class StableDiffusionPipeline:
         """One denoising step on the state's static buffers (per-step graph), or on the given per-step rows of the
         whole-loop tables (loop graph)."""
         n = st.n
-        if st.do_cfg:
-            st.x2[:n].copy_(st.latents)
-            st.x2[n:].copy_(st.latents)
+        if st.do_cfg and self.cfg_shared_prefix and n >= 2:   # (one image: the half-size kernels cost more than they save)
+            # both halves of the CFG pair carry the same latent: the UNet evaluates the layers in front of the first
+            # cross-attention once (bit-identical to the duplicated batch diffusers feeds, `torch.cat([latents] * 2)`)
+            eps2 = self.unet.forward(st.latents, st.t_dev, context=st.context, temb=st.temb if temb is None else temb,
+                                     return_dict=False, cfg_pair=True)[0]
         else:
-            st.x2.copy_(st.latents)
-        eps2 = self.unet.forward(st.x2, st.t_dev, context=st.context, temb=st.temb if temb is None else temb, return_dict=False)[0]
+            if st.do_cfg:
+                st.x2[:n].copy_(st.latents)
+                st.x2[n:].copy_(st.latents)
+            else:
+                st.x2.copy_(st.latents)
+            eps2 = self.unet.forward(st.x2, st.t_dev, context=st.context, temb=st.temb if temb is None else temb, return_dict=False)[0]
         ops.cfg_ddpm_step(eps2, st.latents, st.noise if noise is None else noise, st.coef if coef is None else coef,
                           guidance_scale=st.guidance_scale, use_cfg=st.do_cfg, v_prediction=st.vpred, x_prev=st.lat_next)
         st.latents.copy_(st.lat_next)
@@ -250,7 +258,8 @@ class StableDiffusionPipeline:
         (`/root/reference/inference_ID-Booth.py:103-107`) on the same cached components, and must not re-capture."""
         dev = self.device
         vpred = self.scheduler.config.prediction_type == "v_prediction"
-        key = (n, h, w, do_cfg, float(guidance_scale), vpred, n_ctx, ctx_dim, self.unet.lora_topology, id(self.vae))
+        key = (n, h, w, do_cfg, float(guidance_scale), vpred, n_ctx, ctx_dim, self.unet.lora_topology, id(self.vae),
+               bool(self.cfg_shared_prefix))
         cache = self.unet.step_cache
         st = cache.get(key) if self.use_cuda_graph else None
         if st is not None:

@@ -306,6 +306,44 @@ class UNet2DConditionModel:
                                     stats_hw=T)
         return out.view(B, H, W, Cc), out_st
 
+    def _transformer_shared_prefix(self, t: _Transformer, hs, kv, n_ctx, gnws):
+        """The FIRST transformer of a classifier-free-guidance forward: both halves of the CFG pair carry the same latent,
+        so everything up to the cross-attention (GroupNorm, proj_in, self-attention, to_out, the cross-attention queries)
+        is computed ONCE on the n shared images; the two text contexts split the stream at the cross-attention, and from
+        there on the batch is 2n.  hs: the n-image stream; kv: projected context of all 2n rows.  Bit-identical to running
+        the block on the duplicated batch (every kernel on the shared part is per-image / per-row)."""
+        h, h_st = hs
+        n, H, W, Cc = h.shape
+        M, T = n * H * W, H * W
+        g, _ = ops.groupnorm(h, t.gn_g, t.gn_b, groups=self.groups, eps=1e-6, silu=False, partials=gnws, x0_stats=h_st)
+        x0, _ = self._gemm(g.view(M, Cc), t.w_in, bias=t.b_in, want_f32=True)
+        a = ops.layernorm(x0, *t.ln[0])
+        _, qkv = self._lin_lora(a, t.w_qkv, t.lora["qkv"], Cc, want_bf16=True)
+        o = ops.attention(qkv, qkv, qkv, batch=n, heads=t.heads, t_q=T, t_kv=T, scale=HEAD_DIM ** -0.5,
+                          col0_q=0, col0_k=Cc, col0_v=2 * Cc)
+        x1, _ = self._lin_lora(o, t.w_o1, t.lora["o1"], Cc, bias=t.b_o1, residual=x0, want_f32=True)
+        a = ops.layernorm(x1, *t.ln[1])
+        _, q = self._lin_lora(a, t.w_q2, t.lora["q2"], Cc, want_bf16=True)
+        # ---- the stream splits here: same queries, two contexts; the residuals x1 / h are read by both halves
+        o2 = torch.empty((2 * M, Cc), dtype=bf16, device=self.device)
+        x2 = torch.empty((2 * M, Cc), dtype=f32, device=self.device)
+        for half in range(2):
+            kvh = kv[half * n * n_ctx:(half + 1) * n * n_ctx]
+            ops.attention(q, kvh, kvh, o2[half * M:(half + 1) * M], batch=n, heads=t.heads, t_q=T, t_kv=n_ctx,
+                          scale=HEAD_DIM ** -0.5, col0_q=0, col0_k=0, col0_v=Cc)
+            self._lin_lora(o2[half * M:(half + 1) * M], t.w_o2, t.lora["o2"], Cc, bias=t.b_o2, residual=x1,
+                           out_f32=x2[half * M:(half + 1) * M])
+        a = ops.layernorm(x2, *t.ln[2])
+        _, gg = self._gemm(a, t.w_ff1, bias=t.b_ff1, geglu=True, want_bf16=True)
+        _, x3 = self._gemm(gg, t.w_ff2, bias=t.b_ff2, residual=x2, want_bf16=True)
+        out = torch.empty((2 * M, Cc), dtype=f32, device=self.device)
+        use_sums = ops.epilogue_stats_supported(1, 1, 2 * M) and ops.image_sums_supported(2 * n, T) and Cc % self.stats_gran == 0
+        out_st = self._sums.take(2 * n, Cc // self.stats_gran) if use_sums else None
+        for half in range(2):
+            self._gemm(x3[half * M:(half + 1) * M], t.w_out, bias=t.b_out, residual=h.view(M, Cc), out_f32=out[half * M:(half + 1) * M],
+                       sums=None if out_st is None else out_st[half * n:(half + 1) * n], stats_hw=T)
+        return out.view(2 * n, H, W, Cc), out_st
+
     # ------------------------------------------------------------------ step-invariant context projections
     def encode_context(self, encoder_hidden_states: torch.Tensor):
         """Cross-attention K/V projections (incl. their LoRA deltas) of the text context: they do
@@ -326,12 +364,21 @@ class UNet2DConditionModel:
 
     # ------------------------------------------------------------------ forward
     def forward(self, sample, timestep, encoder_hidden_states=None, class_labels=None, return_dict: bool = True,
-                context=None, taps: Optional[dict] = None, temb: Optional[torch.Tensor] = None):
+                context=None, taps: Optional[dict] = None, temb: Optional[torch.Tensor] = None, cfg_pair: bool = False):
+        """`cfg_pair=True` (an extension the pipeline uses): `sample` holds the n latents ONCE while the context holds 2n
+        rows ([uncond | cond], `pipeline_stable_diffusion.py` feeds `torch.cat([latents] * 2)`); the result has 2n rows
+        and equals `forward(torch.cat([sample] * 2), ...)` bit for bit -- conv_in, the first ResnetBlock2D and the first
+        transformer up to its cross-attention see identical inputs in both halves and are evaluated once."""
         if class_labels is not None:
             raise NotImplementedError("SD2.1-base has no class embedding")
         in_dtype = sample.dtype
         x = sample.to(device=self.device, dtype=f32).contiguous()
+        n_shared = x.shape[0] if cfg_pair else 0
+        if cfg_pair and not (self.down and self.down[0].attns):
+            raise NotImplementedError("cfg_pair needs a cross-attention block right after conv_in")
         B, Cin, H, W = x.shape
+        if cfg_pair:
+            B = 2 * n_shared            # batch of the result (and of everything after the first cross-attention)
         if H % 8 or W % 8:
             raise ValueError("latent height/width must be multiples of 8 (three stride-2 stages)")
         if not torch.is_tensor(timestep):
@@ -339,6 +386,8 @@ class UNet2DConditionModel:
         t = timestep.to(device=self.device, dtype=f32).reshape(-1)
         if t.numel() == 1:
             t = t.expand(B)
+        elif cfg_pair and t.numel() == n_shared:
+            t = t.repeat(2)
         t = t.contiguous()
         if context is None:
             context = self.encode_context(encoder_hidden_states)
@@ -359,11 +408,16 @@ class UNet2DConditionModel:
 
         h0, _, h0_st = self._gemm(ops.latent_operand(x), self.w_conv_in, mode=ops.A_3X3, bias=self.b_conv_in, want_f32=True,
                                   want_stats=True)
-        h = (h0.view(B, H, W, -1), h0_st)
+        h = (h0.view(x.shape[0], H, W, -1), h0_st)
         tap("conv_in", h)
-        skips = [h]
+        skips = [h]                      # (cfg_pair: this skip holds n images; its consumer reads image b % n)
         for i, blk in enumerate(self.down):
             for j, r in enumerate(blk.resnets):
+                if cfg_pair and i == 0 and j == 0:
+                    h = self._resnet(r, h, None, temb[:n_shared], gnws)     # (both halves share the timestep rows)
+                    h = self._transformer_shared_prefix(blk.attns[0], h, next(kvs), context.n_ctx, gnws)
+                    skips.append(h)
+                    continue
                 h = self._resnet(r, h, None, temb, gnws)
                 tap(f"down_blocks.{i}.resnets.{j}", h)
                 if blk.attns:

@@ -234,6 +234,9 @@ typedef struct {
   const int64_t* x0_sums;
   const int64_t* x1_sums;
   int32_t sums_gran;
+  /* 0 (= batch), or the number of images x1 (and x1_sums) holds when that is fewer than batch: image b then reads image
+   * b % x1_batch of x1 -- a skip tensor computed once for both halves of a classifier-free-guidance pair. */
+  int32_t x1_batch;
 } idb_groupnorm_args;
 int idb_groupnorm(const idb_groupnorm_args* args, void* stream);
 size_t idb_groupnorm_workspace_bytes(int32_t batch, int32_t groups);

@@ -292,6 +292,43 @@ def test_two_live_pipelines_keep_their_own_adapters_and_graphs_survive_swaps(wor
     w["unet"].set_lora(w["lora"])     # leave the module's UNet as the other tests expect it
 
 
+@pytest.mark.parametrize("n,side", [(4, 64), (1, 64), (1, 96), (3, 64)])
+def test_cfg_pair_shared_prefix_is_bit_identical_to_the_duplicated_batch(world, n, side):
+    """diffusers feeds the UNet `torch.cat([latents] * 2)` under classifier-free guidance: conv_in, the first ResnetBlock2D
+    and the first transformer up to its cross-attention then see the same input twice.  `forward(cfg_pair=True)` evaluates
+    them once on the n shared images (the conv_in skip is read by both halves through `x1_batch`); every kernel on that
+    part is per-image / per-row, so at the bench batch the 2n-row result equals the duplicated batch bit for bit."""
+    w, dev = world, world["dev"]
+    unet = w["unet"]
+    g = torch.Generator().manual_seed(100 * n + side)
+    x = torch.randn(n, 4, side, side, generator=g).to(dev)
+    ctx = torch.randn(2 * n, 77, 1024, generator=g).to(dev)
+    t = torch.full((2 * n,), 481.0, device=dev)
+    context = unet.encode_context(ctx)
+    ref = unet.forward(torch.cat([x, x]), t, context=context, return_dict=False)[0]
+    out = unet.forward(x, t, context=context, return_dict=False, cfg_pair=True)[0]
+    assert tuple(out.shape) == (2 * n, 4, side, side)
+    if n == 4:      # the bench batch: n and 2n images run the same tile schedules -> the same bits
+        assert torch.equal(out, ref), float((out - ref).abs().max())
+    else:           # small batches: the n-image kernels split K differently from the 2n-image ones (fp32 summation order,
+        assert rel(out, ref) < 1.2e-2, rel(out, ref)    # amplified by the bf16 operand roundings downstream: the noise floor)
+    assert not torch.equal(out[:n], out[n:]), "the two halves must differ (different contexts)"
+
+
+def test_pipeline_cfg_shared_prefix_equals_duplicated_batch(world):
+    w, dev = world, world["dev"]
+    g = torch.Generator().manual_seed(21)
+    kw = dict(prompt_embeds=torch.randn(2, 77, 1024, generator=g).to(dev),
+              negative_prompt_embeds=torch.randn(2, 77, 1024, generator=g).to(dev), num_inference_steps=3,
+              guidance_scale=5.0, output_type="latent", noise_tape=torch.randn(4, 2, 4, 64, 64, generator=g).to(dev))
+    outs = []
+    for shared in (True, False):
+        p = _pipe(w)
+        p.cfg_shared_prefix = shared
+        outs.append(p(**kw).images)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_whole_loop_graph_equals_per_step_graphs_and_eager_with_a_generator(world):
     """The default call replays ONE graph holding every denoising step; the generator draws (initial latents, then one
     per step with t > 0, `DDPMScheduler.step`) are made up front in the same order.  Same seed -> same bits as one graph

@@ -414,6 +414,34 @@ def test_groupnorm(ops, cuda_dev, B, HW, C0, C1, silu, eps):
     assert (yn.float() - ref.to(torch.bfloat16).float()).abs().max() < 0.07
 
 
+@pytest.mark.parametrize("B,B1,HW,C0,C1,with_sums", [(8, 4, 4096, 320, 320, True), (8, 4, 4096, 320, 320, False), (4, 2, 9216, 320, 320, False),
+                                                    (6, 1, 1024, 640, 320, True)])
+def test_groupnorm_shared_second_source(ops, cuda_dev, B, B1, HW, C0, C1, with_sums):
+    """`x1_batch`: the concatenated second source (a UNet skip tensor) holds B1 < B images and image b reads image b % B1 --
+    against the same call on the materialised repeat, bit for bit (normalised output and the raw bf16 copy), with the
+    producers' per-image sums and with the kernel's own statistics pass."""
+    g = torch.Generator(device="cuda").manual_seed(B + HW)
+    x0 = torch.randn(B, HW, C0, device=cuda_dev, generator=g) * 2 + 0.3
+    x1 = torch.randn(B1, HW, C1, device=cuda_dev, generator=g) - 0.5
+    x1r = x1.repeat(B // B1, 1, 1).contiguous()
+    gamma, beta = torch.randn(C0 + C1, device=cuda_dev, generator=g), torch.randn(C0 + C1, device=cuda_dev, generator=g)
+
+    def sums(t):
+        gran = 10
+        f = t.double().view(t.shape[0], HW, t.shape[2] // gran, gran)
+        return torch.stack([(f.sum((1, 3)) * 2.0 ** 32).round().long(), ((f * f).sum((1, 3)) * 2.0 ** 24).round().long()], -1).contiguous()
+    kw = dict(groups=32, eps=1e-5, silu=True, want_raw=True)
+    if with_sums:
+        a, ar = ops.groupnorm(x0, gamma, beta, x1=x1, x0_stats=sums(x0), x1_stats=sums(x1), **kw)
+        b, br = ops.groupnorm(x0, gamma, beta, x1=x1r, x0_stats=sums(x0), x1_stats=sums(x1r), **kw)
+    else:
+        a, ar = ops.groupnorm(x0, gamma, beta, x1=x1, **kw)
+        b, br = ops.groupnorm(x0, gamma, beta, x1=x1r, **kw)
+    assert torch.equal(a, b) and torch.equal(ar, br)
+    ref = F.silu(F.group_norm(torch.cat([x0, x1r], -1).permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1)
+    assert rel(a, ref) < 4e-3
+
+
 @pytest.mark.parametrize("rows,C", [(8192, 320), (2048, 640), (512, 1280), (77, 1024)])
 def test_layernorm(ops, cuda_dev, rows, C):
     g = torch.Generator(device="cuda").manual_seed(C)
