@@ -374,7 +374,13 @@ def run_native(args):
         e2e_value = total_images / (ms_e2e / 1e3)
         unet_step_ms = sum(unet_ms) / max(len(unet_ms), 1)
         rows = 2 * n
-        achieved = rows * tflop_row / (unet_step_ms / 1e3) if unet_ms else None
+        # CFG pair: the layers in front of the first cross-attention see the same input in both halves and are evaluated
+        # once (`UNet2DConditionModel.forward(cfg_pair=True)`): those FLOPs are not executed, so they are not claimed
+        hw_lat = (side // 8) ** 2
+        shared_tflop = (2 * hw_lat * 320 * 36 + 2 * (2 * hw_lat * 320 * 2880) + 6 * (2 * hw_lat * 320 * 320) + 4 * hw_lat * hw_lat * 320) / 1e12
+        shared_on = bool(getattr(pipe, "cfg_shared_prefix", False)) and n >= 2
+        step_tflop = rows * tflop_row - (n * shared_tflop if shared_on else 0.0)
+        achieved = step_tflop / (unet_step_ms / 1e3) if unet_ms else None
         workload = ("configs[3]: SD2.1 768x768 (96x96 latents, 9216-token self-attention) UNet+VAE random-init + rank-4 LoRA "
                     "(fused, unmerged), 8 prompts x CFG pair = UNet batch 16, 30 DDPM steps, CFG 5.0, per GPU") if big else \
                    ("configs[1]: SD2.1-base UNet+VAE random-init + rank-4 LoRA (fused, unmerged), "
@@ -404,7 +410,10 @@ def run_native(args):
                          "traffic": None if big else _step_traffic(),
                          "kernel": "UNet step (CFG pair forward + fused CFG/DDPM update) inside the denoising graph: gemm_tc_kernel / "
                                    "attention_rs_kernel dominate; see profiles/",
-                         "flops_per_launch": rows * tflop_row * 1e12,
+                         "flops_per_launch": step_tflop * 1e12,
+                         "flops_note": (f"{rows} rows x {tflop_row} TFLOP (SURVEY 8d) minus {n} x {shared_tflop:.4f} TFLOP: conv_in, the first "
+                                        "ResnetBlock2D and the first transformer up to its cross-attention are identical in both halves of "
+                                        "the CFG pair and run once") if shared_on else f"{rows} rows x {tflop_row} TFLOP (SURVEY 8d)",
                          "peak_source": peaks["source"] + ", sustained figure (timed inside a long step)"},
             "clocks": clocks,
         }
