@@ -1144,6 +1144,7 @@ static int pow2_divisor(int v, int cap) {
 
 // stream-K launches: 0 = cooperative + programmatic dependent launch, 1 = cooperative only, 2 = unavailable on this driver
 static std::atomic<int> g_sk_launch_mode{0};
+static int env_int(const char* name, int dflt);
 
 template <int BLOCK_N, int STAGES, bool LORA, int CG, int EPI, int NSUB = 1, bool SK = false>
 static int launch_gemm_e(const GemmParams& p, int grid, cudaStream_t stream) {
@@ -1178,13 +1179,27 @@ static int launch_gemm_e(const GemmParams& p, int grid, cudaStream_t stream) {
     if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("gemm_tc launch: ") + cudaGetErrorString(e));
     return IDB_OK;
   }
-  // stream-K: CTAs wait for each other inside the launch, so the WHOLE grid must be resident at once.  A cooperative
-  // launch makes the driver guarantee that (also against kernels of other streams); the combination with programmatic
-  // dependent launch is tried first and dropped for the process if this driver refuses it.
+  // stream-K: CTAs wait for each other inside the launch, so the WHOLE grid must become resident.  The grid is one CTA per
+  // SM and nothing the resident CTAs wait for depends on another kernel, so on a stream of its own (this pipeline, its VAE
+  // and NCCL's gather kernels included) every CTA gets an SM as soon as the kernels in front retire: a plain launch is
+  // deadlock free and is the default -- it is also the only form Nsight Compute can replay (a cooperative cluster launch
+  // fails under ncu with LaunchFailed).  Two stream-K kernels of DIFFERENT streams (or MPS clients) could each hold part
+  // of the machine and wait forever: such deployments set IDB_GEMM_SK_COOP=1, which makes the launch COOPERATIVE (the
+  // driver then guarantees co-residency; combined with programmatic dependent launch when the driver accepts both), or
+  // IDB_GEMM_SK=0.
   attr[1].id = cudaLaunchAttributeCooperative;
   attr[1].val.cooperative = 1;
   attr[2].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[2].val.programmaticStreamSerializationAllowed = 1;
+  static const int coop = env_int("IDB_GEMM_SK_COOP", 0);
+  if (!coop) {
+    attr[1] = attr[2];
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    note_launch();
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e != cudaSuccess) return fail(IDB_E_CUDA, std::string("gemm_tc (stream-K, plain) launch: ") + cudaGetErrorString(e));
+    return IDB_OK;
+  }
   for (;;) {
     const int mode = g_sk_launch_mode.load(std::memory_order_relaxed);
     if (mode >= 2) return IDB_E_UNSUPPORTED;   // (the caller re-plans without stream-K)
