@@ -18,6 +18,7 @@ A_1X1, A_3X3, A_3X3_S2, A_3X3_S2_ASYM, A_2X2 = 0, 1, 2, 3, 4
 EPI_GEGLU = 1
 EPI_F16 = 2
 EPI_GELU = 4
+EPI_PHASES4 = 8
 
 c_void_p, c_int32, c_int64, c_float, c_size_t = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_size_t
 

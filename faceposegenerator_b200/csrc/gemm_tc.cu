@@ -101,6 +101,10 @@ struct GemmParams {
   // stream-K instantiations only (see WorkIter): groups = images, CTA pairs per group, tiles per group; partial tiles
   // travel through `workspace`, arrival counters live in g_sk_flags
   int sk_groups, sk_units, sk_tiles;
+  // IDB_EPI_PHASES4: tile n_blk belongs to output phase n_blk / tiles_per_phase (weights stacked on N); phases 1-3 store
+  // through their own maps (tmOutF / tmOutB are phase 0's)
+  int phases4, tiles_per_phase;
+  CUtensorMap tmOutP[3];
   int ws_tma;   // split-K partials leave through the staged TMA-store path (tmOutF spans the workspace, batch = k_splits x B)
 };
 
@@ -313,6 +317,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
         const int x0 = tx * p.BW, y0 = ty * p.BH, b0 = tb * p.BB;
         const int n0 = n_blk * TILE_N + rank * B_ROWS;
         const int lora_row = LORA ? p.fd_seg.div(n_blk * BLOCK_N) * 16 : 0;   // this tile's adapter (16 padded down-projection rows)
+        const int ph = (!LORA && p.phases4) ? n_blk / p.tiles_per_phase : 0;    // output parity class of this tile (stacked weights)
+        const int tap_off_x = p.phases4 ? (ph & 1) - 1 : p.tap_off_x, tap_off_y = p.phases4 ? (ph >> 1) - 1 : p.tap_off_y;
         const int kb_begin = SK ? wi.kb_begin : ks * p.kb_per_split;
         const int kb_end = SK ? wi.kb_end : min(nkb_total, kb_begin + p.kb_per_split);
         // running (tap, channel-block) counters instead of a division per k-block
@@ -335,7 +341,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
               if (p.mode0 == IDB_A_3X3) {
                 c0 = cb, c1 = x0 + dx - 1, c2 = y0 + dy - 1, c3 = b0;
               } else if (p.mode0 == IDB_A_2X2) {   // tap = 2 * dy + dx over the low-resolution image
-                c0 = cb, c1 = x0 + (tap & 1) + p.tap_off_x, c2 = y0 + (tap >> 1) + p.tap_off_y, c3 = b0;
+                c0 = cb, c1 = x0 + (tap & 1) + tap_off_x, c2 = y0 + (tap >> 1) + tap_off_y, c3 = b0;
               } else if (p.mode0 == IDB_A_3X3_S2_ASYM) {  // stride 2, padding on the right / bottom only: input (2*yo + dy, 2*xo + dx)
                 const int px = (dx == 1) ? 1 : 0, py = (dy == 1) ? 1 : 0;
                 const int ox = (dx == 2) ? 1 : 0, oy = (dy == 2) ? 1 : 0;
@@ -600,12 +606,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 
     float pre_bias[MAXC];
     auto prefetch_tables = [&](int tl, int itn) {   // lane c fetches column col + c of each chunk (coalesced)
-      const int n0_ = decode_tile<CG>(p, tl, 0).n_blk * TILE_N;
+      const int nb_ = decode_tile<CG>(p, tl, 0).n_blk;
+      const int n0_ = nb_ * TILE_N;
+      const int poff_ = (!LORA && p.phases4) ? (nb_ / p.tiles_per_phase) * p.N_out : 0;   // the four phases share the bias
 #pragma unroll
       for (int ci = 0; ci < MAXC; ++ci) {
         const int col = n0_ + (((slot + itn) & 3) + 4 * ci) * 32 + lane;
         const bool ok = (((slot + itn) & 3) + 4 * ci) < NCH && col < p.N;
-        pre_bias[ci] = (ok && p.bias != nullptr) ? __ldg(p.bias + col) : 0.f;
+        pre_bias[ci] = (ok && p.bias != nullptr) ? __ldg(p.bias + col - poff_) : 0.f;
       }
     };
     if (!SK && unit < total_tiles) prefetch_tables(unit, 0);
@@ -626,6 +634,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       const bool row_ok = (x < p.Wo) && (y < p.Ho) && (b < p.B);
       const long long orow = (static_cast<long long>(b) * p.Ho + y) * p.Wo + x;
       const int n0 = n_blk * TILE_N;
+      const int ph = (!LORA && p.phases4) ? n_blk / p.tiles_per_phase : 0;
+      const int ph_col0 = ph * p.N_out;                                   // first stacked column of this tile's phase
+      const CUtensorMap* tm_out_f = ph == 0 ? &p.tmOutF : &p.tmOutP[ph - 1];
+      const CUtensorMap* tm_out_b = ph == 0 ? &p.tmOutB : &p.tmOutP[ph - 1];
       const int chunk0 = (slot + it) & 3;
       const int cx = tx * p.BW + bx0, cy = ty * p.BH + by0, cb = tb * p.BB + bb0;   // this warp's 32-row box
 
@@ -814,7 +826,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; j += 2) geglu2(acc[j], acc[j + 1], 1.0f, 1.0f, acc[j], acc[j + 1]);
         }
-        int nc = 32, ocol = col;
+        int nc = 32, ocol = col - ph_col0;
         if (geglu) {  // chunk = [a(16) | g(16)] -> 16 outputs at column col/2
 #pragma unroll
           for (int j = 0; j < 16; j += 2) geglu2(acc[j], acc[j + 1], acc[j], acc[j + 1], acc[16 + j], acc[17 + j]);
@@ -883,7 +895,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
             }
             const long long rb_local = static_cast<long long>(m_blk) * 4 + quarter;   // (padding row blocks of a ragged batch tile write nothing)
             if (p.stats != nullptr && rb_local < p.n_rowblocks && ocol + lane < p.N_out)
-              p.stats[(p.stats_rowblock0 + rb_local) * p.N_out + ocol + lane] = make_float2(cs, cs2);
+              p.stats[(p.stats_rowblock0 + ph * p.n_rowblocks + rb_local) * p.N_out + ocol + lane] = make_float2(cs, cs2);
             if (p.isums != nullptr) {
               // column sums -> granule sums: segmented warp reduction (lanes of one granule are contiguous; fixed tree, so
               // deterministic), then ONE pair of fire-and-forget integer reductions (RED.ADD.64) per granule segment
@@ -908,7 +920,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           __syncwarp();
           IDB_TICK(6);   // proxy fence
           if (lane == 0) {
-            if (!(dbg & 0x80)) tma_store_4d(&p.tmOutF, sbuf, ocol, cx, cy, cb);
+            if (!(dbg & 0x80)) tma_store_4d(tm_out_f, sbuf, ocol, cx, cy, cb);
             tma_store_commit();
             if (both) tma_store_wait_read();   // the bf16 copy is staged in the same buffer next
           }
@@ -929,7 +941,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
           __syncwarp();
           IDB_TICK(6);   // proxy fence
           if (lane == 0) {
-            if (!(dbg & 0x80)) tma_store_4d(&p.tmOutB, sbuf, ocol, cx, cy, cb);
+            if (!(dbg & 0x80)) tma_store_4d(tm_out_b, sbuf, ocol, cx, cy, cb);
             tma_store_commit();
           }
         }
@@ -1259,6 +1271,10 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   if (phased && ((a->out_phase_x | a->out_phase_y) & ~1)) return fail(IDB_E_BADARG, "idb_gemm_conv: output phase must be 0 or 1");
   if (phased && (a->residual || (a->out_f32 && a->out_bf16) || a->k_splits > 1))
     return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: phased output with residual / both outputs / split-K");
+  const bool phases4 = (a->flags & IDB_EPI_PHASES4) != 0;
+  if (phases4 && (!phased || a->a0_mode != IDB_A_2X2 || a->n % 4 || (a->n / 4) % 32 || a->a1 || a->lora_down || a->rowvec || a->prelu ||
+                  (a->flags & (IDB_EPI_GEGLU | IDB_EPI_GELU))))
+    return fail(IDB_E_BADARG, "idb_gemm_conv: IDB_EPI_PHASES4 needs IDB_A_2X2, out_scale = 2, n = 4 * N_out and a plain bias epilogue");
   const bool stride2 = a->a0_mode == IDB_A_3X3_S2 || a->a0_mode == IDB_A_3X3_S2_ASYM;
   if (stride2 && ((a->height | a->width) & 1))
     return fail(IDB_E_BADARG, "idb_gemm_conv: stride-2 conv needs even H and W");
@@ -1292,7 +1308,8 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   p.B = B;
   p.M = static_cast<long long>(B) * p.Ho * p.Wo;
   p.N = a->n;
-  p.N_out = geglu ? a->n / 2 : a->n;
+  p.N_out = geglu ? a->n / 2 : (phases4 ? a->n / 4 : a->n);
+  p.phases4 = phases4 ? 1 : 0;
   const long long k_total = static_cast<long long>(p.nkb0 + p.nkb1) * 64;
 
   // tile rectangle: 128 output pixels = BW x BH x BB
@@ -1330,7 +1347,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     const int cands[3] = {256, 160, 128};
     for (int ci = 0; ci < 3; ++ci) {
       const int bn = cands[ci];
-      if (a->n % bn) continue;
+      if (a->n % bn || (phases4 && p.N_out % bn)) continue;   // (a tile never straddles two phases)
       const long long tiles = static_cast<long long>(m_units) * (a->n / bn);
       const double bytes_per_clk = (128.0 + bn / static_cast<double>(cg)) * 128.0 / (128.0 * bn / 4096.0);
       double eff = 8000.0 / (148.0 * bytes_per_clk);
@@ -1339,12 +1356,13 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
       if (best < 0 || cost < best) best = cost, block_n = bn;
     }
     if (block_n == 0) block_n = (a->n > 160) ? 256 : (a->n > 128 ? 160 : 128);
+    if (phases4 && p.N_out % block_n) return fail(IDB_E_UNSUPPORTED, "idb_gemm_conv: IDB_EPI_PHASES4 needs N_out % 128 == 0 or N_out % 160 == 0");
     static const int force_bn = env_int("IDB_GEMM_BN", 0);   // profiling only
     if ((force_bn == 128 || force_bn == 160 || force_bn == 256) && a->n % force_bn == 0) block_n = force_bn;
     // dual-N (2 x 160 columns per tile, two accumulators sharing every A tile): fewer operand bytes per MAC for the
     // big-K layers, as long as the halved tile count still fills the machine
     static const int force_dual = env_int("IDB_GEMM_DUAL", -1);   // profiling only: 0 = never, 1 = whenever legal
-    const bool dual_ok = cg == 2 && !geglu && !(a->flags & IDB_EPI_GELU) && a->n % 320 == 0 && force_bn == 0;
+    const bool dual_ok = cg == 2 && !geglu && !(a->flags & IDB_EPI_GELU) && a->n % 320 == 0 && (!phases4 || p.N_out % 320 == 0) && force_bn == 0;
     if (dual_ok && force_dual != 0) {
       const long long tiles = static_cast<long long>(m_units) * (a->n / 320);
       const double cost = static_cast<double>((tiles + units - 1) / units) * (320 + 24) * (128.0 + 160.0) / 320.0;
@@ -1398,6 +1416,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     }
   }
   p.n_tiles_n = (a->n + block_n * (dual ? 2 : 1) - 1) / (block_n * (dual ? 2 : 1));
+  p.tiles_per_phase = phases4 ? p.N_out / (block_n * (dual ? 2 : 1)) : p.n_tiles_n;
 
   int ksp = a->k_splits;
   if (sk) ksp = 1;
@@ -1442,7 +1461,7 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
   p.out_bf16 = static_cast<__nv_bfloat16*>(a->out_bf16);
   p.workspace = a->workspace;
   p.stats = reinterpret_cast<float2*>(a->stats_partials);
-  p.stats_rowblock0 = phased ? static_cast<long long>(2 * a->out_phase_y + a->out_phase_x) * ((p.M + 31) / 32) : 0;
+  p.stats_rowblock0 = (phased && !phases4) ? static_cast<long long>(2 * a->out_phase_y + a->out_phase_x) * ((p.M + 31) / 32) : 0;
   p.n_rowblocks = (p.M + 31) / 32;
   int stats_hw = 0, n_img = 0;
   if (a->stats_image_sums) {
@@ -1523,7 +1542,19 @@ extern "C" int idb_gemm_conv(const idb_gemm_conv_args* a, void* stream_) {
     // pixel / row strides and a shifted base
     const uint64_t sx = phased ? 2 : 1;
     const uint64_t row_elems = sx * uint64_t(p.Wo) * No;                    // elements per output row of the target tensor
-    const uint64_t base_off = phased ? (uint64_t(a->out_phase_y) * row_elems + uint64_t(a->out_phase_x) * No) : 0;
+    const uint64_t base_off = (phased && !phases4) ? (uint64_t(a->out_phase_y) * row_elems + uint64_t(a->out_phase_x) * No) : 0;
+    if (phases4) {   // phases 1-3 (phase = 2 py + px): the same box and strides from a shifted base
+      for (int ph = 1; ph < 4; ++ph) {
+        const uint64_t off = uint64_t(ph >> 1) * row_elems + uint64_t(ph & 1) * No;
+        if (a->out_f32) {
+          uint64_t strides[3] = {sx * No * 4, sx * row_elems * 4, sx * uint64_t(p.Ho) * row_elems * 4};
+          if (int rc = make_tmap(&p.tmOutP[ph - 1], a->out_f32 + off, 4, 128, 4, dims, strides, box)) return rc;
+        } else {
+          uint64_t strides[3] = {sx * No * 2, sx * row_elems * 2, sx * uint64_t(p.Ho) * row_elems * 2};
+          if (int rc = make_tmap(&p.tmOutP[ph - 1], static_cast<const char*>(a->out_bf16) + off * 2, 2, 0, 4, dims, strides, box)) return rc;
+        }
+      }
+    }
     static const int ws_tma_on = env_int("IDB_GEMM_WS_TMA", 1);
     p.ws_tma = 0;
     if (p.k_splits > 1 && ws_tma_on && !geglu && p.N_out == p.N && B % bb32 == 0) {

@@ -7,12 +7,13 @@ from __future__ import annotations
 
 import ctypes as C
 import ctypes as C_
+import os
 from typing import Optional
 
 import torch
 
 from . import _lib
-from ._lib import A_1X1, A_2X2, A_3X3, A_3X3_S2, A_3X3_S2_ASYM, EPI_F16, EPI_GEGLU, EPI_GELU  # noqa: F401  (re-exported)
+from ._lib import A_1X1, A_2X2, A_3X3, A_3X3_S2, A_3X3_S2_ASYM, EPI_F16, EPI_GEGLU, EPI_GELU, EPI_PHASES4  # noqa: F401  (re-exported)
 
 bf16, f16, f32 = torch.bfloat16, torch.float16, torch.float32
 
@@ -34,7 +35,8 @@ def _chk(t: Optional[torch.Tensor], dtype, name: str, allow_none: bool = False):
         raise ValueError(f"{name} must be contiguous")
 
 
-_IMAGE_SUMS_ON = __import__("os").environ.get("IDB_IMAGE_SUMS", "1") != "0"   # 0: row-block sums + finalize kernel (A/B profiling)
+_IMAGE_SUMS_ON = os.environ.get("IDB_IMAGE_SUMS", "1") != "0"   # 0: row-block sums + finalize kernel (A/B profiling)
+PHASES4_ON = os.environ.get("IDB_PHASES4", "1") != "0"   # Upsample2D: the four phase GEMMs as one launch (0: four launches)
 IMAGE_SUMS_MAX_ROWS = 16384     # rows per image up to which the fixed-point per-image sums are used (range: see idb.h)
 
 
@@ -73,7 +75,7 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
               workspace: Optional[torch.Tensor] = None, stats: Optional[torch.Tensor] = None, want_stats: bool = False,
               prelu: Optional[torch.Tensor] = None, half: bool = False, gelu: bool = False,
               tap_off=(0, 0), out_phase=None, sums: Optional[torch.Tensor] = None, stats_hw: int = 0,
-              sums_pool: Optional[SumsPool] = None, stats_gran: int = 1):
+              sums_pool: Optional[SumsPool] = None, stats_gran: int = 1, phases4: bool = False):
     """a0: bf16 [B,H,W,C0] (or [M,K] for a Linear); w: bf16 [N, Ktot].  Returns (out_f32, out_bf16).
     half=True: the 16-bit tensors (a0, a1, w, out_bf16) are IEEE fp16 instead of bf16 (IDB_EPI_F16).
 
@@ -101,7 +103,11 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
             raise ValueError("a1 must have the output geometry")
     if w.shape[1] != taps * C0 + c1:
         raise ValueError(f"w has K={w.shape[1]}, expected {taps * C0 + c1}")
-    n_out = N // 2 if geglu else N
+    # phases4 (A_2X2): w holds the four phase matrices of an Upsample2D stacked on N; one call writes all four output parity
+    # classes of out_f32 [B, 2H, 2W, N / 4] (IDB_EPI_PHASES4); `stats` is then [4, M / 32, N / 4, 2], `sums` as usual
+    if phases4 and (mode != A_2X2 or out_phase is not None or N % 4 or (out_f32 is None and out_bf16 is None)):
+        raise ValueError("phases4 needs mode A_2X2, no out_phase, N = 4 * N_out and an explicit output tensor")
+    n_out = N // 2 if geglu else (N // 4 if phases4 else N)
     for t, nm in ((bias, "bias"), (residual, "residual"), (prelu, "prelu")):
         _chk(t, f32, nm, allow_none=True)
     if prelu is not None and prelu.numel() != N:
@@ -143,12 +149,13 @@ def gemm_conv(a0: torch.Tensor, w: torch.Tensor, *, mode: int = A_1X1, a1: Optio
         w=w.data_ptr(), n=N, bias=_lib.ptr(bias), rowvec=_lib.ptr(rowvec), rowvec_ld=rowvec_ld, residual=_lib.ptr(residual),
         lora_down=_lib.ptr(lora_down), lora_up=_lib.ptr(lora_up),
         lora_rank_pad=0 if lora_up is None else 16, lora_seg_n=lora_seg_n,
-        flags=(EPI_GEGLU if geglu else 0) | (EPI_F16 if half else 0) | (EPI_GELU if gelu else 0), out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
+        flags=(EPI_GEGLU if geglu else 0) | (EPI_F16 if half else 0) | (EPI_GELU if gelu else 0) | (EPI_PHASES4 if phases4 else 0),
+        out_f32=_lib.ptr(out_f32), out_bf16=_lib.ptr(out_bf16),
         k_splits=k_splits, workspace=_lib.ptr(workspace),
         workspace_bytes=0 if workspace is None else workspace.numel() * 4, stats_partials=_lib.ptr(stats),
         stats_image_sums=_lib.ptr(sums), stats_hw=stats_hw, stats_gran=stats_gran,
         prelu=_lib.ptr(prelu), tap_off_x=tap_off[1], tap_off_y=tap_off[0],
-        out_scale=2 if out_phase is not None else 0, out_phase_y=0 if out_phase is None else out_phase[0],
+        out_scale=2 if (out_phase is not None or phases4) else 0, out_phase_y=0 if out_phase is None else out_phase[0],
         out_phase_x=0 if out_phase is None else out_phase[1])
     _lib.call("idb_gemm_conv", C.byref(args), _lib.stream_ptr(),
               desc=None if _lib.trace is None else dict(M=M, N=N, K=taps * C0 + c1, mode=mode, lora=lora_down is not None,

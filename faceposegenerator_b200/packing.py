@@ -25,12 +25,13 @@ def pack_conv_weight(w: torch.Tensor, shortcut: Optional[torch.Tensor] = None, d
     return p.to(device=device, dtype=bf16).contiguous()
 
 
-def pack_upsample_phase_weights(w: torch.Tensor, device=None):
+def pack_upsample_phase_weights(w: torch.Tensor, device=None, stacked: bool = False):
     """Upsample2D = nearest-2x + conv3x3(pad 1).  Output pixel (2i+a, 2j+c) only sees the 2x2 low-resolution
     neighbourhood rows {i+a-1, i+a}, cols {j+c-1, j+c}; the 3x3 taps that land on the same input pixel are summed in
     fp32: a = 0: rows (w0 | w1+w2), a = 1: rows (w0+w1 | w2); same for columns.
     Returns w_ph[a][c]: bf16 [Cout, 4*Cin] (tap = 2u + v major, channel minor) for idb_gemm_conv(IDB_A_2X2) with
-    tap offsets (a - 1, c - 1)."""
+    tap offsets (a - 1, c - 1); `stacked=True`: (w_all, w_ph) where w_all is ONE bf16 [4*Cout, 4*Cin] tensor, phase 2a + c
+    major (the operand of IDB_EPI_PHASES4), and w_ph[a][c] are row-slice views of it."""
     w = w.float()                                        # [Cout, Cin, 3, 3]
     rows = ((w[:, :, 0:1], w[:, :, 1:2] + w[:, :, 2:3]), (w[:, :, 0:1] + w[:, :, 1:2], w[:, :, 2:3]))
     out = []
@@ -39,7 +40,11 @@ def pack_upsample_phase_weights(w: torch.Tensor, device=None):
         cols = ((r[..., 0:1], r[..., 1:2] + r[..., 2:3]), (r[..., 0:1] + r[..., 1:2], r[..., 2:3]))
         out.append([torch.cat(cols[c], dim=3).permute(0, 2, 3, 1).reshape(w.shape[0], -1)
                     .to(device=device, dtype=bf16).contiguous() for c in range(2)])
-    return out
+    if not stacked:
+        return out
+    cout = w.shape[0]
+    w_all = torch.cat([out[a][c] for a in range(2) for c in range(2)], dim=0).contiguous()
+    return w_all, [[w_all[(2 * a + c) * cout:(2 * a + c + 1) * cout] for c in range(2)] for a in range(2)]
 
 
 def pack_edge_conv_weight(w: torch.Tensor, device=None) -> torch.Tensor:

@@ -155,7 +155,7 @@ class UNet2DConditionModel:
             if i < n - 1:
                 q = f"up_blocks.{i}.upsamplers.0.conv"
                 blk.up = (pack_conv_weight(sd[q + ".weight"], device=self.device), self._dev(sd[q + ".bias"]),
-                          pack_upsample_phase_weights(sd[q + ".weight"], device=self.device))
+                          *reversed(pack_upsample_phase_weights(sd[q + ".weight"], device=self.device, stacked=True)))   # [2]: per-phase views, [3]: stacked
             self.up.append(blk)
         self.t_w_all = self._dev(torch.cat(temb_rows, 0))
         self.t_b_all = self._dev(torch.cat(temb_bias, 0))
@@ -452,10 +452,14 @@ class UNet2DConditionModel:
                     o_st = torch.empty((4, B * Hl * Wl // 32, Cu, 2), dtype=f32, device=self.device)
                     # per-image channel sums accumulated by the four phase calls (else: phased row-block sums)
                     o_sums = self._sums.take(B, Cu // self.stats_gran) if ops.image_sums_supported(B, Hl * Wl, Cu, phased=True) else None
-                    for a in range(2):
-                        for c in range(2):
-                            self._gemm(xb, blk.up[2][a][c], mode=ops.A_2X2, bias=blk.up[1], out_f32=o, stats=o_st,
-                                       sums=o_sums, tap_off=(a - 1, c - 1), out_phase=(a, c))
+                    if ops.PHASES4_ON and (Cu % 160 == 0 or Cu % 128 == 0):
+                        # all four parity classes in ONE launch (phase weights stacked on N: 4x the tiles, one fixed cost)
+                        self._gemm(xb, blk.up[3], mode=ops.A_2X2, bias=blk.up[1], out_f32=o, stats=o_st, sums=o_sums, phases4=True)
+                    else:
+                        for a in range(2):
+                            for c in range(2):
+                                self._gemm(xb, blk.up[2][a][c], mode=ops.A_2X2, bias=blk.up[1], out_f32=o, stats=o_st,
+                                           sums=o_sums, tap_off=(a - 1, c - 1), out_phase=(a, c))
                     h = (o, o_sums, 0) if o_sums is not None else (o, o_st, 4)
                 else:
                     hu = ops.upsample2x(ht)

@@ -80,8 +80,13 @@ enum { IDB_A_1X1 = 0, IDB_A_3X3 = 1, IDB_A_3X3_S2 = 2,
 enum {
   IDB_EPI_GEGLU = 1, /* W rows interleaved in 16-blocks [a(16) | g(16)]; out[:, j] = a_j * gelu_erf(g_j); N_out = N/2 */
   IDB_EPI_GELU = 4,  /* out = gelu_erf(acc + bias) (CLIP text MLP fc1); not combined with GEGLU */
-  IDB_EPI_F16 = 2    /* the 16-bit tensors of this call (a0, a1, w, out_bf16) are IEEE fp16 instead of bf16 (the ArcFace IResNet
+  IDB_EPI_F16 = 2,   /* the 16-bit tensors of this call (a0, a1, w, out_bf16) are IEEE fp16 instead of bf16 (the ArcFace IResNet
                         runs under fp16 autocast in the reference, iresnet.py:149); not combined with LoRA */
+  IDB_EPI_PHASES4 = 8 /* IDB_A_2X2 with out_scale = 2 only: ALL FOUR output parity classes of an Upsample2D in one call.  W holds
+                        the four phase weight matrices stacked on N ([4 * N_out, 4 * C0], phase = 2 * py + px major), n = 4 * N_out;
+                        the tile of phase (py, px) reads its taps at offsets (py - 1, px - 1) and writes output pixels
+                        (2y + py, 2x + px); tap_off_* / out_phase_* are ignored; bias [N_out] is shared by the phases;
+                        stats_partials is filled for all four phases, stats_image_sums accumulates over them */
 };
 
 typedef struct {

@@ -298,6 +298,14 @@ def test_upsample_conv_four_phase(ops, cuda_dev, B, H, W, C):
     assert rel(fixed_sums(sums)[0], flat.sum(1)) < 1e-6 and rel(fixed_sums(sums)[1], (flat ** 2).sum(1)) < 1e-6
     y_sm, _ = ops.groupnorm(out, gamma, beta, groups=32, eps=1e-5, silu=True, x0_stats=sums)
     assert rel(y_sm.float(), y_pl.float()) < 2e-3
+    # all four phases in ONE call (IDB_EPI_PHASES4: phase weights stacked on N): the same bits, statistics and sums
+    w_all, views = pack_upsample_phase_weights(w, device=cuda_dev, stacked=True)
+    assert tuple(w_all.shape) == (4 * C, 4 * C) and all(torch.equal(views[a][c], wph[a][c]) for a in range(2) for c in range(2))
+    out3 = torch.full_like(out, float("nan"))
+    st3 = torch.full_like(st, float("nan"))
+    sums3 = torch.zeros_like(sums)
+    ops.gemm_conv(xb, w_all, mode=ops.A_2X2, bias=bias, out_f32=out3, stats=st3, sums=sums3, phases4=True)
+    assert torch.equal(out3, out) and torch.equal(st3, st) and torch.equal(sums3, sums)
 
 
 @pytest.mark.parametrize("B,H,W,Cin,N,gran", [(8, 64, 64, 64, 320, 10), (8, 64, 64, 64, 320, 1),
