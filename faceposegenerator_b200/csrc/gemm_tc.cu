@@ -718,7 +718,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_tc_kernel(const __grid_co
       if (SK && n_contrib > 0) {   // the other K segments of this tile: every epilogue warp of every contributor has stored and fenced
         if (lane == 0) {
           const unsigned int need = static_cast<unsigned int>(n_contrib) * NUM_EPI_WARPS;
-          while (ld_acquire_gpu(sk_flag) < need) __nanosleep(64);
+          unsigned int polls = 0;
+          while (ld_acquire_gpu(sk_flag) < need) {
+            __nanosleep(64);
+            // the contributors finished their segments long before this point; seconds of waiting mean the grid is not
+            // co-resident (two stream-K kernels of different streams sharing the device, see launch_gemm_e): fail loudly
+            // (a launch error the host sees) instead of hanging the GPU
+            if (++polls > (1u << 22)) __trap();   // (~0.8 us per poll: a few seconds)
+          }
         }
         __syncwarp();
       }
