@@ -52,7 +52,7 @@ MODEL = "stabilityai/stable-diffusion-2-1-base"
 def _step_traffic():
     """DRAM bytes of one UNet step from the newest committed ncu capture (profiles/r*_step_traffic.json), or None."""
     import glob
-    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_traffic.json")), reverse=True):
+    for fn in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_step_traffic*.json")), reverse=True):
         try:
             with open(fn) as f:
                 return float(json.load(f)["traffic_bytes"])
