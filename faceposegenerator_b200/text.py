@@ -131,10 +131,40 @@ class CLIPTextEncoder:
             x, _ = ops.gemm_conv(y, L["w_fc2"], bias=L["b_fc2"], residual=x, want_f32=True)
         return ops.layernorm(x, *self.ln_f, eps=cfg["eps"]).view(n, S, h)
 
+    def _forward_ids_graphed(self, ids: torch.Tensor) -> torch.Tensor:
+        """`forward_ids` as one CUDA-graph launch per batch size (164 kernels of a few microseconds each: eager, the host
+        launch rate is the bottleneck).  IDB_CUDA_GRAPH=0: eager."""
+        import os
+        if os.environ.get("IDB_CUDA_GRAPH", "1") == "0" or torch.cuda.is_current_stream_capturing():
+            return self.forward_ids(ids)
+        ids = ids.to(self.device)
+        key = tuple(ids.shape)
+        graphs = self.__dict__.setdefault("_graphs", {})
+        st = graphs.get(key)
+        if st is None:
+            if len(graphs) >= 8:
+                graphs.pop(next(iter(graphs)))
+            from . import _lib
+            buf = ids.clone()
+            with torch.cuda.device(self.device):
+                self.forward_ids(buf)                       # warm-up outside capture (lazy kernel attributes)
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count
+                with torch.cuda.graph(g):
+                    out = self.forward_ids(buf)
+            st = graphs[key] = (g, buf, out, _lib.launch_count - n0)
+        g, buf, out, launches = st
+        buf.copy_(ids)
+        g.replay()
+        from . import pipeline as _pl
+        _pl.graph_launches += launches                      # (replays do not pass through the library's launch counter)
+        return out.clone()
+
     def encode(self, prompts: List[str]) -> torch.Tensor:
         missing = [p for p in dict.fromkeys(prompts) if p not in self._cache]
         if missing:
-            out = self.forward_ids(self.tokenizer(missing))
+            out = self._forward_ids_graphed(self.tokenizer(missing))
             for p, e in zip(missing, out):
                 self._cache[p] = e
         return torch.stack([self._cache[p] for p in prompts])
