@@ -310,6 +310,14 @@ def test_upsample_four_phase_weights_are_the_upsampled_conv():
             y = F.conv2d(xp[:, :, a:a + H + 1, c:c + W + 1], k)
             out[:, :, a::2, c::2] = y
     assert torch.equal(out, ref)
+    # the one-launch form (IDB_EPI_PHASES4) takes the four matrices stacked on N, phase 2a + c major; the per-phase operands
+    # are row-slice views of that tensor (no second copy of the weights)
+    w_all, views = pack_upsample_phase_weights(w, stacked=True)
+    assert tuple(w_all.shape) == (4 * cout, 4 * cin)
+    for a in range(2):
+        for c in range(2):
+            assert torch.equal(views[a][c], wph[a][c]) and torch.equal(w_all[(2 * a + c) * cout:(2 * a + c + 1) * cout], wph[a][c])
+            assert views[a][c].data_ptr() == w_all.data_ptr() + (2 * a + c) * cout * 4 * cin * w_all.element_size()
 
 
 def test_iresnet_batchnorm_folding_is_exact_in_eval_mode():
@@ -463,12 +471,19 @@ def test_c_abi_library_exports_every_declared_symbol():
         prog += f'printf("{cname} %zu\\n", sizeof({cname}));\n'
         for fname, _ in cls._fields_:
             prog += f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));\n'
+    enums = {"IDB_EPI_GEGLU": _lib.EPI_GEGLU, "IDB_EPI_F16": _lib.EPI_F16, "IDB_EPI_GELU": _lib.EPI_GELU, "IDB_EPI_PHASES4": _lib.EPI_PHASES4,
+             "IDB_A_1X1": _lib.A_1X1, "IDB_A_3X3": _lib.A_3X3, "IDB_A_3X3_S2": _lib.A_3X3_S2, "IDB_A_3X3_S2_ASYM": _lib.A_3X3_S2_ASYM,
+             "IDB_A_2X2": _lib.A_2X2}
+    for ename in enums:
+        prog += f'printf("{ename} %d\\n", (int){ename});\n'
     prog += "return 0;}\n"
     with tempfile.TemporaryDirectory() as td:
         src, exe = os.path.join(td, "l.c"), os.path.join(td, "l")
         open(src, "w").write(prog)
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
         got = dict(line.split() for line in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines())
+    for ename, val in enums.items():
+        assert int(got[ename]) == val, ename
     for cname, cls in structs.items():
         assert int(got[cname]) == ctypes.sizeof(cls), cname
         for fname, _ in cls._fields_:
