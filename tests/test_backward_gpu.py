@@ -255,3 +255,27 @@ def test_lora_trainer_reduces_the_denoising_loss(cuda_dev):
     moved = max(float((tr.params[k][1].detach().cpu() - lora[k][1]).abs().max()) for k in lora)
     assert moved > 1e-4
     assert torch.equal(unet.transformers[0].w_qkv, base)
+
+
+def test_lora_trainer_graph_replay_equals_eager_steps(cuda_dev):
+    """The trainer captures add_noise -> forward with tape -> loss -> backward into one CUDA graph per batch geometry and
+    re-installs the adapters in place after every AdamW step, so the graph is replayed with NEW timesteps / data each
+    step.  Its losses and gradient norms must follow the eager trainer's (same start, same batches; the only
+    non-bit-reproducible piece is the fp32 atomic accumulation of dQ in the attention backward)."""
+    from faceposegenerator_b200 import DDPMScheduler
+    from faceposegenerator_b200.lora_backward import LoRATrainer
+    from faceposegenerator_b200.unet import UNet2DConditionModel
+    from faceposegenerator_b200.weights import random_lora, random_state_dict, unet_manifest
+    sched = DDPMScheduler.from_pretrained("stabilityai/stable-diffusion-2-1-base", subfolder="scheduler")
+    g = torch.Generator().manual_seed(9)
+    batches = [(torch.randn(2, 4, 64, 64, generator=g), torch.randn(2, 4, 64, 64, generator=g),
+                torch.randint(0, 1000, (2,), generator=g), torch.randn(2, 77, 1024, generator=g)) for _ in range(4)]
+    runs = {}
+    for graph in (True, False):
+        unet = UNet2DConditionModel(random_state_dict(unet_manifest(), 0), device=cuda_dev)
+        tr = LoRATrainer(unet, random_lora(seed=1), sched, lr=1e-3, use_cuda_graph=graph)
+        runs[graph] = [tr.step(x0, n, t, c.to(cuda_dev)) for (x0, n, t, c) in batches]
+        if graph:
+            assert len(tr._graphs) == 1, "one capture for the four steps"
+    for (lg, ng), (le, ne) in zip(runs[True], runs[False]):
+        assert abs(lg - le) <= 2e-3 * abs(le) and abs(ng - ne) <= 2e-2 * abs(ne), (runs[True], runs[False])
