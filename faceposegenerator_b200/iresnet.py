@@ -169,26 +169,37 @@ def identity_noise_level_weight(timestep, num_train_timesteps: int = 1000, times
     return (1.0 - timestep / num_train_timesteps) ** 2 if timestep_loss_weighting else 1
 
 
+def identity_step_tables(scheduler, timesteps, device):
+    """Host part of `training_forward_identity` for per-sample timesteps: (t fp32 [B], x0 coefficient rows fp32 [B, 5]) on
+    `device`.  Computing them once outside lets the rest of the chain be captured in a CUDA graph (copy new tables into
+    the same tensors before each replay)."""
+    ts = [int(v) for v in (timesteps.tolist() if torch.is_tensor(timesteps) else (timesteps if hasattr(timesteps, "__len__") else [timesteps]))]
+    rows = []
+    for tv in ts:
+        c = scheduler.coef_row(None, tv, "cpu").clone()
+        c[4] = 0.0   # pred_original_sample does not depend on the variance noise
+        rows.append(c)
+    return torch.tensor(ts, dtype=f32).to(device), torch.stack(rows).to(device)
+
+
 def training_forward_identity(unet, vae, scheduler, arcface: IResNet, noisy_latents: torch.Tensor, timesteps,
-                              encoder_hidden_states: torch.Tensor, bbox: torch.Tensor, context=None):
+                              encoder_hidden_states: torch.Tensor, bbox: torch.Tensor, context=None, tables=None):
     """The forward half of the reference's identity-loss branch (config 5; train_ID-Booth.py:1040-1046, :1081,
     :433-455, :1093): UNet(noisy, t, ctx) -> `scheduler.step(...).pred_original_sample` (the x0 estimate) -> VAE decode
     -> (x/2 + 0.5).clamp -> crop bbox -> bilinear 112x112 -> normalise -> IResNet embedding.
     Returns (model_pred [B,4,h,w], x0 latents [B,4,h,w], embeddings [B,512]).  MTCNN (third party, not in the tree)
     is replaced by the caller-supplied bbox."""
     B = noisy_latents.shape[0]
-    t = torch.as_tensor(timesteps, device=unet.device).reshape(-1).float()
-    if t.numel() == 1:
-        t = t.expand(B)
+    # `tables` = identity_step_tables(...) computed by the caller: no host work inside (the chain is then graph-capturable)
+    t, coefs = tables if tables is not None else identity_step_tables(scheduler, timesteps, unet.device)
+    if t.numel() == 1 and B > 1:
+        t, coefs = t.expand(B).contiguous(), coefs.expand(B, 5).contiguous()
     eps = unet.forward(noisy_latents, t, encoder_hidden_states=encoder_hidden_states, context=context, return_dict=False)[0]
     x0 = torch.empty_like(noisy_latents, dtype=f32)
     x_prev = torch.empty_like(x0)
     vpred = scheduler.config.prediction_type == "v_prediction"
     for i in range(B):   # per-sample timesteps (train_ID-Booth.py:1012-1018): one coefficient row each
-        coef = scheduler.coef_row(None, int(t[i].item()), unet.device)
-        coef = coef.clone()
-        coef[4] = 0.0   # pred_original_sample does not depend on the variance noise
-        ops.cfg_ddpm_step(eps[i:i + 1].float().contiguous(), noisy_latents[i:i + 1].float().contiguous(), None, coef,
+        ops.cfg_ddpm_step(eps[i:i + 1].float().contiguous(), noisy_latents[i:i + 1].float().contiguous(), None, coefs[i],
                           guidance_scale=1.0, use_cfg=False, v_prediction=vpred, x_prev=x_prev[i:i + 1], x0_out=x0[i:i + 1])
     img = vae.decode(x0 / vae.config.scaling_factor, output_image=True)[0]          # NHWC fp32 in [0, 1]
     emb = arcface_embedding_from_images(arcface, img, bbox)

@@ -4,7 +4,7 @@ import json, os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from faceposegenerator_b200 import DDPMScheduler
-from faceposegenerator_b200.iresnet import IResNet, arcface_embedding_from_images, training_forward_identity
+from faceposegenerator_b200.iresnet import IResNet, arcface_embedding_from_images, identity_step_tables, training_forward_identity
 from faceposegenerator_b200.unet import UNet2DConditionModel
 from faceposegenerator_b200.vae import AutoencoderKL
 from faceposegenerator_b200.weights import random_iresnet_state_dict, random_lora
@@ -38,4 +38,18 @@ lat = torch.randn(B, 4, 64, 64, device=dev)
 res["vae_decode_ms"] = round(timed(lambda: vae.decode(lat, output_image=True)), 3)
 res["iresnet_gflop_per_image"] = 24.2
 res["iresnet_tflops"] = round(24.2e9 * B / (res["arcface_ms"] * 1e-3) / 1e12, 1)
+# the same chain / backbone as ONE CUDA-graph launch (static shapes; the eager numbers above are bound by the host launch rate)
+def graphed(fn):
+    fn(); torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        fn()
+    return gr.replay
+try:
+    tables = identity_step_tables(sched, ts, dev)
+    res["chain_graph_ms"] = round(timed(graphed(lambda: training_forward_identity(unet, vae, sched, arc, noisy, None, ctx, bbox, context=context, tables=tables))), 3)
+    res["arcface_graph_ms"] = round(timed(graphed(lambda: arcface_embedding_from_images(arc, img, bbox))), 3)
+    res["iresnet_graph_tflops"] = round(24.2e9 * B / (res["arcface_graph_ms"] * 1e-3) / 1e12, 1)
+except Exception as e:   # (a host synchronisation inside the chain would make it uncapturable)
+    res["graph_error"] = f"{type(e).__name__}: {e}"[:200]
 print(json.dumps(res))
